@@ -50,22 +50,29 @@ def _criterion(window, condition, thresh):
 
 def quadtree_labels(img, thresh=0.05, max_size=8, mask=None, high_interest_region=None,
                     transform_func=None, condition="max_larger_than"):
-    """Per-pixel node label, -1 = masked (graph_functions.py:145-259, padding=0).
-
-    Order of labels: the reference pushes base cells in raster order on a LIFO stack and
-    pushes the four children as (x,y) (x+s,y) (x,y+s) (x+s,y+s); the pop order is therefore
-    the reverse.  A depth-first recursion that visits base cells in reverse raster order and
-    children in order (x+s,y+s) (x,y+s) (x+s,y) (x,y) numbers the leaves identically.
-    """
+    """Per-pixel node label, -1 = masked (graph_functions.py:145-259, padding=0)."""
     assert max_size & (max_size - 1) == 0 and max_size > 0
     assert condition in CONDITIONS
     img = np.asarray(img)
     n, m = img.shape
     n_pad = -(n // -max_size) * max_size
     m_pad = -(m // -max_size) * max_size
-    labels = np.full((n_pad, m_pad), -1, dtype=np.int64)
     padded = np.pad(img, ((0, n_pad - n), (0, m_pad - m)), mode="edge")      # :190
     crit = transform_func(padded) if transform_func is not None else padded   # :194
+    return quadtree_labels_on_padded(crit, n, m, thresh, max_size, mask, high_interest_region, condition)
+
+
+def quadtree_labels_on_padded(crit, n, m, thresh, max_size, mask=None, high_interest_region=None,
+                              condition="max_larger_than"):
+    """The traversal of graph_functions.py:196-259 on the padded, transformed criterion image.
+
+    Order of labels: the reference pushes base cells in raster order on a LIFO stack and
+    pushes the four children as (x,y) (x+s,y) (x,y+s) (x+s,y+s); the pop order is therefore
+    the reverse.  A depth-first recursion that visits base cells in reverse raster order and
+    children in order (x+s,y+s) (x,y+s) (x+s,y) (x,y) numbers the leaves identically.
+    """
+    n_pad, m_pad = crit.shape
+    labels = np.full((n_pad, m_pad), -1, dtype=np.int64)
     # the reference clips BOTH axes with shape[1] (= m_pad) (:222-225); numpy slicing then
     # clips rows to the array's own extent
     row_cap = min(m_pad, n_pad)

@@ -1,0 +1,108 @@
+"""ctypes binding of ``libqmp_b200.so`` -- the C-ABI boundary declared in ``include/qmp_b200.h``.
+
+There is no CPU fallback: if the shared library is missing, or a call is made without a CUDA
+device, this module raises.  PyTorch is used only to own device memory and streams; every entry
+point takes raw device pointers, sizes and a ``cudaStream_t``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqmp_b200.so")
+
+_P, _I, _L, _F, _D, _U = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_uint64
+_CODES = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D, "u": _U}
+
+# name -> argument codes (p pointer, i int, l int64, f float, d double, u uint64); all return int
+SIGNATURES = {
+    "qmp_exclusive_scan_i32": "ppippp",
+    "qmp_frame_max_pad": "piiiiiipp",
+    "qmp_quadtree_labels": "pppiiiidppppppppp p".replace(" ", ""),
+    "qmp_mesh_pixels_from_rects": "piippp ipppp p".replace(" ", ""),
+    "qmp_mesh_pixelwise": "pipppppppp p".replace(" ", ""),
+    "qmp_segment_sum": "piiipppipipp",
+    "qmp_gather_by_label": "piiiippifpp",
+    "qmp_adjacency_quadtree": "piippppppplppppp",
+    "qmp_adjacency_pixelwise": "piippppppppp",
+    "qmp_edge_attrs": "ppipppiiifipp",
+    "qmp_add_positional_encoding": "piiiipp",
+    "qmp_csr_from_edge_index": "plippppppppppppp p".replace(" ", ""),
+    "qmp_gather_rows": "pplipp",
+    "qmp_gemm": "ppppiiiiiilllliiiip",
+    "qmp_gemm_tn_acc": "pppiiiiiillliip",
+    "qmp_attn_fwd": "iiipppp iippppp fup".replace(" ", ""),
+    "qmp_attn_bwd_target": "iiipppp iippppp pfup".replace(" ", ""),
+    "qmp_attn_bwd_source": "iiipppppppppp iiiifup".replace(" ", ""),
+    "qmp_edge_norm": "iipppppp ppp".replace(" ", ""),
+    "qmp_spmm": "iippppp iffpipip".replace(" ", ""),
+    "qmp_lstm_gates_fwd": "iipippiiifppppppipp",
+    "qmp_lstm_gates_bwd": "iippppiiifppppipippp",
+    "qmp_head_finish_fwd": "ppiiifuppp",
+    "qmp_head_finish_bwd": "pppppiiifuppp",
+    "qmp_relu_mask": "pplp",
+}
+
+
+class QmpError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise QmpError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(nvcc, sm_100a).  There is no CPU or PyTorch fallback for this path.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.qmp_last_error.restype = ctypes.c_char_p
+        L.qmp_last_error.argtypes = []
+        L.qmp_version.restype = _I
+        L.qmp_quadtree_pyramid_cells.restype = _L
+        L.qmp_quadtree_pyramid_cells.argtypes = [_I, _I, _I]
+        for name, sig in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = _I
+            fn.argtypes = [_CODES[c] for c in sig]
+        _lib = L
+    return _lib
+
+
+def on_device(t):
+    """True when ``t`` lives on a CUDA device (the only place this package computes)."""
+    return bool(t.is_cuda)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        if not on_device(t):
+            raise QmpError("qmp_b200 kernels take CUDA tensors only (no CPU fallback)")
+        return t.data_ptr()
+    return t
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke ``qmp_<name>`` on the current CUDA stream (appended as the last argument)."""
+    L = lib()
+    fn = getattr(L, name)
+    conv = [_ptr(a) if (isinstance(a, torch.Tensor) or a is None) else a for a in args]
+    rc = fn(*conv, stream_ptr())
+    if rc != 0:
+        raise QmpError(f"{name} failed (code {rc}): {L.qmp_last_error().decode(errors='replace')}")
+
+
+def exported_symbols():
+    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells"] + list(SIGNATURES)

@@ -1,0 +1,47 @@
+// Shared helpers for the qmp_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <limits.h>
+#include <float.h>
+
+#define QMP_API extern "C" __attribute__((visibility("default")))
+
+namespace qmp {
+
+void set_error(const char* fmt, ...);
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#define QMP_REQUIRE(cond, ...)                      \
+    do {                                            \
+        if (!(cond)) {                              \
+            qmp::set_error(__VA_ARGS__);            \
+            return -1;                              \
+        }                                           \
+    } while (0)
+
+#define QMP_LAUNCH_CHECK(name)                                                      \
+    do {                                                                            \
+        cudaError_t e__ = cudaGetLastError();                                       \
+        if (e__ != cudaSuccess) {                                                   \
+            qmp::set_error("%s: %s", name, cudaGetErrorString(e__));                \
+            return (int)e__;                                                        \
+        }                                                                           \
+    } while (0)
+
+#define QMP_CUDA(call)                                                              \
+    do {                                                                            \
+        cudaError_t e__ = (call);                                                   \
+        if (e__ != cudaSuccess) {                                                   \
+            qmp::set_error("%s: %s", #call, cudaGetErrorString(e__));               \
+            return (int)e__;                                                        \
+        }                                                                           \
+    } while (0)
+
+// Exclusive scan of n int32 (n <= 4M).  `blocksums` is caller scratch of >= cdiv(n,1024)+1 ints.
+// Writes the grand total to *total (device) when total != nullptr.
+int exclusive_scan_i32(const int* in, int* out, int n, int* total, int* blocksums, cudaStream_t st);
+
+}  // namespace qmp

@@ -1,0 +1,102 @@
+// Error string, version, and the int32 exclusive scan shared by the graph kernels.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace qmp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ---- scan: 1024 items per block (256 threads x 4), then a single block scans the block sums.
+__global__ void __launch_bounds__(256) scan_block_kernel(const int* __restrict__ in, int* __restrict__ out, int n,
+                                                         int* __restrict__ blocksums) {
+    __shared__ int warp_tot[8];
+    const int base = blockIdx.x * 1024 + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (base + k < n) ? in[base + k] : 0;
+    int tsum = v[0] + v[1] + v[2] + v[3];
+    // inclusive warp scan of per-thread sums
+    int incl = tsum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+    int excl = woff + incl - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (base + k < n) out[base + k] = excl;
+        excl += v[k];
+    }
+    if (threadIdx.x == 255) blocksums[blockIdx.x] = woff + incl;
+}
+
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int* __restrict__ blocksums, int nb, int* __restrict__ total) {
+    // each thread owns a contiguous chunk; Hillis-Steele over the 1024 chunk totals
+    __shared__ int part[1024];
+    const int per = (nb + 1023) / 1024;
+    const int lo = threadIdx.x * per;
+    int s = 0;
+    for (int k = 0; k < per; ++k)
+        if (lo + k < nb) s += blocksums[lo + k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        int t = (threadIdx.x >= d) ? part[threadIdx.x - d] : 0;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int run = part[threadIdx.x] - s;  // exclusive prefix of my chunk
+    for (int k = 0; k < per; ++k)
+        if (lo + k < nb) {
+            int t = blocksums[lo + k];
+            blocksums[lo + k] = run;
+            run += t;
+        }
+    if (threadIdx.x == 1023 && total) *total = part[1023];
+}
+
+__global__ void __launch_bounds__(256) scan_add_kernel(int* __restrict__ out, int n, const int* __restrict__ blocksums) {
+    const int base = blockIdx.x * 1024 + threadIdx.x * 4;
+    const int add = blocksums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+int exclusive_scan_i32(const int* in, int* out, int n, int* total, int* blocksums, cudaStream_t st) {
+    if (n <= 0) {
+        if (total) QMP_CUDA(cudaMemsetAsync(total, 0, sizeof(int), st));
+        return 0;
+    }
+    const int nb = cdiv(n, 1024);
+    QMP_REQUIRE(nb <= 4096, "exclusive_scan_i32: n=%d too large", n);
+    scan_block_kernel<<<nb, 256, 0, st>>>(in, out, n, blocksums);
+    scan_sums_kernel<<<1, 1024, 0, st>>>(blocksums, nb, total);
+    if (nb > 1) scan_add_kernel<<<nb, 256, 0, st>>>(out, n, blocksums);
+    QMP_LAUNCH_CHECK("exclusive_scan_i32");
+    return 0;
+}
+
+}  // namespace qmp
+
+QMP_API const char* qmp_last_error(void) { return qmp::g_err; }
+QMP_API int qmp_version(void) { return 100; }
+
+// Exposed for tests: out[i] = sum_{k<i} in[k]; *total = sum.  scratch >= n/1024 + 2 ints.
+QMP_API int qmp_exclusive_scan_i32(const int* in, int* out, int n, int* total, int* scratch, void* stream) {
+    return qmp::exclusive_scan_i32(in, out, n, total, scratch, (cudaStream_t)stream);
+}

@@ -1,0 +1,453 @@
+"""TEST-ONLY emulation of the C ABI on CPU tensors.
+
+Purpose: exercise the HOST logic of ``quadtree_mpnnlstm_b200`` (argument order, strides, saved tensors,
+autograd wiring, driver control flow) and the kernels' FORMULAS (folded attention weights, the LSTM /
+LayerNorm backward, CSR gathers) in the no-GPU container, against the oracle.  Each function below
+restates what the CUDA kernel of the same name computes, on flat memory with the same pointer / leading-
+dimension conventions.  It is installed by monkey-patching in ``tests/test_host_logic.py`` only; the
+product never imports it and has no CPU path.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from oracle import graph_ref as G
+
+
+def flat(t, count=None):
+    """1-D window on the storage behind ``t`` starting at t's first element (pointer semantics)."""
+    if t is None:
+        return None
+    base = t.detach()
+    n = base.untyped_storage().nbytes() // base.element_size() - base.storage_offset()
+    w = torch.as_strided(base, (n,), (1,), base.storage_offset())
+    return w if count is None else w[:count]
+
+
+def win(f, shape, strides, off=0):
+    """Strided window whose offset is RELATIVE to the first element of ``f`` (as_strided's is absolute)."""
+    return torch.as_strided(f, shape, strides, f.storage_offset() + off)
+
+
+def rows(t, n, ld, width):
+    """[n, width] strided window with leading dimension ld starting at t's pointer."""
+    base = t.detach()
+    return torch.as_strided(base, (n, width), (ld, 1), base.storage_offset())
+
+
+# ------------------------------------------------------------------------------------------ graph side
+def qmp_exclusive_scan_i32(inp, out, n, total, scratch):
+    v = flat(inp, n).long()
+    c = torch.cumsum(v, 0)
+    flat(out, n).copy_((c - v).int())
+    if total is not None:
+        flat(total, 1)[0] = int(c[-1]) if n else 0
+
+
+def qmp_add_positional_encoding(x, B, H, W, C, out):
+    xi = flat(x, B * H * W * C).view(B, H, W, C)
+    flat(out, B * H * W * (C + 2)).view(B, H, W, C + 2).copy_(G.add_positional_encoding(xi))
+
+
+def qmp_frame_max_pad(x, T, H, W, C, n_pad, m_pad, crit):
+    xi = flat(x, T * H * W * C).view(T, H, W, C)
+    fr = xi[..., 0].max(0).values.numpy()
+    fr = np.pad(fr, ((0, n_pad - H), (0, m_pad - W)), mode="edge")
+    flat(crit, n_pad * m_pad).copy_(torch.from_numpy(fr).reshape(-1))
+
+
+def qmp_quadtree_labels(crit, mask, hir, n, m, S, cond, thresh, labels, rect, npix, n_nodes, split, cnt, base_off,
+                        top_f, top_b):
+    n_pad, m_pad = -(n // -S) * S, -(m // -S) * S
+    cr = flat(crit, n_pad * m_pad).view(n_pad, m_pad).numpy()
+    mk = flat(mask, n * m).view(n, m).numpy().astype(bool) if mask is not None else None
+    hr = flat(hir, n * m).view(n, m).numpy().astype(bool) if hir is not None else None
+    lab = G.quadtree_labels_on_padded(cr, n, m, thresh, S, mk, hr, G.CONDITIONS[cond])
+    flat(labels, n * m).copy_(torch.from_numpy(lab.reshape(-1)).int())
+    N = int(lab.max()) + 1 if lab.size and lab.max() >= 0 else 0
+    flat(n_nodes, 1)[0] = N
+    rc, npx = flat(rect, 4 * max(N, 1)).view(-1, 4), flat(npix, max(N, 1))
+    for v in range(N):
+        ys, xs = np.nonzero(lab == v)
+        rc[v] = torch.tensor([ys.min(), xs.min(), ys.max() - ys.min() + 1, xs.max() - xs.min() + 1], dtype=torch.int32)
+        npx[v] = float(len(ys))
+
+
+def qmp_mesh_pixels_from_rects(labels, n, m, rect, npix, n_nodes, cap, pix_ptr, pix_idx, tmp, bs):
+    N = int(flat(n_nodes, 1)[0])
+    lab = flat(labels, n * m).long()
+    counts = torch.zeros(cap, dtype=torch.int64)
+    counts[:N] = flat(npix, N).long()
+    ptr = torch.zeros(cap + 1, dtype=torch.int64)
+    ptr[1:] = torch.cumsum(counts, 0)
+    flat(pix_ptr, cap + 1).copy_(ptr.int())
+    order = torch.argsort(torch.where(lab >= 0, lab, torch.full_like(lab, cap + 1)), stable=True)
+    nv = int((lab >= 0).sum())
+    flat(pix_idx, nv).copy_(order[:nv].int())
+
+
+def qmp_mesh_pixelwise(mask, P, labels, pix_ptr, pix_idx, npix, n_nodes, keep, rank, bs):
+    mk = flat(mask, P).bool() if mask is not None else torch.zeros(P, dtype=torch.bool)
+    lab = torch.from_numpy(G.pixelwise_labels(mk.numpy().reshape(1, -1)).reshape(-1))
+    N = int((~mk).sum())
+    flat(labels, P).copy_(lab.int())
+    flat(n_nodes, 1)[0] = N
+    flat(pix_idx, N).copy_(torch.nonzero(~mk).squeeze(1).int())
+    flat(pix_ptr, N + 1).copy_(torch.arange(N + 1).int())
+    flat(npix, N).fill_(1.0)
+
+
+def qmp_segment_sum(img, B, P, C, pix_ptr, pix_idx, npix, n_cap, n_nodes_dev, divide, out):
+    N = int(flat(n_nodes_dev, 1)[0]) if n_nodes_dev is not None else n_cap
+    im = flat(img, B * P * C).view(B, P, C)
+    ptr = flat(pix_ptr, N + 1).long()
+    idx = flat(pix_idx, int(ptr[N])).long()
+    seg = torch.repeat_interleave(torch.arange(N), ptr[1:] - ptr[:-1])
+    res = torch.zeros(B, N, C).index_add(1, seg, im[:, idx])
+    if divide:
+        res = res / flat(npix, N)[None, :, None]
+    flat(out, B * n_cap * C).view(B, n_cap, C)[:, :N] = res
+
+
+def qmp_gather_by_label(data, B, P, C, n_stride, labels, npix, divide, fill, img):
+    lab = flat(labels, P).long()
+    d = flat(data, B * n_stride * C).view(B, n_stride, C)
+    res = d[:, lab.clamp(min=0)]
+    if divide:
+        res = res / flat(npix, n_stride)[lab.clamp(min=0)][None, :, None]
+    res = torch.where((lab >= 0)[None, :, None], res, torch.full_like(res, fill))
+    flat(img, B * P * C).view(B, P, C).copy_(res)
+
+
+def _emit_edges(ei, src64, dst64, src32, dst32, n_edges):
+    E = ei.shape[1]
+    flat(src64, E).copy_(torch.from_numpy(ei[0]))
+    flat(dst64, E).copy_(torch.from_numpy(ei[1]))
+    flat(src32, E).copy_(torch.from_numpy(ei[0]).int())
+    flat(dst32, E).copy_(torch.from_numpy(ei[1]).int())
+    flat(n_edges, 1)[0] = E
+
+
+def qmp_adjacency_quadtree(labels, rows_, cols, src64, dst64, src32, dst32, n_edges, keys, vals, table_cap, emit, count,
+                           offset, bs):
+    lab = flat(labels, rows_ * cols).view(rows_, cols).long().numpy()
+    _emit_edges(G.adjacency(lab), src64, dst64, src32, dst32, n_edges)
+
+
+def qmp_adjacency_pixelwise(labels, rows_, cols, src64, dst64, src32, dst32, n_edges, count, offset, bs):
+    lab = flat(labels, rows_ * cols).view(rows_, cols).long().numpy()
+    _emit_edges(G.adjacency_pixelwise(lab), src64, dst64, src32, dst32, n_edges)
+
+
+def qmp_edge_attrs(src, dst, e_cap, n_edges_dev, pos_ii, pos_jj, pos_stride, img_w, img_h, res, two_cols, out):
+    E = int(flat(n_edges_dev, 1)[0]) if n_edges_dev is not None else e_cap
+    s, d = flat(src, E).long(), flat(dst, E).long()
+    nmax = int(max(s.max(), d.max())) + 1 if E else 0
+    ii = torch.as_strided(pos_ii.detach(), (nmax,), (pos_stride,), pos_ii.storage_offset())
+    jj = torch.as_strided(pos_jj.detach(), (nmax,), (pos_stride,), pos_jj.storage_offset())
+    xx, yy = ii * img_w * res, jj * img_h * res
+    if two_cols:
+        flat(out, 2 * E).view(E, 2).copy_(torch.stack((G.edge_angle(s, d, xx, yy), G.edge_dist(s, d, xx, yy))).T)
+    else:
+        flat(out, E).copy_(G.edge_dist(s, d, xx, yy))
+
+
+def qmp_csr_from_edge_index(ei, E, N, src32, dst32, in_ptr, in_src, in_eid, out_ptr, out_dst, out_kin, bad, tmp, bs,
+                            eid_out, kin_of_edge):
+    e = flat(ei, 2 * E).view(2, E)
+    s, d = e[0], e[1]
+    flat(src32, E).copy_(s.int())
+    flat(dst32, E).copy_(d.int())
+    order_in = torch.argsort(d, stable=True)
+    order_out = torch.argsort(s, stable=True)
+    ptr = lambda key: torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(torch.bincount(key, minlength=N), 0)])
+    flat(in_ptr, N + 1).copy_(ptr(d).int())
+    flat(out_ptr, N + 1).copy_(ptr(s).int())
+    flat(in_eid, E).copy_(order_in.int())
+    flat(in_src, E).copy_(s[order_in].int())
+    kin = torch.empty(E, dtype=torch.int64)
+    kin[order_in] = torch.arange(E)
+    flat(out_dst, E).copy_(d[order_out].int())
+    flat(out_kin, E).copy_(kin[order_out].int())
+
+
+def qmp_gather_rows(inp, idx, n, width, out):
+    flat(out, n * width).view(n, width).copy_(flat(inp, n * width).view(n, width)[flat(idx, n).long()])
+
+
+# ------------------------------------------------------------------------------------------ dense
+def qmp_gemm(A, B, bias, C, n, m, k, lda, ldb, ldc, sA, sB, sC, sBias, batch, b_is_kxm, accumulate, relu):
+    fa, fb, fc = flat(A), flat(B), flat(C)
+    for b in range(batch):
+        a = win(fa, (n, k), (lda, 1), b * sA)
+        bm = win(fb, (k, m), (ldb, 1), b * sB) if b_is_kxm else win(fb, (m, k), (ldb, 1), b * sB).T
+        c = win(fc, (n, m), (ldc, 1), b * sC)
+        v = a @ bm
+        if bias is not None:
+            v = v + flat(bias)[b * sBias: b * sBias + m]
+        if accumulate:
+            v = v + c
+        if relu:
+            v = torch.relu(v)
+        c.copy_(v)
+
+
+def qmp_gemm_tn_acc(A, B, C, n, ma, mb, lda, ldb, ldc, sA, sB, sC, batch, b_ones):
+    fa, fb, fc = flat(A), flat(B), flat(C)
+    real = mb - 1 if b_ones else mb
+    for b in range(batch):
+        a = win(fa, (n, ma), (lda, 1), b * sA)
+        bm = win(fb, (n, real), (ldb, 1), b * sB)
+        if b_ones:
+            bm = torch.cat([bm, torch.ones(n, 1)], 1)
+        c = win(fc, (ma, mb), (ldc, 1), b * sC)
+        c.add_(a.T @ bm)
+
+
+# ------------------------------------------------------------------------------------------ attention
+def _attn_common(N, G_, D, ptr, nbr, ea, x, ldx, xoff):
+    p = flat(ptr, N + 1).long()
+    E = int(p[N])
+    j = flat(nbr, E).long()
+    i = torch.repeat_interleave(torch.arange(N), p[1:] - p[:-1])
+    eattr = flat(ea, 2 * E).view(E, 2) if ea is not None else torch.zeros(E, 2)
+    xs = [win(flat(x), (N, D), (ldx, 1), g * xoff) for g in range(G_)]
+    return E, i, j, eattr, xs
+
+
+def qmp_attn_fwd(N, G_, D, in_ptr, in_src, ea, x, ldx, xoff, U, Z, logit, mstat, linv, drop_p, seed):
+    assert drop_p == 0.0, "emulation covers dropout = 0"
+    E, i, j, eattr, xs = _attn_common(N, G_, D, in_ptr, in_src, ea, x, ldx, xoff)
+    Uv = flat(U, N * G_ * (D + 2)).view(N, G_, D + 2)
+    Zv = flat(Z, N * G_ * (D + 3)).view(N, G_, D + 3)
+    lg, ms, li = flat(logit, max(E, 1) * G_).view(-1, G_), flat(mstat, N * G_).view(N, G_), flat(linv, N * G_).view(N, G_)
+    for g in range(G_):
+        s = (Uv[i, g, :D] * xs[g][j]).sum(-1) + (Uv[i, g, D:] * eattr).sum(-1)
+        lg[:E, g] = s
+        m = torch.full((N,), -math.inf).scatter_reduce(0, i, s, "amax", include_self=True)
+        p = (s - m[i]).exp()
+        l = torch.zeros(N).index_add(0, i, p)
+        inv = torch.where(l > 0, 1 / l, torch.zeros_like(l))
+        al = p * inv[i]
+        Zv[:, g, :D] = torch.zeros(N, D).index_add(0, i, al[:, None] * xs[g][j])
+        Zv[:, g, D:D + 2] = torch.zeros(N, 2).index_add(0, i, al[:, None] * eattr)
+        Zv[:, g, D + 2] = torch.zeros(N).index_add(0, i, al)
+        ms[:, g], li[:, g] = m, inv
+
+
+def qmp_attn_bwd_target(N, G_, D, in_ptr, in_src, ea, x, ldx, xoff, logit, mstat, linv, dZ, ds, dU, drop_p, seed):
+    E, i, j, eattr, xs = _attn_common(N, G_, D, in_ptr, in_src, ea, x, ldx, xoff)
+    dZv = flat(dZ, N * G_ * (D + 3)).view(N, G_, D + 3)
+    dUv = flat(dU, N * G_ * (D + 2)).view(N, G_, D + 2)
+    lg, ms, li = flat(logit, max(E, 1) * G_).view(-1, G_), flat(mstat, N * G_).view(N, G_), flat(linv, N * G_).view(N, G_)
+    dsv = flat(ds, max(E, 1) * G_).view(-1, G_)
+    for g in range(G_):
+        al = (lg[:E, g] - ms[i, g]).exp() * li[i, g]
+        dal = (dZv[i, g, :D] * xs[g][j]).sum(-1) + (dZv[i, g, D:D + 2] * eattr).sum(-1) + dZv[i, g, D + 2]
+        t = torch.zeros(N).index_add(0, i, al * dal)
+        d = al * (dal - t[i])
+        dsv[:E, g] = d
+        dUv[:, g, :D] = torch.zeros(N, D).index_add(0, i, d[:, None] * xs[g][j])
+        dUv[:, g, D:] = torch.zeros(N, 2).index_add(0, i, d[:, None] * eattr)
+
+
+def qmp_attn_bwd_source(N, G_, D, out_ptr, out_dst, out_kin, logit, mstat, linv, ds, dZ, U, dx, lddx, dxoff, shared,
+                        accumulate, drop_p, seed):
+    p = flat(out_ptr, N + 1).long()
+    E = int(p[N])
+    i, kin = flat(out_dst, E).long(), flat(out_kin, E).long()
+    j = torch.repeat_interleave(torch.arange(N), p[1:] - p[:-1])
+    dZv = flat(dZ, N * G_ * (D + 3)).view(N, G_, D + 3)
+    Uv = flat(U, N * G_ * (D + 2)).view(N, G_, D + 2)
+    lg, ms, li = flat(logit, max(E, 1) * G_).view(-1, G_), flat(mstat, N * G_).view(N, G_), flat(linv, N * G_).view(N, G_)
+    dsv = flat(ds, max(E, 1) * G_).view(-1, G_)
+    total = torch.zeros(N, D)
+    for g in range(G_):
+        al = (lg[kin, g] - ms[i, g]).exp() * li[i, g]
+        contrib = torch.zeros(N, D).index_add(0, j, al[:, None] * dZv[i, g, :D] + dsv[kin, g][:, None] * Uv[i, g, :D])
+        if shared:
+            total += contrib
+        else:
+            dst = win(flat(dx), (N, D), (lddx, 1), g * dxoff)
+            dst.copy_(dst + contrib if accumulate else contrib)
+    if shared:
+        dst = win(flat(dx), (N, D), (lddx, 1), 0)
+        dst.copy_(dst + total if accumulate else total)
+
+
+# ------------------------------------------------------------------------------------------ GCN / Cheb
+def qmp_edge_norm(mode, N, in_ptr, in_src, out_ptr, out_dst, out_kin, w, dis, val):
+    p = flat(in_ptr, N + 1).long()
+    E = int(p[N])
+    j = flat(in_src, E).long()
+    i = torch.repeat_interleave(torch.arange(N), p[1:] - p[:-1])
+    wk = flat(w, E) if w is not None else torch.ones(E)
+    if mode == 0:
+        deg = torch.zeros(N).index_add(0, i, wk)
+    else:
+        deg = torch.zeros(N).index_add(0, j, torch.where(i == j, torch.zeros(E), wk))
+    r = deg.pow(-0.5)
+    r = r.masked_fill(r == math.inf, 0.0)
+    v = r[j] * wk * r[i]
+    if mode == 1:
+        v = torch.where(i == j, torch.zeros(E), -v)
+    flat(val, E).copy_(v)
+
+
+def qmp_spmm(N, width, ptr, nbr, vidx, val, x, ldx, alpha, beta, z, ldz, y, ldy):
+    p = flat(ptr, N + 1).long()
+    E = int(p[N])
+    nb = flat(nbr, E).long()
+    row = torch.repeat_interleave(torch.arange(N), p[1:] - p[:-1])
+    v = flat(val, E)[flat(vidx, E).long()] if vidx is not None else flat(val, E)
+    xv = rows(x, N, ldx, width)
+    out = alpha * torch.zeros(N, width).index_add(0, row, v[:, None] * xv[nb])
+    if z is not None:
+        out = out + beta * rows(z, N, ldz, width)
+    rows(y, N, ldy, width).copy_(out)
+
+
+# ------------------------------------------------------------------------------------------ LSTM gates
+def _ln(x, gamma, beta, eps):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    rstd = (var + eps).rsqrt()
+    xh = (x - mu) * rstd
+    return xh * gamma + beta, xh, rstd
+
+
+def _ln_bwd(xh, dy, gamma, rstd):
+    g = dy * gamma
+    return rstd * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+
+
+def qmp_lstm_gates_fwd(N, C, P, ldp, Cprev, params, norm_h, norm_c, norm_o, eps, gates, Craw, Oout, Hout, Cout, head_in,
+                       ldh, concat):
+    Pv = rows(P, N, ldp, 4 * C)
+    prm = flat(params, 13 * C).view(13, C)
+    cp = flat(Cprev, N * C).view(N, C) if Cprev is not None else torch.zeros(N, C)
+    I = torch.sigmoid(Pv[:, :C] + prm[0] * cp + prm[3])
+    Fg = torch.sigmoid(Pv[:, C:2 * C] + prm[1] * cp + prm[4])
+    T = torch.tanh(Pv[:, 2 * C:3 * C] + prm[5])
+    Cn = Fg * cp + I * T
+    O = torch.sigmoid(Pv[:, 3 * C:] + prm[2] * Cn + prm[6])
+    H = O * torch.tanh(Cn)
+    flat(gates, N * 4 * C).view(N, 4 * C).copy_(torch.cat([I, Fg, T, O], 1))
+    flat(Craw, N * C).view(N, C).copy_(Cn)
+    if Oout is not None:
+        flat(Oout, N * C).view(N, C).copy_(O)
+    flat(Hout, N * C).view(N, C).copy_(_ln(H, prm[7], prm[8], eps)[0] if norm_h else H)
+    flat(Cout, N * C).view(N, C).copy_(_ln(Cn, prm[9], prm[10], eps)[0] if norm_c else Cn)
+    if head_in is not None:
+        hv = rows(head_in, N, ldh, C + 1)
+        hv[:, :C] = torch.relu(_ln(O, prm[11], prm[12], eps)[0] if norm_o else O)
+        if concat is not None:
+            hv[:, C] = flat(concat, N)
+
+
+def qmp_lstm_gates_bwd(N, C, gates, Craw, Cprev, params, norm_h, norm_c, norm_o, eps, dHout, dCout, dOdirect, dHead, lddh,
+                       dP, lddp, dCprev, dparams):
+    gt = flat(gates, N * 4 * C).view(N, 4 * C)
+    I, Fg, T, O = gt[:, :C], gt[:, C:2 * C], gt[:, 2 * C:3 * C], gt[:, 3 * C:]
+    Cn = flat(Craw, N * C).view(N, C)
+    cp = flat(Cprev, N * C).view(N, C) if Cprev is not None else torch.zeros(N, C)
+    prm = flat(params, 13 * C).view(13, C)
+    z = lambda t: flat(t, N * C).view(N, C).clone() if t is not None else torch.zeros(N, C)
+    dH, dC, dO = z(dHout), z(dCout), z(dOdirect)
+    dprm = torch.zeros(13, C)
+    tc = torch.tanh(Cn)
+    if norm_h:
+        _, xh, rstd = _ln(O * tc, prm[7], prm[8], eps)
+        dprm[7], dprm[8] = (dH * xh).sum(0), dH.sum(0)
+        dH = _ln_bwd(xh, dH, prm[7], rstd)
+    if norm_c:
+        _, xh, rstd = _ln(Cn, prm[9], prm[10], eps)
+        dprm[9], dprm[10] = (dC * xh).sum(0), dC.sum(0)
+        dC = _ln_bwd(xh, dC, prm[9], rstd)
+    if dHead is not None:
+        dh = rows(dHead, N, lddh, C)
+        if norm_o:
+            y, xh, rstd = _ln(O, prm[11], prm[12], eps)
+            dy = torch.where(y > 0, dh, torch.zeros_like(dh))
+            dprm[11], dprm[12] = (dy * xh).sum(0), dy.sum(0)
+            dO = dO + _ln_bwd(xh, dy, prm[11], rstd)
+        else:
+            dO = dO + torch.where(O > 0, dh, torch.zeros_like(dh))
+    dOt = dH * tc + dO
+    dOp = dOt * O * (1 - O)
+    dCn = dC + dH * O * (1 - tc * tc) + dOp * prm[2]
+    dIp = dCn * T * I * (1 - I)
+    dFp = dCn * cp * Fg * (1 - Fg)
+    dTp = dCn * I * (1 - T * T)
+    rows(dP, N, lddp, 4 * C).copy_(torch.cat([dIp, dFp, dTp, dOp], 1))
+    if dCprev is not None:
+        flat(dCprev, N * C).view(N, C).copy_(dCn * Fg + dIp * prm[0] + dFp * prm[1])
+    dprm[0], dprm[1], dprm[2] = (dIp * cp).sum(0), (dFp * cp).sum(0), (dOp * Cn).sum(0)
+    dprm[3], dprm[4], dprm[5], dprm[6] = dIp.sum(0), dFp.sum(0), dTp.sum(0), dOp.sum(0)
+    if dparams is not None:
+        flat(dparams, 13 * C).view(13, C).add_(dprm)
+
+
+def qmp_head_finish_fwd(y, x, N, F, binary, drop_p, seed, out, x_next):
+    xv = flat(x, N * F).view(N, F)
+    o = torch.tanh(flat(y, N)) + xv[:, 0]
+    if binary:
+        o = torch.sigmoid(o)
+    flat(out, N).copy_(o)
+    if x_next is not None:
+        xn = flat(x_next, N * F).view(N, F)
+        xn.copy_(xv)
+        xn[:, 0] = o
+
+
+def qmp_head_finish_bwd(y, out, x, d_out, d_xnext, N, F, binary, drop_p, seed, dy, dx0):
+    g = torch.zeros(N)
+    if d_out is not None:
+        g = g + flat(d_out, N)
+    if d_xnext is not None:
+        g = g + flat(d_xnext, N * F).view(N, F)[:, 0]
+    if binary:
+        o = flat(out, N)
+        g = g * o * (1 - o)
+    th = torch.tanh(flat(y, N))
+    flat(dy, N).copy_(g * (1 - th * th))
+    flat(dx0, N).copy_(g)
+
+
+def qmp_relu_mask(y, dy, n):
+    d = flat(dy, n)
+    d[~(flat(y, n) > 0)] = 0.0
+
+
+# ------------------------------------------------------------------------------------------ install
+class Emulated:
+    """Context manager: route ``_lib.call`` to the functions above and let CPU tensors through."""
+
+    def __enter__(self):
+        from quadtree_mpnnlstm_b200 import _lib, graph_functions as gf
+        self._lib, self._gf = _lib, gf
+        self._saved = (_lib.call, gf._device, _lib.lib)
+        table = globals()
+
+        def call(name, *args):
+            table[name](*args)
+
+        class _FakeLib:
+            @staticmethod
+            def qmp_quadtree_pyramid_cells(n, m, s):
+                return 1
+
+        _lib.call = call
+        _lib.lib = lambda: _FakeLib
+        gf._device = lambda device=None: torch.device("cpu")
+        self._is_cuda = torch.Tensor.is_cuda
+        torch.Tensor.is_cuda = property(lambda self: True)
+        return self
+
+    def __exit__(self, *exc):
+        self._lib.call, self._gf._device, self._lib.lib = self._saved
+        torch.Tensor.is_cuda = self._is_cuda
+        return False

@@ -1,0 +1,147 @@
+"""GPU parity: conv modules, the grouped LSTM cell and the dense kernels vs the CPU oracle (fp32)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import blob_frames, rel_err
+
+TOL = 2e-5   # relative, fp32 with different summation order
+
+
+def _graph(seed=0, H=24, W=30, quadtree=True, use_edge_attrs=True):
+    from oracle import graph_ref as G
+    rng = np.random.default_rng(seed)
+    x = blob_frames(rng, 1, H, W, c=1)
+    mask = rng.random((H, W)) > 0.85
+    g = G.image_to_graph(G.add_positional_encoding(torch.from_numpy(x)), thresh=0.5 if quadtree else -np.inf,
+                         max_grid_size=8, mask=mask, use_edge_attrs=use_edge_attrs)
+    return g["edge_index"], g["edge_attrs"], g["data"].shape[1]
+
+
+def _copy_params(dst, src):
+    dst.load_state_dict(src.state_dict())
+
+
+def _check_module(be, make_ref, make_gpu, edge_index, edge_attr, n, d_in, seed=0):
+    torch.manual_seed(seed)
+    ref = make_ref()
+    gpu = be.dev(make_gpu())
+    _copy_params(gpu, ref)
+    ref.eval(); gpu.eval()
+    x = torch.randn(n, d_in)
+    xa = x.clone().requires_grad_(True)
+    xb = be.dev(x.clone()).requires_grad_(True)
+    ei_g = be.dev(edge_index)
+    ea_g = be.dev(edge_attr) if edge_attr is not None else None
+    ya = ref(xa, edge_index, edge_attr)
+    yb = gpu(xb, ei_g, ea_g)
+    assert ya.shape == yb.shape
+    assert rel_err(yb, ya) < TOL, f"forward rel err {rel_err(yb, ya)}"
+    w = torch.randn_like(ya)
+    (ya * w).sum().backward()
+    (yb * be.dev(w)).sum().backward()
+    assert rel_err(xb.grad, xa.grad) < 5 * TOL, f"dx rel err {rel_err(xb.grad, xa.grad)}"
+    for (k, pa), (_, pb) in zip(ref.named_parameters(), gpu.named_parameters()):
+        ga = pa.grad if pa.grad is not None else torch.zeros_like(pa)
+        gb = pb.grad if pb.grad is not None else torch.zeros_like(pb)
+        scale = max(float(ga.abs().max()), 1e-3)
+        diff = float((ga - gb.cpu()).abs().max())
+        # lin_key.bias has an exactly-zero gradient here and ~1e-6 cancellation noise under autograd
+        assert diff / scale < 1e-4 or diff < 2e-5, f"grad {k}: rel {diff / scale} abs {diff}"
+
+
+@pytest.mark.parametrize("d_in,d_out", [(4, 32), (8, 32), (32, 32), (33, 32), (32, 1), (16, 16), (70, 8)])
+@pytest.mark.parametrize("quadtree", [True, False])
+def test_transformer_conv(be, d_in, d_out, quadtree):
+    import quadtree_mpnnlstm_b200.convs as C
+    from oracle import convs_ref as R
+    ei, ea, n = _graph(1, quadtree=quadtree)
+    kw = dict(heads=1, edge_dim=2, dropout=0.1, concat=False)
+    _check_module(be, lambda: R.TransformerConv(d_in, d_out, **kw), lambda: C.TransformerConv(d_in, d_out, **kw), ei, ea, n, d_in)
+
+
+@pytest.mark.parametrize("d_in,d_out", [(4, 16), (16, 16), (17, 16), (16, 1), (32, 32)])
+@pytest.mark.parametrize("weighted", [True, False])
+def test_cheb_conv(be, d_in, d_out, weighted):
+    import quadtree_mpnnlstm_b200.convs as C
+    from oracle import convs_ref as R
+    ei, ea, n = _graph(2, use_edge_attrs=False)
+    ew = ea if weighted else None
+    _check_module(be, lambda: R.ChebConv(d_in, d_out, K=3), lambda: C.ChebConv(d_in, d_out, K=3), ei, ew, n, d_in)
+
+
+@pytest.mark.parametrize("d_in,d_out", [(4, 16), (16, 16), (17, 16), (16, 1)])
+@pytest.mark.parametrize("self_loops", [False, True])
+def test_gcn_conv(be, d_in, d_out, self_loops):
+    import quadtree_mpnnlstm_b200.convs as C
+    from oracle import convs_ref as R
+    ei, ea, n = _graph(3, use_edge_attrs=False)
+    _check_module(be, lambda: R.GCNConv(d_in, d_out, add_self_loops=self_loops),
+                  lambda: C.GCNConv(d_in, d_out, add_self_loops=self_loops), ei, ea, n, d_in)
+
+
+@pytest.mark.parametrize("conv,n_conv_layers,f_in,hid", [("TransformerConv", 1, 4, 32), ("TransformerConv", 3, 8, 32),
+                                                         ("ChebConv", 1, 4, 16), ("ChebConv", 2, 4, 16),
+                                                         ("GCNConv", 2, 4, 16), ("TransformerConv", 2, 5, 8)])
+def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid):
+    import quadtree_mpnnlstm_b200.model as M
+    from oracle import cell_ref as R
+    ei, ea, n = _graph(4, use_edge_attrs=(conv == "TransformerConv"))
+    torch.manual_seed(11)
+    ref = R.GConvLSTM(f_in, hid, n_conv_layers, conv)
+    gpu = be.dev(M.GConvLSTM(f_in, hid, n_conv_layers, conv))
+    gpu.load_state_dict(ref.state_dict())
+    with torch.no_grad():      # peepholes / biases are zero-initialised; make them matter
+        for m in (ref, gpu):
+            for k, p in m.named_parameters():
+                if k.startswith(("w_c_", "b_")):
+                    p.copy_(torch.linspace(-0.5, 0.5, p.numel()).view_as(p))
+    ref.eval(); gpu.eval()
+    X, H, Cs = torch.randn(n, f_in), torch.randn(n, hid), torch.randn(n, hid)
+    ins_a = [t.clone().requires_grad_(True) for t in (X, H, Cs)]
+    ins_b = [be.dev(t.clone()).requires_grad_(True) for t in (X, H, Cs)]
+    oa = ref(ins_a[0], ei, ea, ins_a[1], ins_a[2])
+    ob = gpu(ins_b[0], be.dev(ei), be.dev(ea) if ea is not None else None, ins_b[1], ins_b[2])
+    for a, b, name in zip(oa, ob, "OHC"):
+        assert rel_err(b, a) < TOL, f"{name}: {rel_err(b, a)}"
+    ws = [torch.randn_like(a) for a in oa]
+    sum((a * w).sum() for a, w in zip(oa, ws)).backward()
+    sum((b * be.dev(w)).sum() for b, w in zip(ob, ws)).backward()
+    for a, b, name in zip(ins_a, ins_b, ("dX", "dH", "dC")):
+        assert rel_err(b.grad, a.grad) < 1e-4, f"{name}: {rel_err(b.grad, a.grad)}"
+    for (k, pa), (_, pb) in zip(ref.named_parameters(), gpu.named_parameters()):
+        ga = pa.grad if pa.grad is not None else torch.zeros_like(pa)
+        gb = pb.grad if pb.grad is not None else torch.zeros_like(pb)
+        diff = float((ga - gb.cpu()).abs().max())
+        err = diff / max(float(ga.abs().max()), 1e-3)
+        assert err < 2e-4 or diff < 2e-5, f"grad {k}: rel {err} abs {diff}"
+    # H=None / C=None defaults to zeros like the reference
+    oa0 = ref(X, ei, ea)
+    ob0 = gpu(be.dev(X), be.dev(ei), be.dev(ea) if ea is not None else None)
+    assert rel_err(ob0[1], oa0[1]) < TOL
+
+
+def test_gemm_kernels(be):
+    from quadtree_mpnnlstm_b200 import ops
+    torch.manual_seed(0)
+    for (n, m, k, G) in [(1000, 34, 32, 4), (333, 1, 32, 1), (4097, 32, 35, 8), (70, 130, 5, 2)]:
+        A = torch.randn(n, G * k, device=be.device)
+        B = torch.randn(G, m, k, device=be.device)
+        bias = torch.randn(G, m, device=be.device)
+        C = torch.empty(n, G * m, device=be.device)
+        ops.gemm(A, B, bias, C, n, m, k, G * k, k, G * m, sA=k, sB=m * k, sC=m, sBias=m, batch=G)
+        ref = torch.einsum("ngk,gmk->ngm", A.view(n, G, k).double(), B.double()) + bias.double()
+        assert rel_err(C.view(n, G, m), ref) < 1e-5
+        # NN form + accumulate + relu
+        Bt = B.transpose(1, 2).contiguous()          # [G, k, m]
+        C2 = torch.ones(n, G * m, device=be.device)
+        ops.gemm(A, Bt, None, C2, n, m, k, G * k, m, G * m, sA=k, sB=m * k, sC=m, batch=G, b_is_kxm=1, accumulate=1, relu=1)
+        ref2 = torch.relu(torch.einsum("ngk,gkm->ngm", A.view(n, G, k).double(), Bt.double()) + 1.0)
+        assert rel_err(C2.view(n, G, m), ref2) < 1e-5
+        # TN with the implicit ones column
+        D = torch.randn(n, G * m, device=be.device)
+        W = torch.zeros(G, m, k + 1, device=be.device)
+        ops.gemm_tn_acc(D, A, W, n, m, k + 1, G * m, G * k, k + 1, sA=m, sB=k, sC=m * (k + 1), batch=G, b_ones=1)
+        A1 = torch.cat([A.view(n, G, k), torch.ones(n, G, 1, device=be.device)], -1)
+        ref3 = torch.einsum("ngm,ngk->gmk", D.view(n, G, m).double(), A1.double())
+        assert rel_err(W, ref3) < 1e-4

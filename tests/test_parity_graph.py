@@ -1,0 +1,154 @@
+"""GPU parity: graph build, pooling and adjacency vs the CPU oracle (bit-exact labels / edge_index)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import attrs_close, blob_frames, dist_from_05, rel_err
+
+
+CASES = [
+    # H, W, max_size, thresh, cond, mask, hir, transform
+    (64, 64, 64, 0.5, "max_larger_than", False, False, False),
+    (37, 53, 16, 0.5, "max_smaller_than", True, False, False),
+    (20, 70, 64, 0.5, "min_larger_than", False, False, True),
+    (64, 64, 4, 0.5, "min_smaller_than", True, True, False),
+    (50, 90, 32, 0.3, "max_larger_than", False, True, True),
+    (33, 33, 64, 0.5, "max_smaller_than", True, True, False),
+    (100, 130, 128, 0.5, "max_larger_than", True, False, False),   # max_size > 64: level-up kernels
+    (7, 9, 1, 0.5, "max_larger_than", True, False, False),         # max_size 1: every pixel its own base cell
+    (229, 361, 64, 0.15, "max_larger_than", True, True, True),     # ice grid
+]
+
+
+def _inputs(case, seed):
+    H, W, S, thresh, cond, use_mask, use_hir, use_tf = case
+    rng = np.random.default_rng(seed)
+    x = blob_frames(rng, 3, H, W, c=2)
+    mask = (rng.random((H, W)) > 0.9) if use_mask else None
+    hir = (rng.random((H, W)) > 0.98) if use_hir else None
+    return x, mask, hir, (dist_from_05 if use_tf else None)
+
+
+@pytest.mark.parametrize("idx", range(len(CASES)))
+@pytest.mark.parametrize("use_edge_attrs", [True, False])
+def test_image_to_graph_matches_oracle(be, idx, use_edge_attrs):
+    import quadtree_mpnnlstm_b200 as q
+    from oracle import graph_ref as G
+    case = CASES[idx]
+    H, W, S, thresh, cond, *_ = case
+    x, mask, hir, tf = _inputs(case, 100 + idx)
+    xc = G.add_positional_encoding(torch.from_numpy(x))
+    xg = q.add_positional_encoding(be.dev(torch.from_numpy(x)))
+    assert torch.equal(xc, xg.cpu()), "positional encoding differs"
+    ref = G.image_to_graph(xc, thresh=thresh, max_grid_size=S, mask=mask, high_interest_region=hir,
+                           transform_func=tf, condition=cond, use_edge_attrs=use_edge_attrs)
+    got = q.image_to_graph(xg, thresh=thresh, max_grid_size=S, mask=mask, high_interest_region=hir,
+                           transform_func=tf, condition=cond, use_edge_attrs=use_edge_attrs)
+    lab = got["labels"].cpu().long().numpy()
+    assert np.array_equal(lab, ref["labels"]), f"labels differ at {np.argwhere(lab != ref['labels'])[:5]}"
+    assert got["edge_index"].dtype == torch.int64
+    assert torch.equal(got["edge_index"].cpu(), ref["edge_index"]), "edge_index differs (order or content)"
+    assert torch.equal(got["n_pixels_per_node"].cpu(), ref["n_pixels_per_node"])
+    assert torch.equal(got["data"].cpu(), ref["data"]), f"node data not bit-identical: {rel_err(got['data'], ref['data'])}"
+    assert attrs_close(got["edge_attrs"], ref["edge_attrs"])
+    assert got["mapping"].shape == (ref["mapping"].n_nodes, H * W)
+
+
+@pytest.mark.parametrize("shape", [(40, 60), (229, 361), (5, 5)])
+def test_pixelwise_graph_matches_oracle(be, shape):
+    import quadtree_mpnnlstm_b200 as q
+    from oracle import graph_ref as G
+    H, W = shape
+    rng = np.random.default_rng(7)
+    x = rng.random((2, H, W, 3)).astype(np.float32)
+    rr, cc = np.mgrid[0:H, 0:W]
+    mask = ((rr - H / 2) ** 2 / (H / 2.2) ** 2 + (cc - W / 2) ** 2 / (W / 2.5) ** 2) > 1
+    ref = G.image_to_graph(G.add_positional_encoding(torch.from_numpy(x)), thresh=-np.inf, mask=mask)
+    got = q.image_to_graph(q.add_positional_encoding(be.dev(torch.from_numpy(x))), thresh=-np.inf, mask=mask)
+    assert torch.equal(got["edge_index"].cpu(), ref["edge_index"])
+    assert torch.equal(got["data"].cpu(), ref["data"])
+    assert torch.allclose(got["edge_attrs"].cpu(), ref["edge_attrs"], atol=1e-6)
+    assert got["mapping"] is None
+    img_r = G.unpool(ref["data"][0], None, (H, W), mask)
+    img_g = q.unflatten(got["data"][0], None, (H, W), mask).cpu()
+    assert torch.equal(torch.isnan(img_r), torch.isnan(img_g))
+    assert torch.equal(torch.nan_to_num(img_r), torch.nan_to_num(img_g))
+
+
+def test_static_graphs_match_oracle(be):
+    import quadtree_mpnnlstm_b200 as q
+    from oracle import graph_ref as G
+    mask = np.zeros((50, 70), bool)
+    mask[:10, :30] = True
+    mask[30:, 50:] = True
+    mask[20, 20] = True
+    for fn in ("create_static_heterogeneous_graph", "create_static_homogeneous_graph"):
+        a = getattr(G, fn)((50, 70), 4, mask, use_edge_attrs=True, resolution=1 / 12)
+        b = getattr(q, fn)((50, 70), 4, mask, use_edge_attrs=True, resolution=1 / 12, device=be.device)
+        assert torch.equal(b["edge_index"].cpu(), a["edge_index"]), fn
+        assert attrs_close(b["edge_attrs"], a["edge_attrs"]), fn
+        assert torch.equal(b["n_pixels_per_node"].cpu(), a["n_pixels_per_node"]), fn
+        assert torch.equal(b["mapping"].to_dense().cpu(), a["mapping"].dense()), fn
+        assert "data" not in b
+
+
+def test_pool_unpool_forward_backward(be):
+    import quadtree_mpnnlstm_b200 as q
+    from oracle import graph_ref as G
+    rng = np.random.default_rng(3)
+    H, W = 48, 40
+    x = blob_frames(rng, 2, H, W, c=1)
+    ref = G.image_to_graph(G.add_positional_encoding(torch.from_numpy(x)), thresh=0.5, max_grid_size=16)
+    got = q.image_to_graph(q.add_positional_encoding(be.dev(torch.from_numpy(x))), thresh=0.5, max_grid_size=16)
+    img = torch.from_numpy(rng.random((3, H, W, 5)).astype(np.float32))
+    a = img.clone().requires_grad_(True)
+    b = be.dev(img.clone()).requires_grad_(True)
+    pa = G.pool(a, ref["mapping"], ref["n_pixels_per_node"])
+    pb = q.flatten(b, got["mapping"], got["n_pixels_per_node"])
+    assert torch.equal(pa, pb.cpu())
+    w = torch.from_numpy(rng.random(tuple(pa.shape)).astype(np.float32))
+    (pa * w).sum().backward()
+    (pb * be.dev(w)).sum().backward()
+    assert torch.allclose(a.grad, b.grad.cpu(), atol=1e-7)
+    # unpool of [L, N, C] state tensors
+    st = torch.from_numpy(rng.random((2, pa.shape[1], 4)).astype(np.float32))
+    sa = st.clone().requires_grad_(True)
+    sb = be.dev(st.clone()).requires_grad_(True)
+    ua = G.unpool(sa, ref["mapping"], (H, W))
+    ub = q.unflatten(sb, got["mapping"], (H, W))
+    assert ua.shape == ub.shape and torch.equal(ua, ub.cpu())
+    w2 = torch.from_numpy(rng.random(tuple(ua.shape)).astype(np.float32))
+    (ua * w2).sum().backward()
+    (ub * be.dev(w2)).sum().backward()
+    assert torch.allclose(sa.grad, sb.grad.cpu(), rtol=1e-5, atol=1e-5)
+    # a dense [N, P] matrix is still accepted where the reference takes `mapping`
+    dense = got["mapping"].to_dense()
+    pc = q.flatten(be.dev(img), dense, got["n_pixels_per_node"])
+    assert torch.equal(pc.cpu(), pa.detach())
+
+
+def test_nan_input_raises(be):
+    import quadtree_mpnnlstm_b200 as q
+    x = torch.zeros(1, 16, 16, 3, device=be.device)
+    x[0, 3, 3, 0] = float("nan")
+    with pytest.raises(ValueError):
+        q.image_to_graph(x, thresh=0.5, max_grid_size=8)
+    with pytest.raises(AssertionError):
+        q.image_to_graph(torch.zeros(16, 16, 3, device=be.device))
+    with pytest.raises(AssertionError):
+        q.image_to_graph(torch.zeros(1, 16, 16, 3, device=be.device), max_grid_size=6)
+    with pytest.raises(AssertionError):
+        q.image_to_graph(torch.zeros(1, 16, 16, 3, device=be.device), condition="bogus")
+
+
+def test_scan_kernel(be):
+    from quadtree_mpnnlstm_b200 import _lib
+    for n in (1, 5, 1024, 1025, 50000, 330676):
+        v = torch.randint(0, 5, (n,), dtype=torch.int32, device=be.device)
+        out = torch.empty_like(v)
+        tot = torch.zeros(1, dtype=torch.int32, device=be.device)
+        scratch = torch.empty(n // 1024 + 4, dtype=torch.int32, device=be.device)
+        _lib.call("qmp_exclusive_scan_i32", v, out, n, tot, scratch)
+        ref = torch.cumsum(v.long(), 0) - v.long()
+        assert torch.equal(out.long(), ref), n
+        assert int(tot) == int(v.sum())
