@@ -47,6 +47,23 @@ SIGNATURES = {
 }
 
 
+# kernels launched by one call of each entry point (for bench.py's gpu_launches accounting)
+KERNELS_PER_CALL = {
+    "qmp_exclusive_scan_i32": 3, "qmp_frame_max_pad": 1, "qmp_quadtree_labels": 3, "qmp_mesh_pixels_from_rects": 5,
+    "qmp_mesh_pixelwise": 5, "qmp_segment_sum": 1, "qmp_gather_by_label": 1, "qmp_adjacency_quadtree": 8,
+    "qmp_adjacency_pixelwise": 5, "qmp_edge_attrs": 1, "qmp_add_positional_encoding": 1,
+    "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
+    "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
+    "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1,
+}
+CALL_COUNTS = {}
+
+
+def kernel_launches():
+    """Kernels launched through this binding so far (sum over entry points of calls x kernels per call)."""
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in CALL_COUNTS.items())
+
+
 class QmpError(RuntimeError):
     pass
 
@@ -99,6 +116,7 @@ def call(name, *args):
     L = lib()
     fn = getattr(L, name)
     conv = [_ptr(a) if (isinstance(a, torch.Tensor) or a is None) else a for a in args]
+    CALL_COUNTS[name] = CALL_COUNTS.get(name, 0) + 1
     rc = fn(*conv, stream_ptr())
     if rc != 0:
         raise QmpError(f"{name} failed (code {rc}): {L.qmp_last_error().decode(errors='replace')}")
