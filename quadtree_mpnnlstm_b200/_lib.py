@@ -97,6 +97,11 @@ def on_device(t):
     return bool(t.is_cuda)
 
 
+def capturing():
+    """True while the current CUDA stream is being captured into a graph (host read-backs are illegal then)."""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def _ptr(t):
     if t is None:
         return None

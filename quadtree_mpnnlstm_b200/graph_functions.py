@@ -272,16 +272,19 @@ def _edge_buffers(e_cap, device):
     return ei, s32, d32
 
 
-def image_to_graph_pixelwise(img, mask=None, use_edge_attrs=True, resolution=0.25):
-    """image_to_graph() if each pixel is treated as a node (graph_functions.py:506-539)."""
-    if mask is None:
-        raise TypeError("image_to_graph_pixelwise needs a mask (the reference evaluates ~mask)")
-    n, h, w, c = img.shape
-    dev = img.device
-    mesh = pixelwise_mesh(mask, (h, w), dev)
-    N = mesh.n_nodes
-    data = _Pool.apply(img.float(), mesh)
-    P = h * w
+_pixelwise_topology = {}
+
+
+def _pixelwise_edges(mesh, mask, h, w, c_pos_source, use_edge_attrs, resolution):
+    """edge_index / edge_attrs of the pixel-wise mesh.  They depend only on the mask, the image shape and the
+    resolution (node positions are the positional-encoding planes), so they are built once per mask and
+    reused by every later sample -- no per-sample host read-back."""
+    key = (id(mask), h, w, bool(use_edge_attrs), float(resolution), str(mesh.labels.device))
+    hit = _pixelwise_topology.get(key)
+    if hit is not None and hit[0] is mask:
+        return hit[1], hit[2]
+    dev = mesh.labels.device
+    N, P = mesh.n_nodes, h * w
     i32 = dict(dtype=torch.int32, device=dev)
     e_cap = 4 * N
     ei, s32, d32 = _edge_buffers(e_cap, dev)
@@ -289,15 +292,32 @@ def image_to_graph_pixelwise(img, mask=None, use_edge_attrs=True, resolution=0.2
     _lib.call("qmp_adjacency_pixelwise", mesh.labels, h, w, ei[0], ei[1], s32, d32, n_edges, count, offset, bs)
     edge_attrs = None
     if use_edge_attrs:
-        # get_adj_pixelwise is not handed `resolution` for the attrs beyond xx/yy (graph_functions.py:519, 528)
+        # node positions = pooled ii / jj planes of the positional encoding (graph_functions.py:519)
+        pos = _Pool.apply(add_positional_encoding(torch.zeros(1, h, w, 1, device=dev))[..., 1:].contiguous(), mesh)
         edge_attrs = torch.empty(e_cap, 2, dtype=torch.float32, device=dev)
-        d0 = data.detach()
-        _lib.call("qmp_edge_attrs", s32, d32, e_cap, n_edges, d0[0, :, c - 2:], d0[0, :, c - 1:], c, w, h,
-                  float(resolution), 1, edge_attrs)
+        _lib.call("qmp_edge_attrs", s32, d32, e_cap, n_edges, pos[0, :, 0:], pos[0, :, 1:], 2, w, h, float(resolution),
+                  1, edge_attrs)
     E = int(n_edges.item())
     edge_index = ei[:, :E].contiguous()
     if edge_attrs is not None:
-        edge_attrs = edge_attrs[:E]
+        edge_attrs = edge_attrs[:E].contiguous()
+    if len(_pixelwise_topology) > 8:
+        _pixelwise_topology.clear()
+    _pixelwise_topology[key] = (mask, edge_index, edge_attrs)
+    return edge_index, edge_attrs
+
+
+def image_to_graph_pixelwise(img, mask=None, use_edge_attrs=True, resolution=0.25):
+    """image_to_graph() if each pixel is treated as a node (graph_functions.py:506-539).  The last two
+    channels of ``img`` must be the positional encoding, as in the reference (:519)."""
+    if mask is None:
+        raise TypeError("image_to_graph_pixelwise needs a mask (the reference evaluates ~mask)")
+    n, h, w, c = img.shape
+    dev = img.device
+    mesh = pixelwise_mesh(mask, (h, w), dev)
+    N = mesh.n_nodes
+    data = _Pool.apply(img.float(), mesh)
+    edge_index, edge_attrs = _pixelwise_edges(mesh, mask, h, w, c, use_edge_attrs, resolution)
     sizes = torch.full((n, N, 1), float(resolution) ** 2, dtype=torch.float32, device=dev)
     data = torch.cat([data, sizes], -1)
     return dict(edge_index=edge_index, edge_attrs=edge_attrs, data=data, graph_nodes=torch.arange(N),
@@ -318,7 +338,8 @@ def image_to_graph(img, thresh=0.05, max_grid_size=64, mask=None, high_interest_
     img = img.float().contiguous()
     nan_flag = torch.isnan(img.detach()).sum()
     if thresh == -np.inf:
-        if int(nan_flag.item()):
+        # (a CUDA-graph capture cannot read back; the eager warm-up steps before a capture do check)
+        if not _lib.capturing() and int(nan_flag.item()):
             raise ValueError(f'Found NaNs in image data {int(nan_flag.item())} / {img.numel()}')
         return image_to_graph_pixelwise(img, mask, use_edge_attrs=use_edge_attrs, resolution=resolution)
 

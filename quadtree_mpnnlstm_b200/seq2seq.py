@@ -245,7 +245,8 @@ class Seq2Seq(torch.nn.Module):
             self.graph.cell = cell
 
         # first decoder input = last encoder input, [value, ii, jj, node size] (seq2seq.py:336)
-        self.graph.pyg.x = self.graph.pyg.x[-1][:, [0, -3, -2, -1]].contiguous()
+        last = self.graph.pyg.x[-1]
+        self.graph.pyg.x = torch.cat([last[:, :1], last[:, -3:]], dim=1)
 
     def unroll_output(self, unroll_steps, y, concat_layers=None, teacher_forcing_ratio=0.5, mask=None,
                       high_interest_region=None, remesh_every=1):
