@@ -263,8 +263,11 @@ def run_gpu(args):
         except Exception:
             pass
         hbm = float(peaks.get("hbm_gbs", 6650.0))
-        g = model.graph
-        csr = get_csr(g.pyg.edge_index, g.pyg.edge_attr, g.pyg.x.shape[0])
+        if model.graph is not None:
+            topo = (model.graph.pyg.edge_index, model.graph.pyg.edge_attr, int(model.graph.pyg.x.shape[0]))
+        else:
+            topo = step.topology
+        csr = get_csr(*topo)
         k_ms, k_bytes = attention_roofline(model, csr, dev)
         achieved = k_bytes / (k_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": "graph-frames/s", "n_gpus": world, "steps": args.steps,

@@ -44,6 +44,7 @@ SIGNATURES = {
     "qmp_head_finish_fwd": "ppiiifuppp",
     "qmp_head_finish_bwd": "pppppiiifuppp",
     "qmp_relu_mask": "pplp",
+    "qmp_tc_gemm_probe": "pppiiiip",
 }
 
 
@@ -54,7 +55,7 @@ KERNELS_PER_CALL = {
     "qmp_adjacency_pixelwise": 5, "qmp_edge_attrs": 1, "qmp_add_positional_encoding": 1,
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
-    "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1,
+    "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_tc_gemm_probe": 1,
 }
 CALL_COUNTS = {}
 
@@ -84,6 +85,8 @@ def lib():
         L.qmp_version.restype = _I
         L.qmp_quadtree_pyramid_cells.restype = _L
         L.qmp_quadtree_pyramid_cells.argtypes = [_I, _I, _I]
+        L.qmp_set_tensor_cores.restype = _I
+        L.qmp_set_tensor_cores.argtypes = [_I]
         for name, sig in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = _I
@@ -128,4 +131,4 @@ def call(name, *args):
 
 
 def exported_symbols():
-    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells"] + list(SIGNATURES)
+    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores"] + list(SIGNATURES)

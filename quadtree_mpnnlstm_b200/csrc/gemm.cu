@@ -150,8 +150,23 @@ __global__ void __launch_bounds__(256) gemm_tn_kernel(GemmArgs g) {
     }
 }
 
+// tcgen05 paths (tc_gemm.cu); return 1 when they took the call
+int tc_gemm_rows_try(const float* A, const float* B, const float* bias, float* C, int n, int m, int k, int lda, int ldb,
+                     int ldc, long long sA, long long sB, long long sC, long long sBias, int batch, int b_is_kxm,
+                     int accumulate, int relu, cudaStream_t st, int* rc);
+int tc_gemm_tn_try(const float* A, const float* B, float* C, int n, int ma, int mb, int lda, int ldb, int ldc,
+                   long long sA, long long sB, long long sC, int batch, int b_ones, cudaStream_t st, int* rc);
+static int g_use_tc = 0;   // measured on B200 (profiles/r01_c): for K <= 40 the smem staging + TMEM round trip outweighs the math
+
 }  // namespace qmp
 using namespace qmp;
+
+// 1: dense contractions on tcgen05 (3xTF32) when the shape fits; 0: FFMA kernels (default).  Returns the old value.
+QMP_API int qmp_set_tensor_cores(int enable) {
+    const int old = g_use_tc;
+    g_use_tc = enable ? 1 : 0;
+    return old;
+}
 
 // C[b] (n x m) (+)= A[b] (n x k) * op(B[b]) + bias[b];  b_is_kxm = 0: B is m x k (C = A B^T); 1: B is k x m.
 QMP_API int qmp_gemm(const float* A, const float* B, const float* bias, float* C, int n, int m, int k, int lda, int ldb,
@@ -159,6 +174,12 @@ QMP_API int qmp_gemm(const float* A, const float* B, const float* bias, float* C
                      int accumulate, int relu, void* stream) {
     if (n <= 0 || m <= 0 || batch <= 0) return 0;
     QMP_REQUIRE(k >= 0 && batch <= 65535, "qmp_gemm: bad k/batch");
+    if (g_use_tc) {
+        int rc = 0;
+        if (tc_gemm_rows_try(A, B, bias, C, n, m, k, lda, ldb, ldc, sA, sB, sC, sBias, batch, b_is_kxm, accumulate, relu,
+                             (cudaStream_t)stream, &rc))
+            return rc;
+    }
     GemmArgs g{A, B, bias, C, n, m, k, lda, ldb, ldc, sA, sB, sC, sBias, accumulate, relu, 0, 0, 0};
     dim3 grid(cdiv(m, BN), cdiv(n, BM), batch);
     if (b_is_kxm)
@@ -174,6 +195,10 @@ QMP_API int qmp_gemm(const float* A, const float* B, const float* bias, float* C
 QMP_API int qmp_gemm_tn_acc(const float* A, const float* B, float* C, int n, int ma, int mb, int lda, int ldb, int ldc,
                             long long sA, long long sB, long long sC, int batch, int b_ones, void* stream) {
     if (n <= 0 || ma <= 0 || mb <= 0 || batch <= 0) return 0;
+    if (g_use_tc) {
+        int rc = 0;
+        if (tc_gemm_tn_try(A, B, C, n, ma, mb, lda, ldb, ldc, sA, sB, sC, batch, b_ones, (cudaStream_t)stream, &rc)) return rc;
+    }
     int rows = 256;
     int chunks = cdiv(n, rows);
     while ((long long)chunks * batch > 60000) {

@@ -30,6 +30,8 @@ class TrainStep:
         self.eager_steps = 0
         self.launches_per_replay = 0
         self._bucket = None
+        self.stream = None
+        self.topology = None
 
     # -- one eager step -----------------------------------------------------------------------------
     def _step(self, x, y, concat):
@@ -52,6 +54,17 @@ class TrainStep:
         self.opt.step()
         return loss.detach()
 
+    def _drop_autograd_leftovers(self):
+        """Packed-parameter caches and the model's mesh state keep the previous step's autograd graph alive;
+        a capture must not see nodes created on another stream."""
+        for m in self.model.modules():
+            if hasattr(m, "_cache"):
+                m._cache.clear()
+        g = self.model.graph
+        if g is not None:
+            self.topology = (g.pyg.edge_index, g.pyg.edge_attr, int(g.pyg.x.shape[0]))
+        self.model.graph = None
+
     # -- public -------------------------------------------------------------------------------------
     def __call__(self, x, y, concat, warmup_eager=3):
         """Run one optimizer step on device tensors x [T_in,H,W,c], y [T_out,H,W,1], concat [T_out,H,W,1].
@@ -59,16 +72,24 @@ class TrainStep:
         if not self.use_cuda_graph:
             return self._step(x, y, concat)
         if self.graph is None:
-            if self.eager_steps < warmup_eager:        # let allocator / caches / lazy state settle first
-                self.eager_steps += 1
-                return self._step(x, y, concat)
+            if self.stream is None:
+                self.stream = torch.cuda.Stream()
+            if self.eager_steps < warmup_eager:        # let allocator / caches / lazy state settle first,
+                self.eager_steps += 1                  # on the side stream the capture will use
+                self.stream.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.stream):
+                    loss = self._step(x, y, concat)
+                torch.cuda.current_stream().wait_stream(self.stream)
+                return loss
             self.static = [t.clone() for t in (x, y, concat)]
+            self._drop_autograd_leftovers()
             torch.cuda.synchronize()
             from . import _lib
             before = _lib.kernel_launches()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=self.stream):
                 self.loss = self._step(*self.static)
+            self._drop_autograd_leftovers()
             self.launches_per_replay = _lib.kernel_launches() - before   # qmp kernels inside one replay
             # the capture itself does not execute; fall through to the first replay
         for s, t in zip(self.static, (x, y, concat)):

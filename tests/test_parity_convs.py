@@ -121,8 +121,22 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid):
     assert rel_err(ob0[1], oa0[1]) < TOL
 
 
-def test_gemm_kernels(be):
-    from quadtree_mpnnlstm_b200 import ops
+@pytest.mark.parametrize("tensor_cores", [1, 0])
+def test_gemm_kernels(be, tensor_cores):
+    """Dense contractions: tcgen05 3xTF32 path (default for n >= 256) and the FFMA fallback."""
+    from quadtree_mpnnlstm_b200 import ops, _lib
+    if be.name == "cuda":
+        _lib.lib().qmp_set_tensor_cores(tensor_cores)
+    elif not tensor_cores:
+        pytest.skip("the emulation has one contraction path")
+    try:
+        _gemm_checks(be, ops)
+    finally:
+        if be.name == "cuda":
+            _lib.lib().qmp_set_tensor_cores(1)
+
+
+def _gemm_checks(be, ops):
     torch.manual_seed(0)
     for (n, m, k, G) in [(1000, 34, 32, 4), (333, 1, 32, 1), (4097, 32, 35, 8), (70, 130, 5, 2)]:
         A = torch.randn(n, G * k, device=be.device)
@@ -145,3 +159,20 @@ def test_gemm_kernels(be):
         A1 = torch.cat([A.view(n, G, k), torch.ones(n, G, 1, device=be.device)], -1)
         ref3 = torch.einsum("ngm,ngk->gmk", D.view(n, G, m).double(), A1.double())
         assert rel_err(W, ref3) < 1e-4
+
+
+@pytest.mark.gpu
+def test_tcgen05_gemm_probe():
+    """tc.cuh conventions in isolation: 3xTF32 is fp32-accurate, plain TF32 is not."""
+    from quadtree_mpnnlstm_b200 import _lib
+    torch.manual_seed(0)
+    for (M, N, K) in [(128, 32, 8), (128, 136, 32), (300, 128, 40), (1000, 48, 72)]:
+        A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
+        ref = A.double() @ B.double().T
+        errs = []
+        for split in (1, 0):
+            C = torch.full((M, N), float("nan"), device="cuda")
+            _lib.call("qmp_tc_gemm_probe", A, B, C, M, N, K, split)
+            errs.append(rel_err(C, ref))
+        assert errs[0] < 5e-6, (M, N, K, errs)
+        assert 5e-5 < errs[1] < 5e-3, (M, N, K, errs)
