@@ -1,0 +1,4 @@
+#include "fused_fwd.inl"
+namespace qmp {
+template int launch_fwd<4, 32>(const FusedFwdArgs&, cudaStream_t);
+}

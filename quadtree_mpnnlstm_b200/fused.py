@@ -1,0 +1,89 @@
+"""Host side of the fused cell kernels (csrc/fused_fwd.cu, csrc/fused_bwd.cu): weight packing and the
+autograd Function.  Used by GConvLSTM / Decoder when the configuration fits the fused path
+(TransformerConv, hidden size 32, inputs <= 8 wide for the X stacks and <= 36 wide otherwise); anything
+else runs the modular kernels (ops.py), which compute the same thing.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .convs import pack_tconv
+
+FC = 32
+HEADW = 36          # decoder-head input rows: 32 normalised outputs | concat layer | 3 zero pad columns (16-byte rows)
+ENABLED = True      # tests flip this to cross-check the fused kernels against the modular ones
+_f32 = torch.float32
+
+
+def cap_of(D, small):
+    if small:
+        return 4 if D <= 4 else 8
+    return 32 if D <= 32 else 36
+
+
+def conv_total(DC):
+    return (DC + 2) * DC + (DC + 4) + FC * (DC + 4) + FC * DC + FC
+
+
+def pack_fused(convs, DC):
+    """[G, TOTAL] padded pack (layout in csrc/fused.cuh) from PyG-named TransformerConv parameters."""
+    W1, b1, W2, W3, b3 = pack_tconv(convs)                      # unpadded, see convs.pack_tconv
+    G, C, D = W3.shape
+    assert C <= FC and D <= DC
+    W1p = torch.cat([F.pad(W1[:, :D], (0, DC - D, 0, DC - D)), F.pad(W1[:, D:], (0, DC - D))], dim=1)   # [G, DC+2, DC]
+    b1p = torch.cat([F.pad(b1[:, :D], (0, DC - D)), b1[:, D:], b1.new_zeros(G, 2)], dim=1)            # [G, DC+4]
+    W2p = torch.cat([F.pad(W2[:, :, :D], (0, DC - D)), W2[:, :, D:], W2.new_zeros(G, C, 1)], dim=2)    # [G, C, DC+4]
+    W2p = F.pad(W2p, (0, 0, 0, FC - C))
+    W3p = F.pad(W3, (0, DC - D, 0, FC - C))
+    b3p = F.pad(b3, (0, FC - C))
+    return torch.cat([W1p.flatten(1), b1p, W2p.flatten(1), W3p.flatten(1), b3p], dim=1).contiguous()
+
+
+class FusedGroupFn(torch.autograd.Function):
+    """One fused launch: segment A (xa, wa: GA convs on a narrow shared input) + segment B (xb, wb: GB convs),
+    mode 1 -> LSTM gates (+ norms, head input), mode 0 -> plain conv outputs [N, (GA+GB)*C]."""
+
+    @staticmethod
+    def forward(ctx, xa, wa, xb, wb, Cprev, params, concat, csr, cfg):
+        (DA, GA, DB, GB, sharedB, mode, relu_out, C, norm_h, norm_c, norm_o, want_head, eps, drop_p, seed) = cfg
+        N = xb.shape[0]
+        dev = xb.device
+        xb = xb.contiguous()
+        xa = xa.contiguous() if xa is not None else None
+        wa = wa.contiguous() if wa is not None else None
+        wb = wb.contiguous()
+        NC = GA + GB
+        E = csr.n_edges
+        logit = torch.empty(max(E, 1), NC, dtype=_f32, device=dev)
+        mstat = torch.empty(N, NC, dtype=_f32, device=dev)
+        linv = torch.empty(N, NC, dtype=_f32, device=dev)
+        out = gates = Craw = O = H = Cn = head = None
+        if mode == 1:
+            gates = torch.empty(N, 4 * FC, dtype=_f32, device=dev)
+            Craw, O, H, Cn = (torch.empty(N, FC, dtype=_f32, device=dev) for _ in range(4))
+            head = torch.empty(N, HEADW, dtype=_f32, device=dev) if want_head else None
+            if want_head and concat is None:
+                head.zero_()
+        else:
+            out = torch.empty(N, NC * C, dtype=_f32, device=dev)
+        Cp = Cprev.contiguous() if Cprev is not None else None
+        cc = concat.contiguous().reshape(-1) if (want_head and concat is not None) else None
+        prm = params.contiguous() if params is not None else None
+        _lib.call("qmp_fused_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in,
+                  xa, xa.shape[1] if xa is not None else 0, DA, GA, wa,
+                  xb, xb.shape[1], DB, GB, int(sharedB), wb,
+                  mode, int(relu_out), C, out, NC * C, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps),
+                  gates, Craw, O, H, Cn, head, HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
+        ctx.save_for_backward(xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out if relu_out else None)
+        ctx.csr, ctx.cfg = csr, cfg
+        ctx.concat_shape = tuple(concat.shape) if concat is not None else None
+        if mode == 1:
+            return O, H, Cn, head
+        return out
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from .fused_bwd import fused_group_backward
+        return fused_group_backward(ctx, *grads)

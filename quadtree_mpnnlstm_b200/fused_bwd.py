@@ -1,0 +1,130 @@
+"""Backward of FusedGroupFn: gate backward (qmp_lstm_gates_bwd) -> fused target / source kernels ->
+weight-gradient reductions (qmp_gemm_tn_acc) written straight into the padded pack layout."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .ops import gemm_tn_acc
+
+FC = 32
+_f32 = torch.float32
+_bwd_cache = {}
+
+
+def bwd_pack(w, DC):
+    """[G, TOTAL_bwd] = W1 | b1 | W1T | W2T | W3T from the forward pack (layout: csrc/fused_bwd.inl).  Cached per
+    forward pack: the weights are constant over the timesteps of one forward pass."""
+    key = (w.data_ptr(), tuple(w.shape), DC, w._version)
+    hit = _bwd_cache.get(key)
+    if hit is not None and hit[0] is w:
+        return hit[1]
+    G = w.shape[0]
+    orig, w = w, w.detach()
+    o1 = (DC + 2) * DC
+    o2 = o1 + DC + 4
+    o3 = o2 + FC * (DC + 4)
+    o4 = o3 + FC * DC
+    W1 = w[:, :o1].view(G, DC + 2, DC)
+    b1 = w[:, o1:o2]
+    W2 = w[:, o2:o3].view(G, FC, DC + 4)
+    W3 = w[:, o3:o4].view(G, FC, DC)
+    W1T = torch.zeros(G, DC, DC + 4, dtype=_f32, device=w.device)
+    W1T[:, :, :DC + 2] = W1.transpose(1, 2)
+    pack = torch.cat([W1.flatten(1), b1, W1T.flatten(1), W2.transpose(1, 2).flatten(1), W3.transpose(1, 2).flatten(1)],
+                     dim=1).contiguous()
+    if len(_bwd_cache) > 64:
+        _bwd_cache.clear()
+    _bwd_cache[key] = (orig, pack)
+    return pack
+
+
+def _weight_grads(gw, DC, D, G, x, ldx, shared, Zs, dUs, ldz, dP, lddp, dp_off, dp_stride, ma, N):
+    """Reductions over the N nodes, written into the flat pack gradient gw [G, TOTAL] (zero-initialised)."""
+    total = gw.shape[1]
+    o1 = (DC + 2) * DC
+    o2 = o1 + DC + 4
+    o3 = o2 + FC * (DC + 4)
+    o4 = o3 + FC * DC
+    W = DC + 4
+    sx = 0 if shared else D
+    dPv = dP[:, dp_off:]
+    # logit weights: [du, dw] (x) [x | 1]
+    gemm_tn_acc(dUs, x, gw[:, 0:], N, DC + 2, D, ldz, ldx, DC, sA=W, sB=sx, sC=total, batch=G)
+    gemm_tn_acc(dUs, x, gw[:, o1:], N, DC + 2, 1, ldz, ldx, 1, sA=W, sB=sx, sC=total, batch=G, b_ones=1)
+    # value / edge / value-bias: dP (x) [z | ze | zs]
+    gemm_tn_acc(dPv, Zs, gw[:, o2:], N, ma, DC + 3, lddp, ldz, DC + 4, sA=dp_stride, sB=W, sC=total, batch=G)
+    # skip: dP (x) [x | 1]
+    gemm_tn_acc(dPv, x, gw[:, o3:], N, ma, D, lddp, ldx, DC, sA=dp_stride, sB=sx, sC=total, batch=G)
+    gemm_tn_acc(dPv, x, gw[:, o4:], N, ma, 1, lddp, ldx, 1, sA=dp_stride, sB=sx, sC=total, batch=G, b_ones=1)
+
+
+def fused_group_backward(ctx, *grads):
+    from .fused import HEADW, cap_of
+    xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out_relu = ctx.saved_tensors
+    csr = ctx.csr
+    (DA, GA, DB, GB, sharedB, mode, relu_out, C, norm_h, norm_c, norm_o, want_head, eps, drop_p, seed) = ctx.cfg
+    N = xb.shape[0]
+    dev = xb.device
+    NC = GA + GB
+    E = csr.n_edges
+    DAC = cap_of(DA, True) if GA else 0
+    DBC = cap_of(DB, False)
+    c_ = lambda t: t.contiguous() if t is not None else None
+    dCprev = dparams = dconcat = None
+    if mode == 1:
+        dO, dH, dC, dHead = (c_(g) for g in grads)
+        dP = torch.empty(N, 4 * FC, dtype=_f32, device=dev)
+        dCprev = torch.empty(N, FC, dtype=_f32, device=dev) if (Cp is not None and ctx.needs_input_grad[4]) else None
+        dparams = torch.zeros(13, FC, dtype=_f32, device=dev)
+        _lib.call("qmp_lstm_gates_bwd", N, FC, gates, Craw, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps), dH, dC,
+                  dO, dHead, HEADW, dP, 4 * FC, dCprev, dparams)
+        if dHead is not None and ctx.concat_shape is not None and ctx.needs_input_grad[6]:
+            dconcat = dHead[:, FC].reshape(ctx.concat_shape).clone()
+        lddp = 4 * FC
+    else:
+        dP = c_(grads[0])
+        if relu_out:
+            dP = dP.clone()
+            _lib.call("qmp_relu_mask", out_relu, dP, dP.numel())
+        lddp = NC * C
+
+    need_dxa = GA > 0 and ctx.needs_input_grad[0]
+    need_dxb = ctx.needs_input_grad[2]
+    ds = torch.empty(max(E, 1), NC, dtype=_f32, device=dev)
+    ZsA = dUsA = None
+    if GA:
+        ZsA = torch.empty(N, GA, DAC + 4, dtype=_f32, device=dev)
+        dUsA = torch.empty(N, GA, DAC + 4, dtype=_f32, device=dev)
+    ZsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
+    dUsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
+    dxa = torch.empty_like(xa) if need_dxa else None
+    dxb = torch.empty_like(xb) if need_dxb else None
+    pa = bwd_pack(wa, DAC) if GA else None
+    pb = bwd_pack(wb, DBC)
+    lda = xa.shape[1] if xa is not None else 0
+    ldb = xb.shape[1]
+    _lib.call("qmp_fused_bwd_target", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda, DA, GA, pa, xb, ldb, DB, GB,
+              int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, ZsA, dUsA, ZsB, dUsB, dxa, dxb, float(drop_p),
+              int(seed))
+    if need_dxa or need_dxb:
+        _lib.call("qmp_fused_bwd_source", N, csr.out_ptr, csr.out_dst, csr.out_kin, xa, lda, DA, GA, pa, xb, ldb, DB, GB,
+                  int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, dxa, dxb, float(drop_p), int(seed))
+
+    gwa = torch.zeros_like(wa) if GA else None
+    gwb = torch.zeros_like(wb)
+    if mode == 1:
+        if GA:
+            _weight_grads(gwa, DAC, DA, GA, xa, lda, True, ZsA, dUsA, GA * (DAC + 4), dP, lddp, 0, FC, FC, N)
+        if GB == 4:
+            _weight_grads(gwb, DBC, DB, 4, xb, ldb, sharedB, ZsB, dUsB, 4 * (DBC + 4), dP, lddp, 0, FC, FC, N)
+        else:   # 8 convs, one input block each: convs g and 4+g feed gate g
+            W = DBC + 4
+            for half in (0, 1):
+                _weight_grads(gwb[4 * half:], DBC, DB, 4, xb[:, 4 * half * DB:], ldb, False, ZsB[:, 4 * half:], dUsB[:, 4 * half:],
+                              8 * W, dP, lddp, 0, FC, FC, N)
+    else:
+        if GA:
+            _weight_grads(gwa, DAC, DA, GA, xa, lda, True, ZsA, dUsA, GA * (DAC + 4), dP, lddp, 0, C, C, N)
+        _weight_grads(gwb, DBC, DB, GB, xb, ldb, sharedB, ZsB, dUsB, GB * (DBC + 4), dP, lddp, GA * C, C, C, N)
+    return dxa, gwa, dxb, gwb, dCprev, dparams, dconcat, None, None

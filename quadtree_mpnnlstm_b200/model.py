@@ -15,6 +15,7 @@ import torch.nn.functional as F
 
 from .convs import (ChebConv, GATConv, GATv2Conv, GCNConv, MHTransformerConv, TransformerConv, cheb_basis,
                     pack_tconv)
+from . import fused as _fused
 from .graph_csr import get_csr
 from .ops import LstmGatesFn, NodeLinearFn, SpmmFn, TConvFn, next_seed
 
@@ -179,6 +180,36 @@ class GConvLSTM(nn.Module):
             return cur[:, :4 * C] + cur[:, 4 * C:]
         raise NotImplementedError(f"GConvLSTM: convolution_type={kind!r} is not implemented on this path")
 
+    # ---- single-launch path (TransformerConv, hidden 32) ---------------------------------------
+    def _fusable(self):
+        return (_fused.ENABLED and self.convolution_type == 'TransformerConv' and self.out_channels == _fused.FC
+                and self.in_channels <= 8)
+
+    def _fused_cell(self, X, H, C, csr, params, norm_h, norm_c, norm_o, concat, want_head, eps, epoch):
+        """The cell as one fused launch per conv layer (csrc/fused_fwd.inl): layer 0 reads X (4 convs) and H
+        (4 convs); deeper layers read the previous layer's 8 blocks; the last layer ends in the gate epilogue."""
+        S, Cw, Fin = self.n_conv_layers, self.out_channels, self.in_channels
+        p = self.conv_x_i.convolutions[0].dropout if self.training else 0.0
+        seed = (lambda: next_seed()) if p > 0 else (lambda: 0)
+        dac = _fused.cap_of(Fin, True)
+        wa = self._cached(("fa", 0), epoch, lambda: _fused.pack_fused(self._convs("x", 0), dac))
+        wb = self._cached(("fb", 0), epoch, lambda: _fused.pack_fused(self._convs("h", 0), _fused.FC))
+        flags = (bool(norm_h), bool(norm_c), bool(norm_o), bool(want_head), float(eps))
+
+        def cfg(DA, GA, DB, GB, shared, mode):
+            return (DA, GA, DB, GB, shared, mode, False, Cw) + flags + (float(p), seed())
+
+        if S == 1:
+            return _fused.FusedGroupFn.apply(X, wa, H, wb, C, params, concat, csr, cfg(Fin, 4, Cw, 4, True, 1))
+        cur = _fused.FusedGroupFn.apply(X, wa, H, wb, None, None, None, csr, cfg(Fin, 4, Cw, 4, True, 0))
+        for l in range(1, S):
+            w = self._cached(("fb", l), epoch,
+                             lambda: _fused.pack_fused(self._convs("x", l) + self._convs("h", l), _fused.FC))
+            if l < S - 1:
+                cur = _fused.FusedGroupFn.apply(None, None, cur, w, None, None, None, csr, cfg(0, 0, Cw, 8, False, 0))
+            else:
+                return _fused.FusedGroupFn.apply(None, None, cur, w, C, params, concat, csr, cfg(0, 0, Cw, 8, False, 1))
+
     def fused(self, X, edge_index, edge_weight=None, H=None, C=None, norm_h=None, norm_c=None, norm_o=None,
               concat=None, want_head=False, epoch=None):
         """Cell step plus the LayerNorms / head input the encoder and decoder apply to its outputs.
@@ -189,9 +220,12 @@ class GConvLSTM(nn.Module):
         csr = get_csr(edge_index, edge_weight, N)
         if H is None:
             H = torch.zeros(N, self.out_channels, device=X.device)
-        P = self._pre_activations(X, H, csr, epoch)
         params = self._gate_params(epoch, norm_h, norm_c, norm_o)
         eps = norm_h.eps if norm_h is not None else 1e-5
+        if self._fusable():
+            return self._fused_cell(X, H, C, csr, params, norm_h is not None, norm_c is not None, norm_o is not None,
+                                    concat, want_head, eps, epoch)
+        P = self._pre_activations(X, H, csr, epoch)
         return LstmGatesFn.apply(P, C, params, concat, norm_h is not None, norm_c is not None, norm_o is not None,
                                  want_head, eps)
 

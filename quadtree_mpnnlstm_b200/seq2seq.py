@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import fused as _fused
 from .graph_csr import get_csr
 from .graph_functions import Graph, Mesh, flatten, image_to_graph, unflatten
 from .model import CONVOLUTION_KWARGS, CONVOLUTIONS, GConvLSTM, new_epoch
@@ -132,6 +133,15 @@ class Decoder(torch.nn.Module):
         if kind == 'TransformerConv':
             p = self.fc_out1.dropout if self.training else 0.0
             sd = (lambda: next_seed()) if p > 0 else (lambda: 0)
+            if _fused.ENABLED and self.hidden_size == _fused.FC and head.shape[1] == _fused.HEADW:
+                # two fused launches (csrc/fused_fwd.inl): fc_out1 on the 36-wide padded head rows, relu; fc_out2 -> 1
+                w1 = self._cached("ffc1", epoch, lambda: _fused.pack_fused([self.fc_out1], _fused.HEADW))
+                w2 = self._cached("ffc2", epoch, lambda: _fused.pack_fused([self.fc_out2], _fused.FC))
+                tail = (False, False, False, False, 1e-5, float(p))
+                h1 = _fused.FusedGroupFn.apply(None, None, head, w1, None, None, None, csr,
+                                               (0, 0, _fused.HEADW, 1, True, 0, True, _fused.FC) + tail + (sd(),))
+                return _fused.FusedGroupFn.apply(None, None, h1, w2, None, None, None, csr,
+                                                 (0, 0, _fused.FC, 1, True, 0, False, 1) + tail + (sd(),))
             pk1 = self._cached("fc1", epoch, lambda: pack_tconv([self.fc_out1]))
             pk2 = self._cached("fc2", epoch, lambda: pack_tconv([self.fc_out2]))
             h1 = TConvFn.apply(head, *pk1, csr, True, p, sd(), True, None)

@@ -422,6 +422,173 @@ def qmp_relu_mask(y, dy, n):
     d[~(flat(y, n) > 0)] = 0.0
 
 
+# ------------------------------------------------------------------------------------------ fused kernels
+_FC = 32
+
+
+def _unpack_fwd(w, G, DC):
+    w = flat(w, G * ((DC + 2) * DC + DC + 4 + _FC * (DC + 4) + _FC * DC + _FC)).view(G, -1)
+    o1 = (DC + 2) * DC
+    o2 = o1 + DC + 4
+    o3 = o2 + _FC * (DC + 4)
+    o4 = o3 + _FC * DC
+    return (w[:, :o1].view(G, DC + 2, DC), w[:, o1:o2], w[:, o2:o3].view(G, _FC, DC + 4), w[:, o3:o4].view(G, _FC, DC), w[:, o4:])
+
+
+def _unpack_bwd(w, G, DC):
+    tot = (DC + 2) * DC + DC + 4 + DC * (DC + 4) + (DC + 4) * _FC + DC * _FC
+    w = flat(w, G * tot).view(G, -1)
+    o1 = (DC + 2) * DC
+    o2 = o1 + DC + 4
+    o3 = o2 + DC * (DC + 4)
+    o4 = o3 + (DC + 4) * _FC
+    W1, b1 = w[:, :o1].view(G, DC + 2, DC), w[:, o1:o2]
+    W1T, W2T, W3T = w[:, o2:o3].view(G, DC, DC + 4), w[:, o3:o4].view(G, DC + 4, _FC), w[:, o4:].view(G, DC, _FC)
+    assert torch.equal(W1T[:, :, :DC + 2], W1.transpose(1, 2)), "backward pack: W1T is not the transpose of W1"
+    return W1, b1, W2T.transpose(1, 2), W3T.transpose(1, 2)            # W1, b1, W2 [G,32,DC+4], W3 [G,32,DC]
+
+
+def _cap(D, small):
+    return (4 if D <= 4 else 8) if small else (32 if D <= 32 else 36)
+
+
+def _rows_pad(x, N, ld, off, D, DC):
+    v = win(flat(x), (N, D), (ld, 1), off)
+    return torch.cat([v, torch.zeros(N, DC - D)], 1)
+
+
+def _fused_convs(xa, lda, DA, GA, xb, ldb, DB, GB, sharedB):
+    """(conv index, segment, index in segment, x pointer, ld, offset, D, cap)."""
+    out = []
+    for g in range(GA):
+        out.append((g, 0, g, xa, lda, 0, DA, _cap(DA, True)))
+    for g in range(GB):
+        out.append((GA + g, 1, g, xb, ldb, 0 if sharedB else g * DB, DB, _cap(DB, False)))
+    return out
+
+
+def _edge_lists(N, ptr, nbr):
+    p = flat(ptr, N + 1).long()
+    E = int(p[N])
+    return E, torch.repeat_interleave(torch.arange(N), p[1:] - p[:-1]), flat(nbr, E).long()
+
+
+def qmp_fused_fwd(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, mode, relu_out, C, out, ldo, Cprev,
+                  params, norm_h, norm_c, norm_o, eps, gates, Craw, Oout, Hout, Cout, head_in, ldh, concat, logit, mstat, linv,
+                  drop_p, seed):
+    assert drop_p == 0.0
+    NC = GA + GB
+    E, ti, sj = _edge_lists(N, in_ptr, in_src)
+    eattr = flat(ea, 2 * E).view(E, 2) if ea is not None else torch.zeros(E, 2)
+    packs = {0: _unpack_fwd(wa, GA, _cap(DA, True)) if GA else None, 1: _unpack_fwd(wb, GB, _cap(DB, False))}
+    lg, ms, li = flat(logit, max(E, 1) * NC).view(-1, NC), flat(mstat, N * NC).view(N, NC), flat(linv, N * NC).view(N, NC)
+    nslots = 4 if mode == 1 else NC
+    P = torch.zeros(N, nslots, _FC)
+    for (c, seg, g, xp, ld, off, D, DC) in _fused_convs(xa, lda, DA, GA, xb, ldb, DB, GB, sharedB):
+        W1, b1, W2, W3, b3 = (t[g] for t in packs[seg])
+        x = _rows_pad(xp, N, ld, off, D, DC)
+        u = x @ W1[:DC].T + b1[:DC]
+        w = x @ W1[DC:].T + b1[DC:DC + 2]
+        s = (u[ti] * x[sj]).sum(-1) + (w[ti] * eattr).sum(-1)
+        lg[:E, c] = s
+        m = torch.full((N,), -math.inf).scatter_reduce(0, ti, s, "amax", include_self=True)
+        p = (s - m[ti]).exp()
+        l = torch.zeros(N).index_add(0, ti, p)
+        inv = torch.where(l > 0, 1 / l, torch.zeros_like(l))
+        al = p * inv[ti]
+        z = torch.zeros(N, DC + 4)
+        z[:, :DC] = torch.zeros(N, DC).index_add(0, ti, al[:, None] * x[sj])
+        z[:, DC:DC + 2] = torch.zeros(N, 2).index_add(0, ti, al[:, None] * eattr)
+        z[:, DC + 2] = torch.zeros(N).index_add(0, ti, al)
+        ms[:, c], li[:, c] = m, inv
+        slot = (c if c < GA else (c - GA) % 4) if mode == 1 else c
+        P[:, slot] += z @ W2.T + x @ W3.T + b3
+    if mode == 1:
+        Pf = P.reshape(N, 4 * _FC).contiguous()
+        qmp_lstm_gates_fwd(N, _FC, Pf, 4 * _FC, Cprev, params, norm_h, norm_c, norm_o, eps, gates, Craw, Oout, Hout, Cout,
+                           head_in, ldh, concat)
+        if head_in is not None and ldh > _FC + 1:
+            rows(head_in, N, ldh, ldh)[:, _FC + 1:] = 0.0
+    else:
+        o = torch.relu(P) if relu_out else P
+        win(flat(out), (N, NC, C), (ldo, C, 1)).copy_(o[:, :, :C])
+
+
+def _dP_of(dP, lddp, N, mode, C, c, GA):
+    if mode == 1:
+        slot = c if c < GA else (c - GA) % 4
+        return win(flat(dP), (N, _FC), (lddp, 1), slot * _FC)
+    v = win(flat(dP), (N, C), (lddp, 1), c * C)
+    return torch.cat([v, torch.zeros(N, _FC - C)], 1)
+
+
+def qmp_fused_bwd_target(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, mode, C, dP, lddp, logit, mstat,
+                         linv, ds, ZsA, dUsA, ZsB, dUsB, dxa, dxb, drop_p, seed):
+    NC = GA + GB
+    E, ti, sj = _edge_lists(N, in_ptr, in_src)
+    eattr = flat(ea, 2 * E).view(E, 2) if ea is not None else torch.zeros(E, 2)
+    packs = {0: _unpack_bwd(wa, GA, _cap(DA, True)) if GA else None, 1: _unpack_bwd(wb, GB, _cap(DB, False))}
+    lg, ms, li = flat(logit, max(E, 1) * NC).view(-1, NC), flat(mstat, N * NC).view(N, NC), flat(linv, N * NC).view(N, NC)
+    dsv = flat(ds, max(E, 1) * NC).view(-1, NC)
+    first = {0: True, 1: True}
+    for (c, seg, g, xp, ld, off, D, DC) in _fused_convs(xa, lda, DA, GA, xb, ldb, DB, GB, sharedB):
+        W1, b1, W2, W3 = (t[g] for t in packs[seg])
+        G = GA if seg == 0 else GB
+        x = _rows_pad(xp, N, ld, off, D, DC)
+        g32 = _dP_of(dP, lddp, N, mode, C, c, GA)
+        dz = g32 @ W2                                              # [N, DC+4]
+        al = (lg[:E, c] - ms[ti, c]).exp() * li[ti, c]
+        dal = (dz[ti, :DC] * x[sj]).sum(-1) + (dz[ti, DC:DC + 2] * eattr).sum(-1) + dz[ti, DC + 2]
+        t = torch.zeros(N).index_add(0, ti, al * dal)
+        d = al * (dal - t[ti])
+        dsv[:E, c] = d
+        du = torch.zeros(N, DC + 4)
+        du[:, :DC] = torch.zeros(N, DC).index_add(0, ti, d[:, None] * x[sj])
+        du[:, DC:DC + 2] = torch.zeros(N, 2).index_add(0, ti, d[:, None] * eattr)
+        z = torch.zeros(N, DC + 4)
+        z[:, :DC] = torch.zeros(N, DC).index_add(0, ti, al[:, None] * x[sj])
+        z[:, DC:DC + 2] = torch.zeros(N, 2).index_add(0, ti, al[:, None] * eattr)
+        z[:, DC + 2] = torch.zeros(N).index_add(0, ti, al)
+        Zs, dUs = (ZsA, dUsA) if seg == 0 else (ZsB, dUsB)
+        win(flat(Zs), (N, DC + 4), (G * (DC + 4), 1), g * (DC + 4)).copy_(z)
+        win(flat(dUs), (N, DC + 4), (G * (DC + 4), 1), g * (DC + 4)).copy_(du)
+        dxp = dxa if seg == 0 else dxb
+        if dxp is not None:
+            dxs = (g32 @ W3 + du[:, :DC + 2] @ W1)[:, :D]
+            dst = win(flat(dxp), (N, D), (ld, 1), off)
+            shared = seg == 0 or sharedB
+            if shared and not first[seg]:
+                dst.add_(dxs)
+            else:
+                dst.copy_(dxs)
+            first[seg] = False
+
+
+def qmp_fused_bwd_source(N, out_ptr, out_dst, out_kin, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, mode, C, dP, lddp, logit,
+                         mstat, linv, ds, dxa, dxb, drop_p, seed):
+    NC = GA + GB
+    p = flat(out_ptr, N + 1).long()
+    E = int(p[N])
+    ti, kin = flat(out_dst, E).long(), flat(out_kin, E).long()
+    sj = torch.repeat_interleave(torch.arange(N), p[1:] - p[:-1])
+    packs = {0: _unpack_bwd(wa, GA, _cap(DA, True)) if GA else None, 1: _unpack_bwd(wb, GB, _cap(DB, False))}
+    lg, ms, li = flat(logit, max(E, 1) * NC).view(-1, NC), flat(mstat, N * NC).view(N, NC), flat(linv, N * NC).view(N, NC)
+    dsv = flat(ds, max(E, 1) * NC).view(-1, NC)
+    for (c, seg, g, xp, ld, off, D, DC) in _fused_convs(xa, lda, DA, GA, xb, ldb, DB, GB, sharedB):
+        dxp = dxa if seg == 0 else dxb
+        if dxp is None:
+            continue
+        W1, b1, W2, W3 = (t[g] for t in packs[seg])
+        x = _rows_pad(xp, N, ld, off, D, DC)
+        g32 = _dP_of(dP, lddp, N, mode, C, c, GA)
+        al = (lg[kin, c] - ms[ti, c]).exp() * li[ti, c]
+        a = torch.zeros(N, _FC).index_add(0, sj, al[:, None] * g32[ti])
+        b = torch.zeros(N, DC).index_add(0, sj, dsv[kin, c][:, None] * x[ti])
+        sds = torch.zeros(N).index_add(0, sj, dsv[kin, c])
+        contrib = a @ W2[:, :DC] + b @ W1[:DC].T + sds[:, None] * b1[:DC]
+        win(flat(dxp), (N, D), (ld, 1), off).add_(contrib[:, :D])
+
+
 # ------------------------------------------------------------------------------------------ install
 class Emulated:
     """Context manager: route ``_lib.call`` to the functions above and let CPU tensors through."""
@@ -433,6 +600,7 @@ class Emulated:
         table = globals()
 
         def call(name, *args):
+            _lib.CALL_COUNTS[name] = _lib.CALL_COUNTS.get(name, 0) + 1
             table[name](*args)
 
         class _FakeLib:
