@@ -48,6 +48,8 @@ SIGNATURES = {
     "qmp_fused_fwd": "ippppiiippiiiipiiipippiiifppppppippppfup",
     "qmp_fused_bwd_target": "ippppiiippiiiipiipippppppppppfup",
     "qmp_fused_bwd_source": "ippppiiippiiiipiipippppppfup",
+    "qmp_fused_wgrad": "ipiiipiiiiiipippppppp",
+    "qmp_tc_probe2": "pppiiip",
 }
 
 
@@ -59,6 +61,7 @@ KERNELS_PER_CALL = {
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
     "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
+    "qmp_fused_wgrad": 1,
 }
 CALL_COUNTS = {}
 

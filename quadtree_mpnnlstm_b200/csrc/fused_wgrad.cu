@@ -1,0 +1,296 @@
+// Weight gradients of a fused conv layer group (counterpart of fused_fwd / fused_bwd) in ONE launch, on tcgen05.
+//
+// For every conv c of the group the gradient of its packed weights (layout: fused.cuh) is a reduction over the
+// mesh nodes of outer products of per-node rows that the backward target kernel has already produced:
+//
+//     gW1 [(DC+2) x DC] = sum_i dU_i (x) x_i        gb1 = sum_i dU_i              dU = [du | dw]  (DC+4, zero padded)
+//     gW2 [32 x (DC+4)] = sum_i g_i  (x) Z_i                                       Z  = [z | ze | zs | 0]
+//     gW3 [32 x DC]     = sum_i g_i  (x) x_i        gb3 = sum_i g_i               g  = dP rows of the conv's gate
+//
+// i.e. one "TN" GEMM per conv with the node index as the reduction dimension K:
+//     D [M x Nb] = A B^T,   A [m, i] = [dU_i | g_i][m]  (M = DC + 36 rows used of 128),   B [n, i] = [x_i | 1 0 0 0 | Z_i][n]
+// Both operands are node-major in memory (the transposes of what a K-major MMA wants):
+//   * A goes through TENSOR MEMORY: thread m reads component m of 64 consecutive nodes (a warp reads 128 contiguous
+//     bytes per node) and writes them to TMEM lane m with tcgen05.st -- lane = M row, column = node -- which is the
+//     K-major A operand of tcgen05.mma's TMEM-A form.  No shared memory, no transposition code.
+//   * B goes through shared memory in the canonical K-major no-swizzle layout (tc.cuh): a thread loads the same
+//     16-byte column chunk of 4 consecutive nodes, transposes the 4 x 4 block in registers and stores four 16-byte
+//     (n, 4 nodes) pieces; the 8-row block stride is padded by 16 bytes so the stores of a quarter-warp hit 32 banks.
+// (The MN-major descriptor form that would take both operands as they lie returns zeros for kind::tf32 with the
+// no-swizzle layout on this part -- scripts/tc_probe2.py variants 1/3 -- so it is not used.)
+// 3xTF32 (tc.cuh): A_hi B_hi + A_lo B_hi + A_hi B_lo, fp32 accumulation in TMEM.  A CTA owns one conv and a strided
+// set of 64-node tiles, accumulates all of them in TMEM and flushes once with atomics: the node rows are read exactly
+// once and nothing else touches memory.
+#include "common.cuh"
+#include "fused.cuh"
+#include "tc.cuh"
+
+namespace qmp {
+
+constexpr int WG_KT = 64;                       // nodes per tile (K of the tile)
+constexpr int WG_KC = WG_KT / 4;                // 16-byte K chunks per B row
+constexpr int WG_SBO = WG_KC * 128 + 16;        // bytes between consecutive 8-row blocks of B (padded)
+constexpr int WG_MAXCONV = 12;
+constexpr int WG_BIT = 3;                       // B items per thread: 16 node groups x (<= 20 chunks) / 128 threads
+constexpr uint32_t WG_TMEM_COLS = 256, WG_AHI = 128, WG_ALO = 192;
+
+struct WgConv {
+    const float* x; const float* zs; const float* dus; const float* g; float* gw;
+    int ldx, ldz, ldg, gvalid, D, DC, cta0, nctas;
+};
+struct WgArgs {
+    int N, nconv;
+    WgConv c[WG_MAXCONV];
+};
+
+__device__ __forceinline__ float4 wg_load4(const float* __restrict__ p, int nvalid, bool vec) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nvalid >= 4 && vec) return __ldg(reinterpret_cast<const float4*>(p));
+    if (nvalid > 0) v.x = __ldg(p);
+    if (nvalid > 1) v.y = __ldg(p + 1);
+    if (nvalid > 2) v.z = __ldg(p + 2);
+    if (nvalid > 3) v.w = __ldg(p + 3);
+    return v;
+}
+
+__device__ __forceinline__ void wg_st_split(uint8_t* hi, uint8_t* lo, uint32_t off, float a, float b, float c, float d) {
+    float4 h, l;
+    tc::split_tf32(a, h.x, l.x);
+    tc::split_tf32(b, h.y, l.y);
+    tc::split_tf32(c, h.z, l.z);
+    tc::split_tf32(d, h.w, l.w);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+}
+
+__global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant__ WgArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int t = threadIdx.x, warp = t >> 5;
+    int ci = 0;
+    while (ci + 1 < a.nconv && (int)blockIdx.x >= a.c[ci].cta0 + a.c[ci].nctas) ++ci;
+    const WgConv& cv = a.c[ci];
+    const int DC = cv.DC, D = cv.D;
+    const int qx = DC / 4, qb = qx + 1 + (DC + 4) / 4;           // B chunks: x | ones | Z
+    const int NB = (qb * 4 + 15) / 16 * 16;
+    uint8_t* b_hi = smem;
+    uint8_t* b_lo = smem + (NB / 8) * WG_SBO;
+
+    if (t == 0) {
+        tc::mbar_init(&bar, 1);
+        tc::fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, WG_TMEM_COLS);
+    for (int idx = t; idx < 2 * (NB / 8) * WG_SBO / 16; idx += 128) reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t idesc = tc::make_idesc_tf32(128, NB);
+
+    // A: this thread's component of [dU | g]
+    const float* a_src = nullptr;
+    int a_ld = 0;
+    if (t < DC + 4) { a_src = cv.dus + t; a_ld = cv.ldz; }
+    else if (t < DC + 4 + FC && t - (DC + 4) < cv.gvalid) { a_src = cv.g + (t - (DC + 4)); a_ld = cv.ldg; }
+    const bool vx = (cv.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cv.x) & 15) == 0);
+    const int ntiles = (a.N + WG_KT - 1) / WG_KT;
+    const int items = (WG_KT / 4) * qb;
+
+    float va[WG_KT];
+    float4 vb[WG_BIT][4];
+    auto fetch = [&](int tile) {
+        const int n0 = tile * WG_KT;
+#pragma unroll
+        for (int k = 0; k < WG_KT; ++k) {
+            const int i = n0 + k;
+            va[k] = (a_src != nullptr && i < a.N) ? __ldg(a_src + (size_t)i * a_ld) : 0.f;
+        }
+#pragma unroll
+        for (int it = 0; it < WG_BIT; ++it) {
+            const int idx = t + 128 * it;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vb[it][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < items) {
+                const int kg = idx / qb, q = idx - kg * qb;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = n0 + kg * 4 + j;
+                    if (i < a.N) {
+                        if (q < qx) vb[it][j] = wg_load4(cv.x + (size_t)i * cv.ldx + q * 4, D - q * 4, vx);
+                        else if (q == qx) vb[it][j].x = 1.f;
+                        else vb[it][j] = wg_load4(cv.zs + (size_t)i * cv.ldz + (q - qx - 1) * 4, 4, true);
+                    }
+                }
+            }
+        }
+    };
+    auto stage = [&]() {
+        // A -> TMEM lane t, columns = nodes (hi at WG_AHI, lo at WG_ALO)
+#pragma unroll
+        for (int k0 = 0; k0 < WG_KT; k0 += 8) {
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float hi, lo;
+                tc::split_tf32(va[k0 + i], hi, lo);
+                h[i] = __float_as_uint(hi);
+                l[i] = __float_as_uint(lo);
+            }
+            tc::tmem_st8(lane_base + WG_AHI + (uint32_t)k0, h);
+            tc::tmem_st8(lane_base + WG_ALO + (uint32_t)k0, l);
+        }
+        // B -> shared memory, K-major: element (n, node k) at (n/8)*SBO + (k/4)*128 + (n%8)*16 + (k%4)*4
+#pragma unroll
+        for (int it = 0; it < WG_BIT; ++it) {
+            const int idx = t + 128 * it;
+            if (idx < items) {
+                const int kg = idx / qb, q = idx - kg * qb;
+                const int n = q * 4;
+                const uint32_t base = (uint32_t)((n >> 3) * WG_SBO + kg * 128 + (n & 7) * 16);
+                wg_st_split(b_hi, b_lo, base, vb[it][0].x, vb[it][1].x, vb[it][2].x, vb[it][3].x);
+                wg_st_split(b_hi, b_lo, base + 16, vb[it][0].y, vb[it][1].y, vb[it][2].y, vb[it][3].y);
+                wg_st_split(b_hi, b_lo, base + 32, vb[it][0].z, vb[it][1].z, vb[it][2].z, vb[it][3].z);
+                wg_st_split(b_hi, b_lo, base + 48, vb[it][0].w, vb[it][1].w, vb[it][2].w, vb[it][3].w);
+            }
+        }
+        tc::tmem_st_wait();
+    };
+
+    uint32_t parity = 0, acc = 0;
+    int tile = (int)blockIdx.x - cv.cta0;
+    if (tile < ntiles) fetch(tile);
+    for (; tile < ntiles; tile += cv.nctas) {
+        if (acc) {                       // the previous tile's MMAs must have read the operands before they are overwritten
+            tc::mbar_wait(&bar, parity);
+            parity ^= 1;
+            tc::fence_after_sync();
+        }
+        stage();
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        if (t == 0) {
+#pragma unroll 1
+            for (int ks = 0; ks < WG_KT / 8; ++ks) {
+                const uint64_t dbh = tc::make_desc(tc::smem_u32(b_hi) + (uint32_t)ks * 256, 128, WG_SBO);
+                const uint64_t dbl = tc::make_desc(tc::smem_u32(b_lo) + (uint32_t)ks * 256, 128, WG_SBO);
+                const uint32_t ah = tmem + WG_AHI + (uint32_t)ks * 8, al = tmem + WG_ALO + (uint32_t)ks * 8;
+                tc::mma_tf32_ts(tmem, ah, dbh, idesc, (acc | ks) ? 1u : 0u);
+                tc::mma_tf32_ts(tmem, al, dbh, idesc, 1);
+                tc::mma_tf32_ts(tmem, ah, dbl, idesc, 1);
+            }
+            tc::commit(&bar);
+        }
+        acc = 1;
+        if (tile + cv.nctas < ntiles) fetch(tile + cv.nctas);     // next tile's rows fly while the tensor core works
+    }
+    if (acc) {
+        tc::mbar_wait(&bar, parity);
+        tc::fence_after_sync();
+        // flush: thread t owns accumulator row t.  Pack offsets (fused.cuh): W1 | b1 | W2 | W3 | b3
+        const int o1 = (DC + 2) * DC, o2 = o1 + DC + 4, o3 = o2 + FC * (DC + 4), o4 = o3 + FC * DC;
+        const bool du_row = t < DC + 2;
+        const int o = t - (DC + 4);
+        const bool g_row = o >= 0 && o < FC && o < cv.gvalid;
+        float* gw = cv.gw;
+        for (int c0 = 0; c0 < qb * 4; c0 += 8) {
+            float r[8];
+            tc::tmem_ld8(lane_base + (uint32_t)c0, r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int col = c0 + i;
+                if (col < DC) {
+                    if (du_row) atomicAdd(gw + t * DC + col, r[i]);
+                    else if (g_row) atomicAdd(gw + o3 + o * DC + col, r[i]);
+                } else if (col == DC) {
+                    if (du_row) atomicAdd(gw + o1 + t, r[i]);
+                    else if (g_row) atomicAdd(gw + o4 + o, r[i]);
+                } else if (col >= DC + 4 && col < 2 * DC + 8) {
+                    if (g_row) atomicAdd(gw + o2 + o * (DC + 4) + (col - DC - 4), r[i]);
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, WG_TMEM_COLS);
+}
+
+}  // namespace qmp
+using namespace qmp;
+
+// Weight gradients of one fused layer group (see the top of this file): accumulates into gwa [GA, TOTAL(cap DA)] /
+// gwb [GB, TOTAL(cap DB)] (forward pack layout, caller zero-initialises).  Arguments as qmp_fused_bwd_target, whose
+// outputs ZsA / dUsA [N, GA, capA+4] and ZsB / dUsB [N, GB, capB+4] are this kernel's inputs.
+QMP_API int qmp_fused_wgrad(int N, const float* xa, int lda, int DA, int GA, const float* xb, int ldb, int DB, int GB,
+                            int sharedB, int mode, int C, const float* dP, int lddp, const float* ZsA, const float* dUsA,
+                            const float* ZsB, const float* dUsB, float* gwa, float* gwb, void* stream) {
+    if (N <= 0) return 0;
+    const int NC = GA + GB;
+    QMP_REQUIRE(NC >= 1 && NC <= WG_MAXCONV, "qmp_fused_wgrad: at most %d convs per group", WG_MAXCONV);
+    QMP_REQUIRE(DB >= 1 && DB <= 36 && DA >= 0 && DA <= 8 && C >= 1 && C <= FC, "qmp_fused_wgrad: unsupported sizes");
+    const int dac = (GA == 0) ? 0 : (DA <= 4 ? 4 : 8);
+    const int dbc = (DB <= 32) ? 32 : 36;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        QMP_CUDA(cudaGetDevice(&dev));
+        QMP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    WgArgs a{};
+    a.N = N;
+    a.nconv = NC;
+    const int ntiles = cdiv(N, WG_KT);
+    int wsum = 0, w[WG_MAXCONV], nbmax = 16;
+    for (int c = 0; c < NC; ++c) {
+        const int DC = c < GA ? dac : dbc;
+        w[c] = 16 + DC / 4 + 1 + (DC + 4) / 4;
+        wsum += w[c];
+        const int nb = ((DC / 4 + 1 + (DC + 4) / 4) * 4 + 15) / 16 * 16;
+        nbmax = nb > nbmax ? nb : nbmax;
+    }
+    const int budget = 2 * n_sm;
+    int cta = 0;
+    for (int c = 0; c < NC; ++c) {
+        WgConv& v = a.c[c];
+        const bool segA = c < GA;
+        const int g = segA ? c : c - GA;
+        v.DC = segA ? dac : dbc;
+        v.D = segA ? DA : DB;
+        const int G = segA ? GA : GB, W = v.DC + 4;
+        v.x = segA ? xa : xb + (sharedB ? 0 : (size_t)g * DB);
+        v.ldx = segA ? lda : ldb;
+        v.zs = (segA ? ZsA : ZsB) + (size_t)g * W;
+        v.dus = (segA ? dUsA : dUsB) + (size_t)g * W;
+        v.ldz = G * W;
+        if (mode == 1) {
+            v.g = dP + (size_t)(segA ? c : (g & 3)) * FC;
+            v.gvalid = FC;
+        } else {
+            v.g = dP + (size_t)c * C;
+            v.gvalid = C;
+        }
+        v.ldg = lddp;
+        const int total = (v.DC + 2) * v.DC + (v.DC + 4) + FC * (v.DC + 4) + FC * v.DC + FC;
+        v.gw = (segA ? gwa : gwb) + (size_t)g * total;
+        int n = (int)((long long)budget * w[c] / wsum);
+        n = n < 1 ? 1 : (n > ntiles ? ntiles : n);
+        v.cta0 = cta;
+        v.nctas = n;
+        cta += n;
+    }
+    const size_t smem = (size_t)2 * (nbmax / 8) * WG_SBO;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        QMP_CUDA(cudaFuncSetAttribute(fused_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    fused_wgrad_kernel<<<cta, 128, smem, (cudaStream_t)stream>>>(a);
+    QMP_LAUNCH_CHECK("fused_wgrad_kernel");
+    return 0;
+}

@@ -14,6 +14,7 @@ from .convs import pack_tconv
 FC = 32
 HEADW = 36          # decoder-head input rows: 32 normalised outputs | concat layer | 3 zero pad columns (16-byte rows)
 ENABLED = True      # tests flip this to cross-check the fused kernels against the modular ones
+TC_WGRAD = True     # weight gradients: one tcgen05 launch per group (False: ten FFMA reductions, the cross-check)
 _f32 = torch.float32
 
 

@@ -113,7 +113,11 @@ def fused_group_backward(ctx, *grads):
 
     gwa = torch.zeros_like(wa) if GA else None
     gwb = torch.zeros_like(wb)
-    if mode == 1:
+    from . import fused as _f
+    if _f.TC_WGRAD:
+        _lib.call("qmp_fused_wgrad", N, xa, lda, DA, GA, xb, ldb, DB, GB, int(sharedB), mode, C, dP, lddp, ZsA, dUsA, ZsB,
+                  dUsB, gwa, gwb)
+    elif mode == 1:
         if GA:
             _weight_grads(gwa, DAC, DA, GA, xa, lda, True, ZsA, dUsA, GA * (DAC + 4), dP, lddp, 0, FC, FC, N)
         if GB == 4:

@@ -1,0 +1,24 @@
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from quadtree_mpnnlstm_b200 import _lib
+torch.manual_seed(0)
+for (N, K) in [(16, 8), (32, 64), (80, 64)]:
+    for variant in (0, 1, 2, 3, 4):
+        if variant < 4:
+            A = torch.randn(K, 128, device="cuda"); B = torch.randn(K, N, device="cuda")
+            ref = A.double().T @ B.double()
+        else:
+            A = torch.randn(128, K, device="cuda"); B = torch.randn(N, K, device="cuda")
+            ref = A.double() @ B.double().T
+        C = torch.full((128, N), float("nan"), device="cuda")
+        _lib.call("qmp_tc_probe2", A, B, C, N, K, variant)
+        torch.cuda.synchronize()
+        err = ((C.double() - ref).abs().max() / ref.abs().max()).item()
+        nz = int((C != 0).sum())
+        print(f"N={N} K={K} variant={variant}: rel err {err:.3e} nonzero={nz}/{C.numel()} nan={int(torch.isnan(C).sum())}", flush=True)
+        if variant < 4 and err > 1e-2 and K == 8 and N == 16:
+            # diagnose: which (m, n) of ref does C[i, j] correlate with?
+            Cd = C.double().cpu(); R = ref.cpu()
+            print("  C[0:4,0:4]=", Cd[:4, :4].tolist())
+            print("  ref[0:4,0:4]=", R[:4, :4].tolist())

@@ -589,6 +589,28 @@ def qmp_fused_bwd_source(N, out_ptr, out_dst, out_kin, xa, lda, DA, GA, wa, xb, 
         win(flat(dxp), (N, D), (ld, 1), off).add_(contrib[:, :D])
 
 
+def qmp_fused_wgrad(N, xa, lda, DA, GA, xb, ldb, DB, GB, sharedB, mode, C, dP, lddp, ZsA, dUsA, ZsB, dUsB, gwa, gwb):
+    for (c, seg, g, xp, ld, off, D, DC) in _fused_convs(xa, lda, DA, GA, xb, ldb, DB, GB, sharedB):
+        G = GA if seg == 0 else GB
+        W = DC + 4
+        Zs, dUs, gw = (ZsA, dUsA, gwa) if seg == 0 else (ZsB, dUsB, gwb)
+        z = win(flat(Zs), (N, W), (G * W, 1), g * W)
+        du = win(flat(dUs), (N, W), (G * W, 1), g * W)
+        x = _rows_pad(xp, N, ld, off, D, DC)
+        g32 = _dP_of(dP, lddp, N, mode, C, c, GA)
+        total = (DC + 2) * DC + DC + 4 + _FC * (DC + 4) + _FC * DC + _FC
+        o1 = (DC + 2) * DC
+        o2 = o1 + DC + 4
+        o3 = o2 + _FC * (DC + 4)
+        o4 = o3 + _FC * DC
+        row = flat(gw, G * total).view(G, total)[g]
+        row[:o1] += (du[:, :DC + 2].T @ x).reshape(-1)
+        row[o1:o1 + DC + 2] += du[:, :DC + 2].sum(0)
+        row[o2:o3] += (g32.T @ z).reshape(-1)
+        row[o3:o4] += (g32.T @ x).reshape(-1)
+        row[o4:] += g32.sum(0)
+
+
 # ------------------------------------------------------------------------------------------ install
 class Emulated:
     """Context manager: route ``_lib.call`` to the functions above and let CPU tensors through."""

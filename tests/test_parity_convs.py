@@ -187,3 +187,58 @@ def test_tcgen05_gemm_probe():
             errs.append(rel_err(C, ref))
         assert errs[0] < 5e-6, (M, N, K, errs)
         assert 5e-5 < errs[1] < 5e-3, (M, N, K, errs)
+
+
+@pytest.mark.parametrize("N,DA,GA,DB,GB,shared,mode,C", [(1000, 4, 4, 32, 4, 1, 1, 32), (4133, 8, 4, 32, 4, 1, 0, 32),
+                                                        (777, 0, 0, 32, 8, 0, 1, 32), (2048, 0, 0, 36, 1, 1, 0, 32),
+                                                        (300, 0, 0, 32, 1, 1, 0, 1), (50, 6, 4, 32, 4, 1, 1, 32)])
+def test_fused_wgrad_kernel(be, N, DA, GA, DB, GB, shared, mode, C):
+    """qmp_fused_wgrad (tcgen05, MN-major 3xTF32 reduction over the nodes) against float64 outer-product sums."""
+    from quadtree_mpnnlstm_b200 import _lib
+    torch.manual_seed(N)
+    dev = be.device
+    dac = 0 if GA == 0 else (4 if DA <= 4 else 8)
+    dbc = 32 if DB <= 32 else 36
+    NC = GA + GB
+    tot = lambda dc: (dc + 2) * dc + dc + 4 + 32 * (dc + 4) + 32 * dc + 32
+    xa = torch.randn(N, DA, device=dev) if GA else None
+    xb = torch.randn(N, DB if shared else GB * DB, device=dev)
+    lddp = 128 if mode == 1 else NC * C
+    dP = torch.randn(N, lddp, device=dev)
+
+    def rows(G, dc, nvalid):
+        t = torch.randn(N, G, dc + 4, device=dev)
+        t[:, :, nvalid:] = 0
+        return t
+    ZsA, dUsA = (rows(GA, dac, dac + 3), rows(GA, dac, dac + 2)) if GA else (None, None)
+    ZsB, dUsB = rows(GB, dbc, dbc + 3), rows(GB, dbc, dbc + 2)
+    gwa = torch.zeros(GA, tot(dac), device=dev) if GA else None
+    gwb = torch.zeros(GB, tot(dbc), device=dev)
+    _lib.call("qmp_fused_wgrad", N, xa, DA, DA, GA, xb, xb.shape[1], DB, GB, shared, mode, C, dP, lddp, ZsA, dUsA, ZsB, dUsB,
+              gwa, gwb)
+    for c in range(NC):
+        segA = c < GA
+        g = c if segA else c - GA
+        dc, D = (dac, DA) if segA else (dbc, DB)
+        x = (xa if segA else (xb if shared else xb[:, g * DB:(g + 1) * DB])).double().cpu()
+        x = torch.cat([x, torch.zeros(N, dc - D, dtype=torch.float64)], 1)
+        z = (ZsA if segA else ZsB)[:, g].double().cpu()
+        du = (dUsA if segA else dUsB)[:, g].double().cpu()
+        if mode == 1:
+            slot = c if segA else g % 4
+            gg = dP[:, slot * 32:(slot + 1) * 32].double().cpu()
+        else:
+            gg = torch.cat([dP[:, c * C:(c + 1) * C].double().cpu(), torch.zeros(N, 32 - C, dtype=torch.float64)], 1)
+        o1 = (dc + 2) * dc
+        o2 = o1 + dc + 4
+        o3 = o2 + 32 * (dc + 4)
+        o4 = o3 + 32 * dc
+        ref = torch.zeros(tot(dc), dtype=torch.float64)
+        ref[:o1] = (du[:, :dc + 2].T @ x).reshape(-1)
+        ref[o1:o1 + dc + 2] = du[:, :dc + 2].sum(0)
+        ref[o2:o3] = (gg.T @ z).reshape(-1)
+        ref[o3:o4] = (gg.T @ x).reshape(-1)
+        ref[o4:] = gg.sum(0)
+        got = (gwa if segA else gwb)[g].double().cpu()
+        err = float((got - ref).abs().max() / ref.abs().max())
+        assert err < 2e-5, f"conv {c}: rel err {err}"
