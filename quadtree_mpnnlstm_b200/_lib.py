@@ -50,6 +50,9 @@ SIGNATURES = {
     "qmp_fused_bwd_source": "ippppiiippiiiipiipippppppfup",
     "qmp_fused_wgrad": "ipiiipiiiiiipippppppp",
     "qmp_tc_probe2": "pppiiip",
+    "qmp_tc_probe3": "piiiip",
+    "qmp_fused_fwd_tc": "ippppiiippiiiipiiipippiiifppppppippppfup",
+    "qmp_fused_pack_tc": "piiipp",
 }
 
 
@@ -61,7 +64,7 @@ KERNELS_PER_CALL = {
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
     "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
-    "qmp_fused_wgrad": 1,
+    "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1,
 }
 CALL_COUNTS = {}
 
@@ -93,6 +96,8 @@ def lib():
         L.qmp_quadtree_pyramid_cells.argtypes = [_I, _I, _I]
         L.qmp_set_tensor_cores.restype = _I
         L.qmp_set_tensor_cores.argtypes = [_I]
+        L.qmp_fused_tc_image_bytes.restype = _L
+        L.qmp_fused_tc_image_bytes.argtypes = [_I, _I]
         for name, sig in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = _I
@@ -137,4 +142,4 @@ def call(name, *args):
 
 
 def exported_symbols():
-    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores"] + list(SIGNATURES)
+    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes"] + list(SIGNATURES)

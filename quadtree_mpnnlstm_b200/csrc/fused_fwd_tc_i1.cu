@@ -1,0 +1,4 @@
+#include "fused_fwd_tc.inl"
+namespace qmp {
+template int launch_fwd_tc<0, 36>(const FusedFwdArgs&, cudaStream_t);
+}

@@ -1,0 +1,4 @@
+#include "fused_fwd_tc.inl"
+namespace qmp {
+template int launch_fwd_tc<4, 32>(const FusedFwdArgs&, cudaStream_t);
+}

@@ -1,0 +1,132 @@
+// Building blocks of the tcgen05 versions of the fused cell kernels (fused_fwd_tc / fused_bwd_tc).
+//
+// Thread t of a 128-thread CTA owns node t of a 128-node tile AND tensor-memory lane t.  The dense per-node
+// contractions of a conv (logit projection, value / skip projection and their transposes in the backward pass) are
+// tcgen05.mma kind::tf32 instructions, 3xTF32 split (tc.cuh), whose A operand lives in TENSOR MEMORY: a thread
+// writes its node's row (x_i, z_i, g_i, ...) to its own lane with tcgen05.st and reads the accumulator row back
+// with tcgen05.ld -- no shared-memory tile, no layout shuffling, and the per-node rows never leave the SM between
+// the gather phase and the contraction.  The B operand (the conv's weights, pre-split into hi / lo and laid out in
+// the canonical K-major no-swizzle form by qmp_fused_pack_tc) is streamed through a double-buffered shared-memory
+// slot, one conv at a time.  The edge phase in between (gathers over the CSR, segment softmax, fp32 accumulation)
+// is plain SIMT code on the same thread.
+//
+// TMEM column map of a CTA (256 columns, two CTAs per SM):
+//     [  0,128)  P   accumulators of the conv outputs: 4 gates x 32 (gate mode) or one 32-column block
+//     [128,176)  U   accumulator of the current conv's first contraction (<= 48 columns)
+//     [176,216)  A_hi   the A operand, high parts (<= 40 columns = K)
+//     [216,256)  A_lo   low parts
+#pragma once
+#include "fused.cuh"
+#include "tc.cuh"
+
+namespace qmp {
+
+constexpr uint32_t TC_COLS = 256, TC_P = 0, TC_U = 128, TC_AH = 176, TC_AL = 216;
+
+__host__ __device__ constexpr int tc_pad8(int v) { return (v + 7) / 8 * 8; }
+
+// byte layout of one conv's FORWARD image (B operands in canonical K-major no-swizzle form, SBO = 32 K bytes... see img_off)
+struct TcFwdLayout {
+    int K1, K2, N1, W1H, W1L, W3H, W3L, W2H, W2L, B1, B3, BYTES;
+    __host__ __device__ constexpr TcFwdLayout(int DC)
+        : K1(tc_pad8(DC)), K2(tc_pad8(DC + 4)), N1(DC + 2 <= 16 ? 16 : 48), W1H(0), W1L(W1H + N1 * K1 * 4),
+          W3H(W1L + N1 * K1 * 4), W3L(W3H + FC * K1 * 4), W2H(W3L + FC * K1 * 4), W2L(W2H + FC * K2 * 4),
+          B1(W2L + FC * K2 * 4), B3(B1 + 48 * 4), BYTES(B3 + FC * 4) {}
+};
+
+// byte offset of element (n, k) of a K-major operand with K columns (K % 8 == 0): 8-row x 16-byte core matrices,
+// consecutive K chunks 128 bytes apart (LBO), consecutive 8-row blocks 32 K bytes apart (SBO)
+__host__ __device__ __forceinline__ int img_off(int n, int k, int K) {
+    return (n >> 3) * (32 * K) + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4;
+}
+
+// D[tmem + dcol] (+)= A (TMEM, K columns at TC_AH / TC_AL) * B^T (shared memory, N rows x K, hi / lo), 3xTF32.
+// Called by ONE thread.
+__device__ __forceinline__ void tc_mma3(uint32_t tmem, uint32_t dcol, uint32_t bh_addr, uint32_t bl_addr, int N, int K,
+                                        bool accumulate) {
+    const uint32_t idesc = tc::make_idesc_tf32(128, N);
+    const uint32_t sbo = 32u * (uint32_t)K;
+#pragma unroll 1
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t dbh = tc::make_desc(bh_addr + (uint32_t)ks * 256, 128, sbo);
+        const uint64_t dbl = tc::make_desc(bl_addr + (uint32_t)ks * 256, 128, sbo);
+        const uint32_t ah = tmem + TC_AH + (uint32_t)ks * 8, al = tmem + TC_AL + (uint32_t)ks * 8;
+        tc::mma_tf32_ts(tmem + dcol, ah, dbh, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        tc::mma_tf32_ts(tmem + dcol, al, dbh, idesc, 1);
+        tc::mma_tf32_ts(tmem + dcol, ah, dbl, idesc, 1);
+    }
+}
+
+// this thread's row v[0..K) -> its TMEM lane, split into hi / lo (the A operand of the next tc_mma3)
+template <int K>
+__device__ __forceinline__ void tc_stage_a(uint32_t lane_base, const float (&v)[K]) {
+    static_assert(K % 8 == 0 && K <= 40, "A operand: K multiple of 8, at most 40 columns");
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float hi, lo;
+            tc::split_tf32(v[k0 + i], hi, lo);
+            h[i] = __float_as_uint(hi);
+            l[i] = __float_as_uint(lo);
+        }
+        tc::tmem_st8(lane_base + TC_AH + (uint32_t)k0, h);
+        tc::tmem_st8(lane_base + TC_AL + (uint32_t)k0, l);
+    }
+}
+
+// N8 * 8 accumulator columns of this thread's lane starting at column col
+template <int N8>
+__device__ __forceinline__ void tc_load_cols(uint32_t lane_base, uint32_t col, float (&v)[N8 * 8]) {
+    uint32_t r[N8][8];
+#pragma unroll
+    for (int q = 0; q < N8; ++q) tc::tmem_ld8_nowait(lane_base + col + (uint32_t)q * 8, r[q]);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < N8; ++q)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[q * 8 + i] = __uint_as_float(r[q][i]);
+}
+
+// zero-padded row load into K >= D registers; vec = 16-byte aligned rows with D % 4 == 0
+template <int K>
+__device__ __forceinline__ void tc_load_row(float (&x)[K], const float* __restrict__ p, int D, bool vec, bool valid) {
+    if (vec) {
+#pragma unroll
+        for (int k = 0; k < K; k += 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && k < D) v = __ldg(reinterpret_cast<const float4*>(p + k));
+            x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) x[k] = (valid && k < D) ? __ldg(p + k) : 0.f;
+    }
+}
+
+struct TcCtx {
+    uint8_t* wbuf[2];        // double-buffered weight image slot, filled by bulk copies one conv ahead
+    uint64_t* wfull;         // [2] "image landed" barriers (byte-counted)
+    uint32_t wparity[2];
+    int toggle;              // slot of the current conv
+    uint64_t* bar;           // all MMA groups of this CTA commit here, every commit is waited exactly once
+    uint32_t parity;
+    bool pending;            // a committed group has not been waited yet
+    uint32_t tmem, lane_base;
+};
+
+// one thread: start the bulk copy of a conv's image into slot `buf`
+__device__ __forceinline__ void tc_prefetch_image(TcCtx& cx, int buf, const uint8_t* img, uint32_t bytes) {
+    tc::mbar_expect_tx(cx.wfull + buf, bytes);
+    tc::bulk_g2s(cx.wbuf[buf], img, bytes, cx.wfull + buf);
+}
+
+__device__ __forceinline__ void tc_wait(TcCtx& cx) {
+    tc::mbar_wait(cx.bar, cx.parity);
+    cx.parity ^= 1;
+    cx.pending = false;
+    tc::fence_after_sync();
+}
+
+}  // namespace qmp

@@ -15,6 +15,7 @@ FC = 32
 HEADW = 36          # decoder-head input rows: 32 normalised outputs | concat layer | 3 zero pad columns (16-byte rows)
 ENABLED = True      # tests flip this to cross-check the fused kernels against the modular ones
 TC_WGRAD = True     # weight gradients: one tcgen05 launch per group (False: ten FFMA reductions, the cross-check)
+TC_FWD = True       # forward on tcgen05 (csrc/fused_fwd_tc.inl); False: the fp32-FFMA kernel (csrc/fused_fwd.inl)
 _f32 = torch.float32
 
 
@@ -40,6 +41,35 @@ def pack_fused(convs, DC):
     W3p = F.pad(W3, (0, DC - D, 0, FC - C))
     b3p = F.pad(b3, (0, FC - C))
     return torch.cat([W1p.flatten(1), b1p, W2p.flatten(1), W3p.flatten(1), b3p], dim=1).contiguous()
+
+
+def _pad8(v):
+    return (v + 7) // 8 * 8
+
+
+def tc_image_bytes(DC, kind=0):
+    """Bytes of one conv's weight image (csrc/fused_tc.cuh TcFwdLayout)."""
+    assert kind == 0
+    K1, K2, N1 = _pad8(DC), _pad8(DC + 4), (16 if DC + 2 <= 16 else 48)
+    return 8 * (N1 * K1 + FC * K1 + FC * K2) + 4 * (48 + FC)
+
+
+_img_cache = {}
+
+
+def tc_image(w, DC, kind=0):
+    """[G, image bytes] uint8: the tensor-core image of a padded pack (built by qmp_fused_pack_tc, cached per pack)."""
+    key = (w.data_ptr(), tuple(w.shape), DC, kind, w._version)
+    hit = _img_cache.get(key)
+    if hit is not None and hit[0] is w:
+        return hit[1]
+    G = w.shape[0]
+    img = torch.empty(G, tc_image_bytes(DC, kind), dtype=torch.uint8, device=w.device)
+    _lib.call("qmp_fused_pack_tc", w.detach().contiguous(), G, DC, kind, img)
+    if len(_img_cache) > 64:
+        _img_cache.clear()
+    _img_cache[key] = (w, img)
+    return img
 
 
 class FusedGroupFn(torch.autograd.Function):
@@ -72,9 +102,14 @@ class FusedGroupFn(torch.autograd.Function):
         Cp = Cprev.contiguous() if Cprev is not None else None
         cc = concat.contiguous().reshape(-1) if (want_head and concat is not None) else None
         prm = params.contiguous() if params is not None else None
-        _lib.call("qmp_fused_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in,
-                  xa, xa.shape[1] if xa is not None else 0, DA, GA, wa,
-                  xb, xb.shape[1], DB, GB, int(sharedB), wb,
+        entry, wa_k, wb_k = "qmp_fused_fwd", wa, wb
+        if TC_FWD:
+            entry = "qmp_fused_fwd_tc"
+            wa_k = tc_image(wa, cap_of(DA, True)) if GA else None
+            wb_k = tc_image(wb, cap_of(DB, False))
+        _lib.call(entry, N, csr.in_ptr, csr.in_src, csr.edge_attr_in,
+                  xa, xa.shape[1] if xa is not None else 0, DA, GA, wa_k,
+                  xb, xb.shape[1], DB, GB, int(sharedB), wb_k,
                   mode, int(relu_out), C, out, NC * C, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps),
                   gates, Craw, O, H, Cn, head, HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
         ctx.save_for_backward(xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out if relu_out else None)

@@ -589,6 +589,26 @@ def qmp_fused_bwd_source(N, out_ptr, out_dst, out_kin, xa, lda, DA, GA, wa, xb, 
         win(flat(dxp), (N, D), (ld, 1), off).add_(contrib[:, :D])
 
 
+def qmp_fused_pack_tc(pack, G, DC, which, out):
+    """Emulated image = the raw pack bytes at the start of each image row (the emulated kernels unpack it again)."""
+    total = (DC + 2) * DC + DC + 4 + _FC * (DC + 4) + _FC * DC + _FC
+    src = flat(pack, G * total).view(G, total)
+    rows = out.view(G, -1)
+    rows[:, :total * 4] = src.contiguous().view(torch.uint8).view(G, total * 4)
+
+
+def _pack_from_image(img, G, DC):
+    if img is None:
+        return None
+    total = (DC + 2) * DC + DC + 4 + _FC * (DC + 4) + _FC * DC + _FC
+    return img.view(G, -1)[:, :total * 4].contiguous().view(torch.float32).view(G, total)
+
+
+def qmp_fused_fwd_tc(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, *rest):
+    qmp_fused_fwd(N, in_ptr, in_src, ea, xa, lda, DA, GA, _pack_from_image(wa, GA, _cap(DA, True)) if GA else None, xb, ldb, DB,
+                  GB, sharedB, _pack_from_image(wb, GB, _cap(DB, False)), *rest)
+
+
 def qmp_fused_wgrad(N, xa, lda, DA, GA, xb, ldb, DB, GB, sharedB, mode, C, dP, lddp, ZsA, dUsA, ZsB, dUsB, gwa, gwb):
     for (c, seg, g, xp, ld, off, D, DC) in _fused_convs(xa, lda, DA, GA, xb, ldb, DB, GB, sharedB):
         G = GA if seg == 0 else GB

@@ -83,17 +83,20 @@ def test_gcn_conv(be, d_in, d_out, self_loops):
 @pytest.mark.parametrize("conv,n_conv_layers,f_in,hid", [("TransformerConv", 1, 4, 32), ("TransformerConv", 3, 8, 32),
                                                          ("ChebConv", 1, 4, 16), ("ChebConv", 2, 4, 16),
                                                          ("GCNConv", 2, 4, 16), ("TransformerConv", 2, 5, 8)])
-@pytest.mark.parametrize("fused", [True, False])
-def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, fused, monkeypatch):
+@pytest.mark.parametrize("path", ["tc", "ffma", "modular"])
+def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     import quadtree_mpnnlstm_b200.model as M
     import quadtree_mpnnlstm_b200.fused as FZ
     from quadtree_mpnnlstm_b200 import _lib
     from oracle import cell_ref as R
     fusable = conv == "TransformerConv" and hid == 32 and f_in <= 8
-    if not fused and not fusable:
+    fused = path != "modular"
+    if path != "tc" and not fusable:
         pytest.skip("only one path exists for this configuration")
     monkeypatch.setattr(FZ, "ENABLED", fused)
-    calls_before = _lib.CALL_COUNTS.get("qmp_fused_fwd", 0)
+    monkeypatch.setattr(FZ, "TC_FWD", path == "tc")
+    n_fused = lambda: _lib.CALL_COUNTS.get("qmp_fused_fwd", 0) + _lib.CALL_COUNTS.get("qmp_fused_fwd_tc", 0)
+    calls_before = n_fused()
     ei, ea, n = _graph(4, use_edge_attrs=(conv == "TransformerConv"))
     torch.manual_seed(11)
     ref = R.GConvLSTM(f_in, hid, n_conv_layers, conv)
@@ -123,7 +126,7 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, fused, monkeypatch)
         diff = float((ga - gb.cpu()).abs().max())
         err = diff / max(float(ga.abs().max()), 1e-3)
         assert err < 2e-4 or diff < 2e-5, f"grad {k}: rel {err} abs {diff}"
-    took_fused = _lib.CALL_COUNTS.get("qmp_fused_fwd", 0) > calls_before
+    took_fused = n_fused() > calls_before
     if True:
         assert took_fused == (fused and fusable), "the fused kernels must be the path that runs when the shape fits"
     # H=None / C=None defaults to zeros like the reference

@@ -65,12 +65,13 @@ def _data(seed, T_in, T_out, H, W, c=1):
     return x, y, cl
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_ice_like_pixelwise_transformer(be, fused, monkeypatch):
+@pytest.mark.parametrize("path", ["tc", "ffma", "modular"])
+def test_ice_like_pixelwise_transformer(be, path, monkeypatch):
     """configs[1] in miniature: pixel-wise static mesh, TransformerConv, 1 layer, 3 encoder conv layers; on the
     single-launch fused kernels (the default for this shape) and on the modular kernels."""
     import quadtree_mpnnlstm_b200.fused as FZ
-    monkeypatch.setattr(FZ, "ENABLED", fused)
+    monkeypatch.setattr(FZ, "ENABLED", path != "modular")
+    monkeypatch.setattr(FZ, "TC_FWD", path == "tc")
     H, W = 24, 40
     x, y, cl = _data(1, 4, 6, H, W, c=5)
     rr, cc = np.mgrid[0:H, 0:W]
