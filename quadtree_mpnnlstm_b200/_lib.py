@@ -53,6 +53,8 @@ SIGNATURES = {
     "qmp_tc_probe3": "piiiip",
     "qmp_fused_fwd_tc": "ippppiiippiiiipiiipippiiifppppppippppfup",
     "qmp_fused_pack_tc": "piiipp",
+    "qmp_fused_bwd_target_tc": "ippppiiippiiiipiipippppppppppfup",
+    "qmp_fused_bwd_source_tc": "ippppiiippiiiipiipippppppfup",
 }
 
 
@@ -64,7 +66,7 @@ KERNELS_PER_CALL = {
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
     "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
-    "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1,
+    "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1, "qmp_fused_bwd_target_tc": 1, "qmp_fused_bwd_source_tc": 1,
 }
 CALL_COUNTS = {}
 

@@ -1,0 +1,62 @@
+// C-ABI entries of the tcgen05 fused backward (kernels in fused_bwd_tc.inl, instantiated in fused_bwd_tc_k*_i*.cu).
+#include "fused_bwd_tc.inl"
+
+namespace qmp {
+#define QMP_DECL(K)                                                                     \
+    extern template int launch_bwd_tc<0, 32, K>(const FusedBwdArgs&, cudaStream_t);     \
+    extern template int launch_bwd_tc<0, 36, K>(const FusedBwdArgs&, cudaStream_t);     \
+    extern template int launch_bwd_tc<4, 32, K>(const FusedBwdArgs&, cudaStream_t);     \
+    extern template int launch_bwd_tc<8, 32, K>(const FusedBwdArgs&, cudaStream_t);
+QMP_DECL(1)
+QMP_DECL(2)
+#undef QMP_DECL
+
+template <int KIND>
+static int dispatch_bwd_tc(const FusedBwdArgs& a, cudaStream_t st) {
+    const int dac = (a.GA == 0) ? 0 : (a.DA <= 4 ? 4 : 8);
+    const int dbc = (a.DB <= 32) ? 32 : 36;
+    if (dac == 0 && dbc == 32) return launch_bwd_tc<0, 32, KIND>(a, st);
+    if (dac == 0 && dbc == 36) return launch_bwd_tc<0, 36, KIND>(a, st);
+    if (dac == 4 && dbc == 32) return launch_bwd_tc<4, 32, KIND>(a, st);
+    if (dac == 8 && dbc == 32) return launch_bwd_tc<8, 32, KIND>(a, st);
+    set_error("qmp_fused_bwd_tc: no kernel variant for DA=%d DB=%d", a.DA, a.DB);
+    return -1;
+}
+}  // namespace qmp
+using namespace qmp;
+
+// Same contract as qmp_fused_bwd_target, on the tensor cores: wa / wb are weight images of kind 1 (qmp_fused_pack_tc).
+QMP_API int qmp_fused_bwd_target_tc(int N, const int* in_ptr, const int* in_src, const float* ea, const float* xa, int lda,
+                                    int DA, int GA, const void* wa, const float* xb, int ldb, int DB, int GB, int sharedB,
+                                    const void* wb, int mode, int C, const float* dP, int lddp, const float* logit,
+                                    const float* mstat, const float* linv, float* ds, float* ZsA, float* dUsA, float* ZsB,
+                                    float* dUsB, float* dxa, float* dxb, float drop_p, unsigned long long seed, void* stream) {
+    if (N <= 0) return 0;
+    QMP_REQUIRE(GB >= 1 && DB >= 1 && DB <= 36 && DA >= 0 && DA <= 8 && C >= 1 && C <= FC, "qmp_fused_bwd_target_tc: unsupported sizes");
+    FusedBwdArgs a{};
+    a.N = N; a.ptr = in_ptr; a.nbr = in_src; a.ea = ea; a.xa = xa; a.lda = lda; a.DA = DA; a.GA = GA;
+    a.wa = reinterpret_cast<const float*>(wa);
+    a.xb = xb; a.ldb = ldb; a.DB = DB; a.GB = GB; a.sharedB = sharedB; a.wb = reinterpret_cast<const float*>(wb);
+    a.NC = GA + GB; a.mode = mode; a.C = C;
+    a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ds = ds; a.ZsA = ZsA; a.dUsA = dUsA;
+    a.ZsB = ZsB; a.dUsB = dUsB; a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr;
+    a.drop_p = drop_p; a.seed = seed;
+    return dispatch_bwd_tc<1>(a, (cudaStream_t)stream);
+}
+
+// Same contract as qmp_fused_bwd_source, on the tensor cores: wa / wb are weight images of kind 2.
+QMP_API int qmp_fused_bwd_source_tc(int N, const int* out_ptr, const int* out_dst, const int* out_kin, const float* xa, int lda,
+                                    int DA, int GA, const void* wa, const float* xb, int ldb, int DB, int GB, int sharedB,
+                                    const void* wb, int mode, int C, const float* dP, int lddp, const float* logit,
+                                    const float* mstat, const float* linv, const float* ds, float* dxa, float* dxb,
+                                    float drop_p, unsigned long long seed, void* stream) {
+    if (N <= 0 || (dxa == nullptr && dxb == nullptr)) return 0;
+    FusedBwdArgs a{};
+    a.N = N; a.ptr = out_ptr; a.nbr = out_dst; a.kin = out_kin; a.xa = xa; a.lda = lda; a.DA = DA; a.GA = GA;
+    a.wa = reinterpret_cast<const float*>(wa);
+    a.xb = xb; a.ldb = ldb; a.DB = DB; a.GB = GB; a.sharedB = sharedB; a.wb = reinterpret_cast<const float*>(wb);
+    a.NC = GA + GB; a.mode = mode; a.C = C;
+    a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ds = const_cast<float*>(ds);
+    a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr; a.drop_p = drop_p; a.seed = seed;
+    return dispatch_bwd_tc<2>(a, (cudaStream_t)stream);
+}

@@ -1,0 +1,345 @@
+// tcgen05 versions of the fused backward kernels (same contract, arguments and outputs as fused_bwd.inl, which stays
+// as the fp32-FFMA cross-check).  Thread = node = TMEM lane as in fused_fwd_tc.inl; per conv
+//
+//   target side:  g_i --st--> A --mma--> dz = W2^T g (logit-side gradient of [z | ze | zs]),  dx_i (+)= W3^T g
+//                 dz --ld--> registers; two SIMT passes over the in-edges (d alpha, then ds / du / z);
+//                 [du | dw] --st--> A --mma--> dx_i += W1^T [du | dw];  Zs / dUs rows written for qmp_fused_wgrad.
+//   source side:  SIMT pass over the out-edges: av = sum alpha g_i, bv = sum ds x_i, sds = sum ds;
+//                 [av | bv | sds] --st--> A --mma--> dx_j += W2[:, :D]^T av + W1[:D] bv + b1 sds.
+// dx accumulates in TMEM over the convs that share an input and is written (target) / added (source) once.
+#pragma once
+#include "fused_bwd.inl"
+#include "fused_tc.cuh"
+
+namespace qmp {
+
+constexpr uint32_t TCB_DXB = 0, TCB_DXA = 64;                           // target kernel: dx accumulators inside the P block
+constexpr uint32_t TCS_DXB = 0, TCS_DXA = 48, TCS_AH = 64, TCS_AL = 144;   // source kernel map (A up to 80 columns)
+
+struct TcBStep {
+    const uint8_t* img; uint32_t bytes;
+    const float* xin; int ld, D;
+    int c, gseg, G;                 // conv index in the group, index inside its segment, convs in the segment
+    float* Zs; float* dUs;          // [N, G, cap+4]
+    float* dx; int lddx;            // gradient rows of this conv's input (nullptr: not needed)
+    uint32_t pcol;
+    bool segA, first, last;
+};
+
+template <int DA_, int DBC, int KIND>
+__device__ __forceinline__ void tc_bwd_step(const FusedBwdArgs& a, int k, TcBStep& st) {
+    const uint8_t* imgA = reinterpret_cast<const uint8_t*>(a.wa);
+    const uint8_t* imgB = reinterpret_cast<const uint8_t*>(a.wb);
+    constexpr int BA = KIND == 1 ? TcBwdTLayout(DA_).BYTES : TcBwdSLayout(DA_).BYTES;
+    constexpr int BB = KIND == 1 ? TcBwdTLayout(DBC).BYTES : TcBwdSLayout(DBC).BYTES;
+    st.segA = k < a.GA;
+    const int g = st.segA ? k : k - a.GA;
+    st.c = k;
+    st.gseg = g;
+    if (st.segA) {
+        st.img = imgA + (size_t)g * BA; st.bytes = BA; st.xin = a.xa; st.ld = a.lda; st.D = a.DA; st.G = a.GA;
+        st.Zs = a.ZsA; st.dUs = a.dUsA; st.dx = a.need_dxa ? a.dxa : nullptr; st.lddx = a.lda;
+        st.first = g == 0; st.last = g == a.GA - 1;
+        st.pcol = KIND == 1 ? TCB_DXA : TCS_DXA;
+    } else {
+        const int off = a.sharedB ? 0 : g * a.DB;
+        st.img = imgB + (size_t)g * BB; st.bytes = BB; st.xin = a.xb + off; st.ld = a.ldb; st.D = a.DB; st.G = a.GB;
+        st.Zs = a.ZsB; st.dUs = a.dUsB; st.dx = a.need_dxb ? a.dxb + off : nullptr; st.lddx = a.ldb;
+        st.first = a.sharedB ? g == 0 : true; st.last = a.sharedB ? g == a.GB - 1 : true;
+        st.pcol = KIND == 1 ? TCB_DXB : TCS_DXB;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ target side
+template <int DC>
+__device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs& a, int i, bool valid, const TcBStep& st,
+                                                   const TcBStep& nx, bool has_next) {
+    constexpr TcBwdTLayout L(DC);
+    const int t = threadIdx.x;
+    const int buf = cx.toggle;
+    uint8_t* wb = cx.wbuf[buf];
+    const float* __restrict__ xin = st.xin;
+    const int ld = st.ld, D = st.D, c = st.c;
+    const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0);
+    const bool need_dx = st.dx != nullptr;
+    {
+        float g[FC];
+        if (valid) load_dP(g, a, i, c);
+        else {
+#pragma unroll
+            for (int o = 0; o < FC; ++o) g[o] = 0.f;
+        }
+        if (cx.pending) tc_wait(cx);
+        if (t == 0 && has_next) tc_prefetch_image(cx, buf ^ 1, nx.img, nx.bytes);
+        tc_stage_a<FC>(cx.lane_base, g);
+    }
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (t == 0) {
+        tc::mbar_wait(cx.wfull + buf, cx.wparity[buf]);
+        tc::fence_after_sync();
+        tc_mma3(cx.tmem, TC_U, tc::smem_u32(wb + L.W2TH), tc::smem_u32(wb + L.W2TL), L.N2, FC, false);
+        if (need_dx) tc_mma3(cx.tmem, st.pcol, tc::smem_u32(wb + L.W3TH), tc::smem_u32(wb + L.W3TL), L.N1P, FC, !st.first);
+        tc::commit(cx.bar);
+    }
+    const int k0 = valid ? a.ptr[i] : 0, k1 = valid ? a.ptr[i + 1] : 0;
+    float xa[DC], xb[DC];
+    int kk = k0;
+    if (kk < k1) {
+        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+        if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
+    }
+    const float m = valid ? a.mstat[(size_t)i * a.NC + c] : 0.f, li = valid ? a.linv[(size_t)i * a.NC + c] : 0.f;
+    tc::mbar_wait(cx.bar, cx.parity);
+    cx.parity ^= 1;
+    tc::fence_after_sync();
+    float dz[DC + 4];
+    {
+        constexpr int N8 = (DC + 3 + 7) / 8;
+        float tmp[N8 * 8];
+        tc_load_cols<N8>(cx.lane_base, TC_U, tmp);
+#pragma unroll
+        for (int k = 0; k < DC + 3; ++k) dz[k] = tmp[k];
+        dz[DC + 3] = 0.f;
+    }
+    // pass 1: d alpha per edge (stashed in ds), t = sum alpha d alpha
+    float tsum = 0.f;
+    auto pass1 = [&](int e, const float(&xj)[DC]) {
+        const float a0 = a.ea ? a.ea[(size_t)e * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)e * 2 + 1] : 0.f;
+        float dal = fmaf(dz[DC], a0, fmaf(dz[DC + 1], a1, dz[DC + 2]));
+#pragma unroll
+        for (int k = 0; k < DC; ++k) dal = fmaf(dz[k], xj[k], dal);
+        dal *= fdropout_scale(a.seed, (long long)e * a.NC + c, a.drop_p);
+        const float al = expf(a.logit[(size_t)e * a.NC + c] - m) * li;
+        tsum = fmaf(al, dal, tsum);
+        a.ds[(size_t)e * a.NC + c] = dal;
+    };
+    while (kk < k1) {
+        pass1(kk, xa);
+        if (kk + 1 < k1) pass1(kk + 1, xb);
+        kk += 2;
+        if (kk < k1) {
+            load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+            if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
+        }
+    }
+    // pass 2: ds, du = sum ds x_j, z = sum alpha x_j
+    float du[L.K2], z[DC + 4];
+#pragma unroll
+    for (int k = 0; k < L.K2; ++k) du[k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < DC + 4; ++k) z[k] = 0.f;
+    auto pass2 = [&](int e, const float(&xj)[DC]) {
+        const float a0 = a.ea ? a.ea[(size_t)e * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)e * 2 + 1] : 0.f;
+        const float al = expf(a.logit[(size_t)e * a.NC + c] - m) * li;
+        const float dsv = al * (a.ds[(size_t)e * a.NC + c] - tsum);
+        a.ds[(size_t)e * a.NC + c] = dsv;
+        const float alk = al * fdropout_scale(a.seed, (long long)e * a.NC + c, a.drop_p);
+#pragma unroll
+        for (int k = 0; k < DC; ++k) {
+            du[k] = fmaf(dsv, xj[k], du[k]);
+            z[k] = fmaf(alk, xj[k], z[k]);
+        }
+        du[DC] = fmaf(dsv, a0, du[DC]);
+        du[DC + 1] = fmaf(dsv, a1, du[DC + 1]);
+        z[DC] = fmaf(alk, a0, z[DC]);
+        z[DC + 1] = fmaf(alk, a1, z[DC + 1]);
+        z[DC + 2] += alk;
+    };
+    kk = k0;
+    if (kk < k1) {
+        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+        if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
+    }
+    while (kk < k1) {
+        pass2(kk, xa);
+        if (kk + 1 < k1) pass2(kk + 1, xb);
+        kk += 2;
+        if (kk < k1) {
+            load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+            if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
+        }
+    }
+    if (valid) {
+        store_row<DC + 4>(st.Zs + ((size_t)i * st.G + st.gseg) * (DC + 4), z, true);
+        float* dr = st.dUs + ((size_t)i * st.G + st.gseg) * (DC + 4);
+#pragma unroll
+        for (int k = 0; k < DC + 4; k += 4) *reinterpret_cast<float4*>(dr + k) = make_float4(du[k], du[k + 1], du[k + 2], du[k + 3]);
+    }
+    if (need_dx) {
+        tc_stage_a<L.K2>(cx.lane_base, du);
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (t == 0) {
+            tc::fence_after_sync();
+            tc_mma3(cx.tmem, st.pcol, tc::smem_u32(wb + L.W1TH), tc::smem_u32(wb + L.W1TL), L.N1P, L.K2, true);
+            tc::commit(cx.bar);
+        }
+        cx.pending = true;
+        if (st.last) {          // dx_i (self part) = accumulated over the convs sharing this input
+            tc_wait(cx);
+            float dx[L.K1];
+            tc_load_cols<L.K1 / 8>(cx.lane_base, st.pcol, dx);
+            if (valid) {
+                float* row = st.dx + (size_t)i * st.lddx;
+#pragma unroll
+                for (int k = 0; k < L.K1; ++k)
+                    if (k < D) row[k] = dx[k];
+            }
+        }
+    }
+    cx.wparity[buf] ^= 1;
+    cx.toggle ^= 1;
+}
+
+// ------------------------------------------------------------------------------------------------ source side
+template <int DC>
+__device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs& a, int j, bool valid, const TcBStep& st,
+                                                   const TcBStep& nx, bool has_next) {
+    constexpr TcBwdSLayout L(DC);
+    const int t = threadIdx.x;
+    const int buf = cx.toggle;
+    uint8_t* wb = cx.wbuf[buf];
+    const float* __restrict__ xin = st.xin;
+    const int ld = st.ld, D = st.D, c = st.c;
+    const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0);
+    float A[L.KS];
+#pragma unroll
+    for (int k = 0; k < L.KS; ++k) A[k] = 0.f;
+    const int k0 = valid ? a.ptr[j] : 0, k1 = valid ? a.ptr[j + 1] : 0;
+    for (int kk = k0; kk < k1; ++kk) {
+        const int i = a.nbr[kk], kin = a.kin[kk];
+        float g[FC], xi[DC];
+        load_dP(g, a, i, c);
+        load_row<DC>(xi, xin + (size_t)i * ld, D, vec);
+        const float al = expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
+                         fdropout_scale(a.seed, (long long)kin * a.NC + c, a.drop_p);
+        const float dsv = a.ds[(size_t)kin * a.NC + c];
+#pragma unroll
+        for (int o = 0; o < FC; ++o) A[o] = fmaf(al, g[o], A[o]);
+#pragma unroll
+        for (int k = 0; k < DC; ++k) A[FC + k] = fmaf(dsv, xi[k], A[FC + k]);
+        A[FC + L.K1] += dsv;
+    }
+    if (cx.pending) tc_wait(cx);
+    if (t == 0 && has_next) tc_prefetch_image(cx, buf ^ 1, nx.img, nx.bytes);
+    tc_stage_a_at<L.KS>(cx.lane_base, TCS_AH, TCS_AL, A);
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (t == 0) {
+        tc::mbar_wait(cx.wfull + buf, cx.wparity[buf]);
+        tc::fence_after_sync();
+        tc_mma3_at(cx.tmem, st.pcol, TCS_AH, TCS_AL, tc::smem_u32(wb + L.BSH), tc::smem_u32(wb + L.BSL), L.N1P, L.KS, !st.first);
+        tc::commit(cx.bar);
+    }
+    cx.pending = true;
+    if (st.last) {
+        tc_wait(cx);
+        float dx[L.K1];
+        tc_load_cols<L.K1 / 8>(cx.lane_base, st.pcol, dx);
+        if (valid) {
+            float* row = st.dx + (size_t)j * st.lddx;
+#pragma unroll
+            for (int k = 0; k < L.K1; ++k)
+                if (k < D) row[k] += dx[k];
+        }
+    }
+    cx.wparity[buf] ^= 1;
+    cx.toggle ^= 1;
+}
+
+template <int DAC, int DBC, int KIND>
+__global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_constant__ FusedBwdArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bars[3];
+    __shared__ uint32_t tmem_slot;
+    constexpr int DA_ = DAC > 0 ? DAC : 4;
+    constexpr int BA = KIND == 1 ? TcBwdTLayout(DA_).BYTES : TcBwdSLayout(DA_).BYTES;
+    constexpr int BB = KIND == 1 ? TcBwdTLayout(DBC).BYTES : TcBwdSLayout(DBC).BYTES;
+    constexpr int SLOT = BA > BB ? BA : BB;
+    const int t = threadIdx.x, warp = t >> 5;
+    if (t == 0) {
+        tc::mbar_init(&bars[0], 1);
+        tc::mbar_init(&bars[1], 1);
+        tc::mbar_init(&bars[2], 1);
+        tc::fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc::tmem_alloc(&tmem_slot, TC_COLS);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    TcCtx cx;
+    cx.wbuf[0] = smem;
+    cx.wbuf[1] = smem + SLOT;
+    cx.wfull = &bars[1];
+    cx.wparity[0] = cx.wparity[1] = 0;
+    cx.toggle = 0;
+    cx.bar = &bars[0];
+    cx.parity = 0;
+    cx.pending = false;
+    cx.tmem = tmem_slot;
+    cx.lane_base = cx.tmem + ((uint32_t)(warp * 32) << 16);
+
+    const int ntiles = (a.N + 127) / 128;
+    // source side: only the convs whose input needs a gradient
+    const int kfirst = (KIND == 2 && !a.need_dxa) ? a.GA : 0;
+    const int kend = (KIND == 2 && !a.need_dxb) ? a.GA : a.NC;
+    TcBStep st, nx;
+    if ((int)blockIdx.x < ntiles && kfirst < kend) {
+        tc_bwd_step<DA_, DBC, KIND>(a, kfirst, st);
+        if (t == 0) tc_prefetch_image(cx, 0, st.img, st.bytes);
+    }
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int i = tile * 128 + t;
+        const bool valid = i < a.N;
+        for (int k = kfirst; k < kend; ++k) {
+            tc_bwd_step<DA_, DBC, KIND>(a, k, st);
+            const bool has_next = (k + 1 < kend) || (tile + (int)gridDim.x < ntiles);
+            tc_bwd_step<DA_, DBC, KIND>(a, (k + 1 < kend) ? k + 1 : kfirst, nx);
+            bool ranA = false;
+            if constexpr (DAC > 0) {
+                if (st.segA) {
+                    if constexpr (KIND == 1) conv_bwd_target_tc<DA_>(cx, a, i, valid, st, nx, has_next);
+                    else conv_bwd_source_tc<DA_>(cx, a, i, valid, st, nx, has_next);
+                    ranA = true;
+                }
+            }
+            if (!ranA) {
+                if constexpr (KIND == 1) conv_bwd_target_tc<DBC>(cx, a, i, valid, st, nx, has_next);
+                else conv_bwd_source_tc<DBC>(cx, a, i, valid, st, nx, has_next);
+            }
+        }
+    }
+    if (cx.pending) tc_wait(cx);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(cx.tmem, TC_COLS);
+}
+
+template <int DAC, int DBC, int KIND>
+int launch_bwd_tc(const FusedBwdArgs& a, cudaStream_t st) {
+    constexpr int DA_ = DAC > 0 ? DAC : 4;
+    constexpr int BA = KIND == 1 ? TcBwdTLayout(DA_).BYTES : TcBwdSLayout(DA_).BYTES;
+    constexpr int BB = KIND == 1 ? TcBwdTLayout(DBC).BYTES : TcBwdSLayout(DBC).BYTES;
+    constexpr int SLOT = BA > BB ? BA : BB;
+    const size_t smem = 2 * (size_t)SLOT;
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        QMP_CUDA(cudaGetDevice(&dev));
+        QMP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    auto kern = fused_bwd_tc_kernel<DAC, DBC, KIND>;
+    QMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = cdiv(a.N, 128);
+    const int grid = ntiles < 2 * n_sm ? ntiles : 2 * n_sm;
+    kern<<<grid, 128, smem, st>>>(a);
+    QMP_LAUNCH_CHECK("fused_bwd_tc_kernel");
+    return 0;
+}
+
+}  // namespace qmp

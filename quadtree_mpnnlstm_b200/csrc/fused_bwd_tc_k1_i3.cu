@@ -1,0 +1,4 @@
+#include "fused_bwd_tc.inl"
+namespace qmp {
+template int launch_bwd_tc<8, 32, 1>(const FusedBwdArgs&, cudaStream_t);
+}

@@ -34,6 +34,24 @@ struct TcFwdLayout {
           B1(W2L + FC * K2 * 4), B3(B1 + 48 * 4), BYTES(B3 + FC * 4) {}
 };
 
+__host__ __device__ constexpr int tc_pad16(int v) { return (v + 15) / 16 * 16; }
+
+// BACKWARD, target side: g (32) -> dz = W2^T g (N2 rows), dx_self = W3^T g (+ W1^T du) (N1P rows)
+struct TcBwdTLayout {
+    int K1, K2, N2, N1P, W2TH, W2TL, W3TH, W3TL, W1TH, W1TL, BYTES;
+    __host__ __device__ constexpr TcBwdTLayout(int DC)
+        : K1(tc_pad8(DC)), K2(tc_pad8(DC + 4)), N2(tc_pad16(K2)), N1P(tc_pad16(K1)), W2TH(0), W2TL(W2TH + N2 * FC * 4),
+          W3TH(W2TL + N2 * FC * 4), W3TL(W3TH + N1P * FC * 4), W1TH(W3TL + N1P * FC * 4), W1TL(W1TH + N1P * K2 * 4),
+          BYTES(W1TL + N1P * K2 * 4) {}
+};
+
+// BACKWARD, source side: [av (32) | bv (K1) | sum ds, 0 ...] (KS columns) -> dx += W2[:, :D]^T av + W1[:D] bv + b1 sum ds
+struct TcBwdSLayout {
+    int K1, KS, N1P, BSH, BSL, BYTES;
+    __host__ __device__ constexpr TcBwdSLayout(int DC)
+        : K1(tc_pad8(DC)), KS(FC + K1 + 8), N1P(tc_pad16(K1)), BSH(0), BSL(N1P * KS * 4), BYTES(2 * N1P * KS * 4) {}
+};
+
 // byte offset of element (n, k) of a K-major operand with K columns (K % 8 == 0): 8-row x 16-byte core matrices,
 // consecutive K chunks 128 bytes apart (LBO), consecutive 8-row blocks 32 K bytes apart (SBO)
 __host__ __device__ __forceinline__ int img_off(int n, int k, int K) {
@@ -42,6 +60,21 @@ __host__ __device__ __forceinline__ int img_off(int n, int k, int K) {
 
 // D[tmem + dcol] (+)= A (TMEM, K columns at TC_AH / TC_AL) * B^T (shared memory, N rows x K, hi / lo), 3xTF32.
 // Called by ONE thread.
+__device__ __forceinline__ void tc_mma3_at(uint32_t tmem, uint32_t dcol, uint32_t ah_col, uint32_t al_col, uint32_t bh_addr,
+                                           uint32_t bl_addr, int N, int K, bool accumulate) {
+    const uint32_t idesc = tc::make_idesc_tf32(128, N);
+    const uint32_t sbo = 32u * (uint32_t)K;
+#pragma unroll 1
+    for (int ks = 0; ks < K / 8; ++ks) {
+        const uint64_t dbh = tc::make_desc(bh_addr + (uint32_t)ks * 256, 128, sbo);
+        const uint64_t dbl = tc::make_desc(bl_addr + (uint32_t)ks * 256, 128, sbo);
+        const uint32_t ah = tmem + ah_col + (uint32_t)ks * 8, al = tmem + al_col + (uint32_t)ks * 8;
+        tc::mma_tf32_ts(tmem + dcol, ah, dbh, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        tc::mma_tf32_ts(tmem + dcol, al, dbh, idesc, 1);
+        tc::mma_tf32_ts(tmem + dcol, ah, dbl, idesc, 1);
+    }
+}
+
 __device__ __forceinline__ void tc_mma3(uint32_t tmem, uint32_t dcol, uint32_t bh_addr, uint32_t bl_addr, int N, int K,
                                         bool accumulate) {
     const uint32_t idesc = tc::make_idesc_tf32(128, N);
@@ -73,6 +106,24 @@ __device__ __forceinline__ void tc_stage_a(uint32_t lane_base, const float (&v)[
         }
         tc::tmem_st8(lane_base + TC_AH + (uint32_t)k0, h);
         tc::tmem_st8(lane_base + TC_AL + (uint32_t)k0, l);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ void tc_stage_a_at(uint32_t lane_base, uint32_t ah_col, uint32_t al_col, const float (&v)[K]) {
+    static_assert(K % 8 == 0, "A operand: K multiple of 8");
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += 8) {
+        uint32_t h[8], l[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float hi, lo;
+            tc::split_tf32(v[k0 + i], hi, lo);
+            h[i] = __float_as_uint(hi);
+            l[i] = __float_as_uint(lo);
+        }
+        tc::tmem_st8(lane_base + ah_col + (uint32_t)k0, h);
+        tc::tmem_st8(lane_base + al_col + (uint32_t)k0, l);
     }
 }
 

@@ -15,6 +15,7 @@ FC = 32
 HEADW = 36          # decoder-head input rows: 32 normalised outputs | concat layer | 3 zero pad columns (16-byte rows)
 ENABLED = True      # tests flip this to cross-check the fused kernels against the modular ones
 TC_WGRAD = True     # weight gradients: one tcgen05 launch per group (False: ten FFMA reductions, the cross-check)
+TC_BWD = True       # backward (target / source side) on tcgen05 (csrc/fused_bwd_tc.inl); False: fp32-FFMA kernels
 TC_FWD = True       # forward on tcgen05 (csrc/fused_fwd_tc.inl); False: the fp32-FFMA kernel (csrc/fused_fwd.inl)
 _f32 = torch.float32
 
@@ -47,11 +48,21 @@ def _pad8(v):
     return (v + 7) // 8 * 8
 
 
+def _pad16(v):
+    return (v + 15) // 16 * 16
+
+
 def tc_image_bytes(DC, kind=0):
-    """Bytes of one conv's weight image (csrc/fused_tc.cuh TcFwdLayout)."""
-    assert kind == 0
-    K1, K2, N1 = _pad8(DC), _pad8(DC + 4), (16 if DC + 2 <= 16 else 48)
-    return 8 * (N1 * K1 + FC * K1 + FC * K2) + 4 * (48 + FC)
+    """Bytes of one conv's weight image (csrc/fused_tc.cuh: TcFwdLayout / TcBwdTLayout / TcBwdSLayout)."""
+    K1, K2 = _pad8(DC), _pad8(DC + 4)
+    if kind == 0:
+        N1 = 16 if DC + 2 <= 16 else 48
+        return 8 * (N1 * K1 + FC * K1 + FC * K2) + 4 * (48 + FC)
+    if kind == 1:
+        N2, N1P = _pad16(K2), _pad16(K1)
+        return 8 * (N2 * FC + N1P * FC + N1P * K2)
+    assert kind == 2
+    return 8 * _pad16(K1) * (FC + K1 + 8)
 
 
 _img_cache = {}

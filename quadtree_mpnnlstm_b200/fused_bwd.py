@@ -100,20 +100,28 @@ def fused_group_backward(ctx, *grads):
     dUsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
     dxa = torch.empty_like(xa) if need_dxa else None
     dxb = torch.empty_like(xb) if need_dxb else None
-    pa = bwd_pack(wa, DAC) if GA else None
-    pb = bwd_pack(wb, DBC)
+    from . import fused as _f
+    tcb = _f.TC_BWD
+    if tcb:
+        pa = _f.tc_image(wa, DAC, 1) if GA else None
+        pb = _f.tc_image(wb, DBC, 1)
+    else:
+        pa = bwd_pack(wa, DAC) if GA else None
+        pb = bwd_pack(wb, DBC)
     lda = xa.shape[1] if xa is not None else 0
     ldb = xb.shape[1]
-    _lib.call("qmp_fused_bwd_target", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda, DA, GA, pa, xb, ldb, DB, GB,
+    _lib.call("qmp_fused_bwd_target_tc" if tcb else "qmp_fused_bwd_target", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda, DA, GA, pa, xb, ldb, DB, GB,
               int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, ZsA, dUsA, ZsB, dUsB, dxa, dxb, float(drop_p),
               int(seed))
     if need_dxa or need_dxb:
-        _lib.call("qmp_fused_bwd_source", N, csr.out_ptr, csr.out_dst, csr.out_kin, xa, lda, DA, GA, pa, xb, ldb, DB, GB,
+        if tcb:
+            pa = _f.tc_image(wa, DAC, 2) if GA else None
+            pb = _f.tc_image(wb, DBC, 2)
+        _lib.call("qmp_fused_bwd_source_tc" if tcb else "qmp_fused_bwd_source", N, csr.out_ptr, csr.out_dst, csr.out_kin, xa, lda, DA, GA, pa, xb, ldb, DB, GB,
                   int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, dxa, dxb, float(drop_p), int(seed))
 
     gwa = torch.zeros_like(wa) if GA else None
     gwb = torch.zeros_like(wb)
-    from . import fused as _f
     if _f.TC_WGRAD:
         _lib.call("qmp_fused_wgrad", N, xa, lda, DA, GA, xb, ldb, DB, GB, int(sharedB), mode, C, dP, lddp, ZsA, dUsA, ZsB,
                   dUsB, gwa, gwb)

@@ -609,6 +609,32 @@ def qmp_fused_fwd_tc(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb, DB, GB
                   GB, sharedB, _pack_from_image(wb, GB, _cap(DB, False)), *rest)
 
 
+def _bwd_pack_from_image(img, G, DC):
+    """Backward pack (W1 | b1 | W1T | W2T | W3T) rebuilt from the forward pack stored in an emulated image."""
+    if img is None:
+        return None
+    w = _pack_from_image(img, G, DC)
+    o1 = (DC + 2) * DC
+    o2 = o1 + DC + 4
+    o3 = o2 + _FC * (DC + 4)
+    o4 = o3 + _FC * DC
+    W1, b1 = w[:, :o1].view(G, DC + 2, DC), w[:, o1:o2]
+    W2, W3 = w[:, o2:o3].view(G, _FC, DC + 4), w[:, o3:o4].view(G, _FC, DC)
+    W1T = torch.zeros(G, DC, DC + 4)
+    W1T[:, :, :DC + 2] = W1.transpose(1, 2)
+    return torch.cat([W1.flatten(1), b1, W1T.flatten(1), W2.transpose(1, 2).flatten(1), W3.transpose(1, 2).flatten(1)], 1).contiguous()
+
+
+def qmp_fused_bwd_target_tc(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, *rest):
+    qmp_fused_bwd_target(N, in_ptr, in_src, ea, xa, lda, DA, GA, _bwd_pack_from_image(wa, GA, _cap(DA, True)) if GA else None, xb,
+                         ldb, DB, GB, sharedB, _bwd_pack_from_image(wb, GB, _cap(DB, False)), *rest)
+
+
+def qmp_fused_bwd_source_tc(N, out_ptr, out_dst, out_kin, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, *rest):
+    qmp_fused_bwd_source(N, out_ptr, out_dst, out_kin, xa, lda, DA, GA, _bwd_pack_from_image(wa, GA, _cap(DA, True)) if GA else None,
+                         xb, ldb, DB, GB, sharedB, _bwd_pack_from_image(wb, GB, _cap(DB, False)), *rest)
+
+
 def qmp_fused_wgrad(N, xa, lda, DA, GA, xb, ldb, DB, GB, sharedB, mode, C, dP, lddp, ZsA, dUsA, ZsB, dUsB, gwa, gwb):
     for (c, seg, g, xp, ld, off, D, DC) in _fused_convs(xa, lda, DA, GA, xb, ldb, DB, GB, sharedB):
         G = GA if seg == 0 else GB

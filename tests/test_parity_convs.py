@@ -95,6 +95,7 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
         pytest.skip("only one path exists for this configuration")
     monkeypatch.setattr(FZ, "ENABLED", fused)
     monkeypatch.setattr(FZ, "TC_FWD", path == "tc")
+    monkeypatch.setattr(FZ, "TC_BWD", path == "tc")
     n_fused = lambda: _lib.CALL_COUNTS.get("qmp_fused_fwd", 0) + _lib.CALL_COUNTS.get("qmp_fused_fwd_tc", 0)
     calls_before = n_fused()
     ei, ea, n = _graph(4, use_edge_attrs=(conv == "TransformerConv"))

@@ -72,6 +72,7 @@ def test_ice_like_pixelwise_transformer(be, path, monkeypatch):
     import quadtree_mpnnlstm_b200.fused as FZ
     monkeypatch.setattr(FZ, "ENABLED", path != "modular")
     monkeypatch.setattr(FZ, "TC_FWD", path == "tc")
+    monkeypatch.setattr(FZ, "TC_BWD", path == "tc")
     H, W = 24, 40
     x, y, cl = _data(1, 4, 6, H, W, c=5)
     rr, cc = np.mgrid[0:H, 0:W]
