@@ -52,8 +52,8 @@ __device__ __forceinline__ void tc_bwd_step(const FusedBwdArgs& a, int k, TcBSte
 
 // ------------------------------------------------------------------------------------------------ target side
 template <int DC>
-__device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs& a, int i, bool valid, const TcBStep& st,
-                                                   const TcBStep& nx, bool has_next) {
+__device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs& a, int i, bool valid, const TcEdges& te,
+                                                   const TcBStep& st, const TcBStep& nx, bool has_next) {
     constexpr TcBwdTLayout L(DC);
     const int t = threadIdx.x;
     const int buf = cx.toggle;
@@ -83,14 +83,19 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         if (need_dx) tc_mma3(cx.tmem, st.pcol, tc::smem_u32(wb + L.W3TH), tc::smem_u32(wb + L.W3TL), L.N1P, FC, !st.first);
         tc::commit(cx.bar);
     }
-    const int k0 = valid ? a.ptr[i] : 0, k1 = valid ? a.ptr[i + 1] : 0;
+    const int k0 = te.k0, k1 = te.k1;
     float xa[DC], xb[DC];
-    int kk = k0;
-    if (kk < k1) {
-        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
-        if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
+    if (k0 < k1) {
+        load_row<DC>(xa, xin + (size_t)te.j[0] * ld, D, vec);
+        if (k0 + 1 < k1) load_row<DC>(xb, xin + (size_t)te.j[1] * ld, D, vec);
     }
     const float m = valid ? a.mstat[(size_t)i * a.NC + c] : 0.f, li = valid ? a.linv[(size_t)i * a.NC + c] : 0.f;
+    float al4[4], dal4[4];                   // alpha and d alpha of edges 0..3 stay in registers between the passes
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        al4[e] = (k0 + e < k1) ? expf(a.logit[(size_t)(k0 + e) * a.NC + c] - m) * li : 0.f;
+        dal4[e] = 0.f;
+    }
     tc::mbar_wait(cx.bar, cx.parity);
     cx.parity ^= 1;
     tc::fence_after_sync();
@@ -103,26 +108,30 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         for (int k = 0; k < DC + 3; ++k) dz[k] = tmp[k];
         dz[DC + 3] = 0.f;
     }
-    // pass 1: d alpha per edge (stashed in ds), t = sum alpha d alpha
+    // pass 1: d alpha per edge, t = sum alpha d alpha
     float tsum = 0.f;
-    auto pass1 = [&](int e, const float(&xj)[DC]) {
-        const float a0 = a.ea ? a.ea[(size_t)e * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)e * 2 + 1] : 0.f;
+    auto dalpha = [&](int e, const float(&xj)[DC], float a0, float a1) {
         float dal = fmaf(dz[DC], a0, fmaf(dz[DC + 1], a1, dz[DC + 2]));
 #pragma unroll
         for (int k = 0; k < DC; ++k) dal = fmaf(dz[k], xj[k], dal);
-        dal *= fdropout_scale(a.seed, (long long)e * a.NC + c, a.drop_p);
-        const float al = expf(a.logit[(size_t)e * a.NC + c] - m) * li;
-        tsum = fmaf(al, dal, tsum);
-        a.ds[(size_t)e * a.NC + c] = dal;
+        return dal * fdropout_scale(a.seed, (long long)e * a.NC + c, a.drop_p);
     };
-    while (kk < k1) {
-        pass1(kk, xa);
-        if (kk + 1 < k1) pass1(kk + 1, xb);
-        kk += 2;
-        if (kk < k1) {
-            load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
-            if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
-        }
+    if (k0 < k1) {
+        dal4[0] = dalpha(k0, xa, te.e0[0], te.e1[0]);
+        if (k0 + 2 < k1) load_row<DC>(xa, xin + (size_t)te.j[2] * ld, D, vec);
+        if (k0 + 1 < k1) dal4[1] = dalpha(k0 + 1, xb, te.e0[1], te.e1[1]);
+        if (k0 + 3 < k1) load_row<DC>(xb, xin + (size_t)te.j[3] * ld, D, vec);
+        if (k0 + 2 < k1) dal4[2] = dalpha(k0 + 2, xa, te.e0[2], te.e1[2]);
+        if (k0 + 3 < k1) dal4[3] = dalpha(k0 + 3, xb, te.e0[3], te.e1[3]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tsum = fmaf(al4[e], dal4[e], tsum);
+    }
+    for (int kk = k0 + 4; kk < k1; ++kk) {   // larger in-degrees: d alpha stashed in ds
+        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+        const float a0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
+        const float dal = dalpha(kk, xa, a0, a1);
+        tsum = fmaf(expf(a.logit[(size_t)kk * a.NC + c] - m) * li, dal, tsum);
+        a.ds[(size_t)kk * a.NC + c] = dal;
     }
     // pass 2: ds, du = sum ds x_j, z = sum alpha x_j
     float du[L.K2], z[DC + 4];
@@ -130,10 +139,8 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
     for (int k = 0; k < L.K2; ++k) du[k] = 0.f;
 #pragma unroll
     for (int k = 0; k < DC + 4; ++k) z[k] = 0.f;
-    auto pass2 = [&](int e, const float(&xj)[DC]) {
-        const float a0 = a.ea ? a.ea[(size_t)e * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)e * 2 + 1] : 0.f;
-        const float al = expf(a.logit[(size_t)e * a.NC + c] - m) * li;
-        const float dsv = al * (a.ds[(size_t)e * a.NC + c] - tsum);
+    auto accum = [&](int e, const float(&xj)[DC], float a0, float a1, float al, float dal) {
+        const float dsv = al * (dal - tsum);
         a.ds[(size_t)e * a.NC + c] = dsv;
         const float alk = al * fdropout_scale(a.seed, (long long)e * a.NC + c, a.drop_p);
 #pragma unroll
@@ -147,19 +154,21 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         z[DC + 1] = fmaf(alk, a1, z[DC + 1]);
         z[DC + 2] += alk;
     };
-    kk = k0;
-    if (kk < k1) {
-        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
-        if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
-    }
-    while (kk < k1) {
-        pass2(kk, xa);
-        if (kk + 1 < k1) pass2(kk + 1, xb);
-        kk += 2;
-        if (kk < k1) {
-            load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
-            if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
+    if (k0 < k1) {
+        if (k0 + 2 < k1) {                   // xa / xb hold edges 2, 3: finish them first, then re-gather 0, 1 (L1 hits)
+            if (k0 + 4 < k1) load_row<DC>(xa, xin + (size_t)te.j[2] * ld, D, vec);   // the long-degree loop reused xa
+            accum(k0 + 2, xa, te.e0[2], te.e1[2], al4[2], dal4[2]);
+            load_row<DC>(xa, xin + (size_t)te.j[0] * ld, D, vec);
+            if (k0 + 3 < k1) accum(k0 + 3, xb, te.e0[3], te.e1[3], al4[3], dal4[3]);
+            load_row<DC>(xb, xin + (size_t)te.j[1] * ld, D, vec);
         }
+        accum(k0, xa, te.e0[0], te.e1[0], al4[0], dal4[0]);
+        if (k0 + 1 < k1) accum(k0 + 1, xb, te.e0[1], te.e1[1], al4[1], dal4[1]);
+    }
+    for (int kk = k0 + 4; kk < k1; ++kk) {
+        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+        const float a0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
+        accum(kk, xa, a0, a1, expf(a.logit[(size_t)kk * a.NC + c] - m) * li, a.ds[(size_t)kk * a.NC + c]);
     }
     if (valid) {
         store_row<DC + 4>(st.Zs + ((size_t)i * st.G + st.gseg) * (DC + 4), z, true);
@@ -196,8 +205,8 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
 
 // ------------------------------------------------------------------------------------------------ source side
 template <int DC>
-__device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs& a, int j, bool valid, const TcBStep& st,
-                                                   const TcBStep& nx, bool has_next) {
+__device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs& a, int j, bool valid, const TcEdges& te,
+                                                   const TcBStep& st, const TcBStep& nx, bool has_next) {
     constexpr TcBwdSLayout L(DC);
     const int t = threadIdx.x;
     const int buf = cx.toggle;
@@ -208,20 +217,44 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
     float A[L.KS];
 #pragma unroll
     for (int k = 0; k < L.KS; ++k) A[k] = 0.f;
-    const int k0 = valid ? a.ptr[j] : 0, k1 = valid ? a.ptr[j + 1] : 0;
-    for (int kk = k0; kk < k1; ++kk) {
-        const int i = a.nbr[kk], kin = a.kin[kk];
-        float g[FC], xi[DC];
-        load_dP(g, a, i, c);
-        load_row<DC>(xi, xin + (size_t)i * ld, D, vec);
-        const float al = expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
-                         fdropout_scale(a.seed, (long long)kin * a.NC + c, a.drop_p);
-        const float dsv = a.ds[(size_t)kin * a.NC + c];
+    const int k0 = te.k0, k1 = te.k1;
+    auto edge = [&](int i, int kin, const float(&g)[FC], const float(&xi)[DC], float al, float dsv) {
 #pragma unroll
         for (int o = 0; o < FC; ++o) A[o] = fmaf(al, g[o], A[o]);
 #pragma unroll
         for (int k = 0; k < DC; ++k) A[FC + k] = fmaf(dsv, xi[k], A[FC + k]);
         A[FC + L.K1] += dsv;
+    };
+    auto coef = [&](int i, int kin, float& al, float& dsv) {
+        al = expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
+             fdropout_scale(a.seed, (long long)kin * a.NC + c, a.drop_p);
+        dsv = a.ds[(size_t)kin * a.NC + c];
+    };
+    // out-edges 0..3: targets and in-CSR slots were loaded once per tile (te.j = target, te.e0 = slot as int bits)
+#pragma unroll
+    for (int e0 = 0; e0 < 4; e0 += 2) {
+        if (k0 + e0 < k1) {
+            const int i0 = te.j[e0], kin0 = __float_as_int(te.e0[e0]);
+            const bool two = k0 + e0 + 1 < k1;
+            const int i1 = two ? te.j[e0 + 1] : i0, kin1 = two ? __float_as_int(te.e0[e0 + 1]) : kin0;
+            float g0[FC], x0[DC], g1[FC], x1[DC], al0, ds0, al1, ds1;
+            load_dP(g0, a, i0, c);
+            load_row<DC>(x0, xin + (size_t)i0 * ld, D, vec);
+            load_dP(g1, a, i1, c);
+            load_row<DC>(x1, xin + (size_t)i1 * ld, D, vec);
+            coef(i0, kin0, al0, ds0);
+            coef(i1, kin1, al1, ds1);
+            edge(i0, kin0, g0, x0, al0, ds0);
+            if (two) edge(i1, kin1, g1, x1, al1, ds1);
+        }
+    }
+    for (int kk = k0 + 4; kk < k1; ++kk) {
+        const int i = a.nbr[kk], kin = a.kin[kk];
+        float g[FC], xi[DC], al, dsv;
+        load_dP(g, a, i, c);
+        load_row<DC>(xi, xin + (size_t)i * ld, D, vec);
+        coef(i, kin, al, dsv);
+        edge(i, kin, g, xi, al, dsv);
     }
     if (cx.pending) tc_wait(cx);
     if (t == 0 && has_next) tc_prefetch_image(cx, buf ^ 1, nx.img, nx.bytes);
@@ -296,6 +329,9 @@ __global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = tile * 128 + t;
         const bool valid = i < a.N;
+        TcEdges te;
+        if constexpr (KIND == 1) tc_load_edges(te, a.ptr, a.nbr, a.ea, i, valid);
+        else tc_load_out_edges(te, a.ptr, a.nbr, a.kin, i, valid);
         for (int k = kfirst; k < kend; ++k) {
             tc_bwd_step<DA_, DBC, KIND>(a, k, st);
             const bool has_next = (k + 1 < kend) || (tile + (int)gridDim.x < ntiles);
@@ -303,14 +339,14 @@ __global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_const
             bool ranA = false;
             if constexpr (DAC > 0) {
                 if (st.segA) {
-                    if constexpr (KIND == 1) conv_bwd_target_tc<DA_>(cx, a, i, valid, st, nx, has_next);
-                    else conv_bwd_source_tc<DA_>(cx, a, i, valid, st, nx, has_next);
+                    if constexpr (KIND == 1) conv_bwd_target_tc<DA_>(cx, a, i, valid, te, st, nx, has_next);
+                    else conv_bwd_source_tc<DA_>(cx, a, i, valid, te, st, nx, has_next);
                     ranA = true;
                 }
             }
             if (!ranA) {
-                if constexpr (KIND == 1) conv_bwd_target_tc<DBC>(cx, a, i, valid, st, nx, has_next);
-                else conv_bwd_source_tc<DBC>(cx, a, i, valid, st, nx, has_next);
+                if constexpr (KIND == 1) conv_bwd_target_tc<DBC>(cx, a, i, valid, te, st, nx, has_next);
+                else conv_bwd_source_tc<DBC>(cx, a, i, valid, te, st, nx, has_next);
             }
         }
     }

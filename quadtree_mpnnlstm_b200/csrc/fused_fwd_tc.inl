@@ -28,9 +28,8 @@ struct TcStep {
 // one edge of the online segment softmax
 template <int DC>
 __device__ __forceinline__ void tc_edge(const FusedFwdArgs& a, int kk, int c, const float (&u)[DC], const float (&w01)[2],
-                                        const float (&xj)[DC], float (&z)[DC], float& m, float& l, float& zs, float& ze0,
-                                        float& ze1) {
-    const float e0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, e1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
+                                        const float (&xj)[DC], float e0, float e1, float (&z)[DC], float& m, float& l, float& zs,
+                                        float& ze0, float& ze1) {
     float s = fmaf(w01[0], e0, w01[1] * e1);
 #pragma unroll
     for (int k = 0; k < DC; ++k) s = fmaf(u[k], xj[k], s);
@@ -48,8 +47,8 @@ __device__ __forceinline__ void tc_edge(const FusedFwdArgs& a, int kk, int c, co
 }
 
 template <int DC>
-__device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, int i, bool valid, const TcStep& st,
-                                            const TcStep& nx, bool has_next) {
+__device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, int i, bool valid, const TcEdges& te,
+                                            const TcStep& st, const TcStep& nx, bool has_next) {
     constexpr TcFwdLayout L(DC);
     const int t = threadIdx.x;
     const int buf = cx.toggle;
@@ -75,12 +74,11 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
         tc::commit(cx.bar);
     }
     // (3) first pair of neighbour rows: issued before the wait for U
-    const int k0 = valid ? a.ptr[i] : 0, k1 = valid ? a.ptr[i + 1] : 0;
+    const int k0 = te.k0, k1 = te.k1;
     float xa[DC], xb[DC];
-    int kk = k0;
-    if (kk < k1) {
-        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
-        if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
+    if (k0 < k1) {
+        load_row<DC>(xa, xin + (size_t)te.j[0] * ld, D, vec);
+        if (k0 + 1 < k1) load_row<DC>(xb, xin + (size_t)te.j[1] * ld, D, vec);
     }
     tc::mbar_wait(cx.wfull + buf, cx.wparity[buf]);       // biases below are read from the image
     tc::mbar_wait(cx.bar, cx.parity);
@@ -103,14 +101,18 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
 #pragma unroll
     for (int k = 0; k < DC; ++k) z[k] = 0.f;
     float m = -INFINITY, l = 0.f, zs = 0.f, ze0 = 0.f, ze1 = 0.f;
-    while (kk < k1) {
-        tc_edge<DC>(a, kk, c, u, w01, xa, z, m, l, zs, ze0, ze1);
-        if (kk + 1 < k1) tc_edge<DC>(a, kk + 1, c, u, w01, xb, z, m, l, zs, ze0, ze1);
-        kk += 2;
-        if (kk < k1) {
-            load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
-            if (kk + 1 < k1) load_row<DC>(xb, xin + (size_t)a.nbr[kk + 1] * ld, D, vec);
-        }
+    if (k0 < k1) {                          // edges 0..3: indices and attributes were loaded once per tile
+        tc_edge<DC>(a, k0, c, u, w01, xa, te.e0[0], te.e1[0], z, m, l, zs, ze0, ze1);
+        if (k0 + 2 < k1) load_row<DC>(xa, xin + (size_t)te.j[2] * ld, D, vec);
+        if (k0 + 1 < k1) tc_edge<DC>(a, k0 + 1, c, u, w01, xb, te.e0[1], te.e1[1], z, m, l, zs, ze0, ze1);
+        if (k0 + 3 < k1) load_row<DC>(xb, xin + (size_t)te.j[3] * ld, D, vec);
+        if (k0 + 2 < k1) tc_edge<DC>(a, k0 + 2, c, u, w01, xa, te.e0[2], te.e1[2], z, m, l, zs, ze0, ze1);
+        if (k0 + 3 < k1) tc_edge<DC>(a, k0 + 3, c, u, w01, xb, te.e0[3], te.e1[3], z, m, l, zs, ze0, ze1);
+    }
+    for (int kk = k0 + 4; kk < k1; ++kk) {   // larger in-degrees (quadtree meshes)
+        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+        const float e0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, e1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
+        tc_edge<DC>(a, kk, c, u, w01, xa, e0, e1, z, m, l, zs, ze0, ze1);
     }
     const float li = (l > 0.f) ? 1.f / l : 0.f;
     if (valid) {
@@ -230,6 +232,8 @@ __global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_const
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int i = tile * 128 + t;
         const bool valid = i < a.N;
+        TcEdges te;
+        tc_load_edges(te, a.ptr, a.nbr, a.ea, i, valid);
         for (int k = 0; k < nsteps; ++k) {
             tc_fwd_step<DA_, DBC>(a, k, st);
             const bool has_next = (k + 1 < nsteps) || (tile + (int)gridDim.x < ntiles);
@@ -237,11 +241,11 @@ __global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_const
             bool ranA = false;
             if constexpr (DAC > 0) {
                 if (st.segA) {
-                    conv_fwd_tc<DA_>(cx, a, i, valid, st, nx, has_next);
+                    conv_fwd_tc<DA_>(cx, a, i, valid, te, st, nx, has_next);
                     ranA = true;
                 }
             }
-            if (!ranA) conv_fwd_tc<DBC>(cx, a, i, valid, st, nx, has_next);
+            if (!ranA) conv_fwd_tc<DBC>(cx, a, i, valid, te, st, nx, has_next);
             if (!st.last) continue;
             float P[FC];
             tc_collect(cx, st.pcol, P);

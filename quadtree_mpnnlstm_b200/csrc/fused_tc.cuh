@@ -156,6 +156,39 @@ __device__ __forceinline__ void tc_load_row(float (&x)[K], const float* __restri
     }
 }
 
+// the first four in-edges of this thread's node (all of them on a pixel-wise mesh): loaded once per tile
+struct TcEdges {
+    int k0, k1;
+    int j[4];
+    float e0[4], e1[4];
+};
+__device__ __forceinline__ void tc_load_edges(TcEdges& te, const int* __restrict__ ptr, const int* __restrict__ nbr,
+                                              const float* __restrict__ ea, int i, bool valid) {
+    te.k0 = valid ? __ldg(ptr + i) : 0;
+    te.k1 = valid ? __ldg(ptr + i + 1) : 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool on = te.k0 + e < te.k1;
+        te.j[e] = on ? __ldg(nbr + te.k0 + e) : 0;
+        te.e0[e] = (on && ea) ? __ldg(ea + (size_t)(te.k0 + e) * 2) : 0.f;
+        te.e1[e] = (on && ea) ? __ldg(ea + (size_t)(te.k0 + e) * 2 + 1) : 0.f;
+    }
+}
+
+// out-edges of a node for the source-side kernel: j = target node, e0 = in-CSR slot of the edge (int bits)
+__device__ __forceinline__ void tc_load_out_edges(TcEdges& te, const int* __restrict__ ptr, const int* __restrict__ dst,
+                                                  const int* __restrict__ kin, int i, bool valid) {
+    te.k0 = valid ? __ldg(ptr + i) : 0;
+    te.k1 = valid ? __ldg(ptr + i + 1) : 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool on = te.k0 + e < te.k1;
+        te.j[e] = on ? __ldg(dst + te.k0 + e) : 0;
+        te.e0[e] = __int_as_float(on ? __ldg(kin + te.k0 + e) : 0);
+        te.e1[e] = 0.f;
+    }
+}
+
 struct TcCtx {
     uint8_t* wbuf[2];        // double-buffered weight image slot, filled by bulk copies one conv ahead
     uint64_t* wfull;         // [2] "image landed" barriers (byte-counted)
