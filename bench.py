@@ -159,28 +159,43 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def attention_roofline(model, csr, dev, iters=20):
-    """Time the dominant message-passing kernel (decoder h-stack attention forward, G=4, D=32) alone with CUDA
-    events, flushing L2 between launches.  Algorithmic bytes per launch."""
-    from quadtree_mpnnlstm_b200 import _lib
-    N, E, G, D = csr.n_nodes, csr.n_edges, 4, HIDDEN
-    x = torch.randn(N, D, device=dev)
-    U = torch.randn(N, G * (D + 2), device=dev)
-    Z = torch.empty(N, G * (D + 3), device=dev)
-    logit, ms, li = torch.empty(E, G, device=dev), torch.empty(N, G, device=dev), torch.empty(N, G, device=dev)
+def cell_roofline(model, csr, dev, iters=20):
+    """Time the dominant kernel of the step -- the fused decoder-cell forward (qmp_fused_fwd_tc: 8 TransformerConvs'
+    message passing over the CSR + their gate contractions on tcgen05 + the LSTM gate epilogue, ONE launch per
+    forecast step) -- alone with CUDA events on the launching stream, flushing L2 between launches.
+    Algorithmic bytes per launch: DESIGN.md section 5 (inputs X, H, C + CSR + edge attributes; outputs O, H', C',
+    head input; activations saved for the backward pass: gates, raw cell state, edge logits, softmax statistics)."""
+    from quadtree_mpnnlstm_b200 import _lib, fused
+    N, E, C = csr.n_nodes, csr.n_edges, HIDDEN
+    cell = model.decoder.rnns[0]
+    F_in = cell.in_channels
+    with torch.no_grad():
+        wa = fused.tc_image(fused.pack_fused(cell._convs("x", 0), fused.cap_of(F_in, True)), fused.cap_of(F_in, True))
+        wb = fused.tc_image(fused.pack_fused(cell._convs("h", 0), C), C)
+        prm = cell._gate_params(-1, model.decoder.norm_h, model.decoder.norm_c, model.decoder.norm_o).contiguous()
+    f32 = dict(dtype=torch.float32, device=dev)
+    X, Hs, Cs, cc = torch.randn(N, F_in, **f32), torch.randn(N, C, **f32), torch.randn(N, C, **f32), torch.randn(N, **f32)
+    gates = torch.empty(N, 4 * C, **f32)
+    Craw, O, Hn, Cn = (torch.empty(N, C, **f32) for _ in range(4))
+    head = torch.empty(N, fused.HEADW, **f32)
+    logit, ms, li = torch.empty(E, 8, **f32), torch.empty(N, 8, **f32), torch.empty(N, 8, **f32)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     for k in range(iters + 3):
         flush.zero_()
         if k >= 3:
             ev[k - 3][0].record()
-        _lib.call("qmp_attn_fwd", N, G, D, csr.in_ptr, csr.in_src, csr.edge_attr_in, x, D, 0, U, Z, logit, ms, li, 0.0, 0)
+        _lib.call("qmp_fused_fwd_tc", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, X, F_in, F_in, 4, wa, Hs, C, C, 4, 1, wb,
+                  1, 0, C, None, 8 * C, Cs, prm, 1, 1, 1, 1e-5, gates, Craw, O, Hn, Cn, head, fused.HEADW, cc, logit, ms, li,
+                  0.0, 0)
         if k >= 3:
             ev[k - 3][1].record()
     torch.cuda.synchronize()
     ms_avg = sum(a.elapsed_time(b) for a, b in ev) / iters
-    bytes_alg = 4 * (N * D + N * G * (D + 2) + (N + 1) + E + 2 * E) + 4 * (N * G * (D + 3) + E * G + 2 * N * G)
-    return ms_avg, bytes_alg
+    reads = 4 * (N * (F_in + 2 * C) + N) + 4 * (N + 1 + E) + 8 * E          # X, H, C, concat; CSR; edge attributes
+    writes = 4 * (3 * N * C + N * fused.HEADW)                                # O, H', C', head input
+    saved = 4 * (4 * N * C + N * C + 8 * E + 16 * N)                          # gates, raw C', logits, softmax max / 1/sum
+    return ms_avg, reads + writes + saved
 
 
 def run_gpu(args):
@@ -268,7 +283,12 @@ def run_gpu(args):
         else:
             topo = step.topology
         csr = get_csr(*topo)
-        k_ms, k_bytes = attention_roofline(model, csr, dev)
+        k_ms, k_bytes = cell_roofline(model, csr, dev)
+        traffic = None
+        try:      # dram bytes of the same kernel from the committed ncu --set full capture (profiles/), per launch
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_kernel_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
         achieved = k_bytes / (k_ms * 1e-3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": "graph-frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -282,9 +302,10 @@ def run_gpu(args):
                 "e2e": {"value": e2e, "unit": "graph-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
                 "clocks": clocks.summary(),
-                "roofline": {"bound": "hbm", "kernel": "attn_fwd_kernel<4> (decoder h-stack, G=4, D=32)",
+                "roofline": {"bound": "hbm", "kernel": "fused_fwd_tc_kernel<4,32> (decoder cell forward: 8 convs' message "
+                                                         "passing + tcgen05 gate contractions + LSTM epilogue, one launch)",
                              "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                             "traffic": None, "ms_per_launch": k_ms, "algorithmic_bytes": k_bytes,
+                             "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes": k_bytes,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650"}}
         if world == 1 and not args.no_cpu:
             rate, dt, done, what = cpu_oracle_rate(os.cpu_count() or 1, seconds_target=15.0)

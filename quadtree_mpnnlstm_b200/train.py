@@ -17,6 +17,15 @@ import torch
 from .graph_functions import flatten
 
 
+def shard_launch_dates(n_dates, rank, world, seed=0):
+    """Launch dates (sample indices) of one rank: a seed-fixed permutation dealt round-robin, the same count on every
+    rank (the remainder is dropped) so that every optimizer step has exactly one gradient all-reduce on all ranks."""
+    import numpy as np
+    perm = np.random.default_rng(seed).permutation(n_dates) if seed else np.arange(n_dates)
+    per = n_dates // world
+    return [int(d) for d in perm[rank:per * world:world]]
+
+
 class TrainStep:
     def __init__(self, model, mask, lr=1e-4, graph_structure=None, use_cuda_graph=True, process_group=None,
                  world_size=1, max_norm=10.0):
