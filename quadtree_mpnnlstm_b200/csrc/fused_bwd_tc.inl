@@ -57,7 +57,7 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
     constexpr TcBwdTLayout L(DC);
     const int t = threadIdx.x;
     const int buf = cx.toggle;
-    uint8_t* wb = cx.wbuf[buf];
+    uint8_t* wb = cx.wbase + (size_t)buf * cx.wslot;
     const float* __restrict__ xin = st.xin;
     const int ld = st.ld, D = st.D, c = st.c;
     const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0);
@@ -77,7 +77,7 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
     tc::fence_before_sync();
     __syncthreads();
     if (t == 0) {
-        tc::mbar_wait(cx.wfull + buf, cx.wparity[buf]);
+        tc::mbar_wait(cx.wfull + buf, (cx.wpar >> buf) & 1u);
         tc::fence_after_sync();
         tc_mma3(cx.tmem, TC_U, tc::smem_u32(wb + L.W2TH), tc::smem_u32(wb + L.W2TL), L.N2, FC, false);
         if (need_dx) tc_mma3(cx.tmem, st.pcol, tc::smem_u32(wb + L.W3TH), tc::smem_u32(wb + L.W3TL), L.N1P, FC, !st.first);
@@ -199,7 +199,7 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
             }
         }
     }
-    cx.wparity[buf] ^= 1;
+    cx.wpar ^= 1u << buf;
     cx.toggle ^= 1;
 }
 
@@ -210,7 +210,7 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
     constexpr TcBwdSLayout L(DC);
     const int t = threadIdx.x;
     const int buf = cx.toggle;
-    uint8_t* wb = cx.wbuf[buf];
+    uint8_t* wb = cx.wbase + (size_t)buf * cx.wslot;
     const float* __restrict__ xin = st.xin;
     const int ld = st.ld, D = st.D, c = st.c;
     const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0);
@@ -263,7 +263,7 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
     tc::fence_before_sync();
     __syncthreads();
     if (t == 0) {
-        tc::mbar_wait(cx.wfull + buf, cx.wparity[buf]);
+        tc::mbar_wait(cx.wfull + buf, (cx.wpar >> buf) & 1u);
         tc::fence_after_sync();
         tc_mma3_at(cx.tmem, st.pcol, TCS_AH, TCS_AL, tc::smem_u32(wb + L.BSH), tc::smem_u32(wb + L.BSL), L.N1P, L.KS, !st.first);
         tc::commit(cx.bar);
@@ -280,7 +280,7 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
                 if (k < D) row[k] += dx[k];
         }
     }
-    cx.wparity[buf] ^= 1;
+    cx.wpar ^= 1u << buf;
     cx.toggle ^= 1;
 }
 
@@ -306,10 +306,10 @@ __global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_const
     __syncthreads();
     tc::fence_after_sync();
     TcCtx cx;
-    cx.wbuf[0] = smem;
-    cx.wbuf[1] = smem + SLOT;
+    cx.wbase = smem;
+    cx.wslot = SLOT;
     cx.wfull = &bars[1];
-    cx.wparity[0] = cx.wparity[1] = 0;
+    cx.wpar = 0;
     cx.toggle = 0;
     cx.bar = &bars[0];
     cx.parity = 0;

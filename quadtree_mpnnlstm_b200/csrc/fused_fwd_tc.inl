@@ -52,7 +52,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
     constexpr TcFwdLayout L(DC);
     const int t = threadIdx.x;
     const int buf = cx.toggle;
-    uint8_t* wb = cx.wbuf[buf];
+    uint8_t* wb = cx.wbase + (size_t)buf * cx.wslot;
     const float* __restrict__ xin = st.xin;
     const int ld = st.ld, D = st.D, c = st.c;
     const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0);
@@ -67,7 +67,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
     tc::fence_before_sync();
     __syncthreads();
     if (t == 0) {
-        tc::mbar_wait(cx.wfull + buf, cx.wparity[buf]);
+        tc::mbar_wait(cx.wfull + buf, (cx.wpar >> buf) & 1u);
         tc::fence_after_sync();
         tc_mma3(cx.tmem, TC_U, tc::smem_u32(wb + L.W1H), tc::smem_u32(wb + L.W1L), L.N1, L.K1, false);
         tc_mma3(cx.tmem, st.pcol, tc::smem_u32(wb + L.W3H), tc::smem_u32(wb + L.W3L), FC, L.K1, !st.first);
@@ -80,7 +80,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
         load_row<DC>(xa, xin + (size_t)te.j[0] * ld, D, vec);
         if (k0 + 1 < k1) load_row<DC>(xb, xin + (size_t)te.j[1] * ld, D, vec);
     }
-    tc::mbar_wait(cx.wfull + buf, cx.wparity[buf]);       // biases below are read from the image
+    tc::mbar_wait(cx.wfull + buf, (cx.wpar >> buf) & 1u);       // biases below are read from the image
     tc::mbar_wait(cx.bar, cx.parity);
     cx.parity ^= 1;
     tc::fence_after_sync();
@@ -140,7 +140,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
         tc::commit(cx.bar);
     }
     cx.pending = true;
-    cx.wparity[buf] ^= 1;
+    cx.wpar ^= 1u << buf;
     cx.toggle ^= 1;
 }
 
@@ -211,10 +211,10 @@ __global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_const
     __syncthreads();
     tc::fence_after_sync();
     TcCtx cx;
-    cx.wbuf[0] = smem;
-    cx.wbuf[1] = smem + SLOT;
+    cx.wbase = smem;
+    cx.wslot = SLOT;
     cx.wfull = &bars[1];
-    cx.wparity[0] = cx.wparity[1] = 0;
+    cx.wpar = 0;
     cx.toggle = 0;
     cx.bar = &bars[0];
     cx.parity = 0;

@@ -189,10 +189,11 @@ __device__ __forceinline__ void tc_load_out_edges(TcEdges& te, const int* __rest
     }
 }
 
-struct TcCtx {
-    uint8_t* wbuf[2];        // double-buffered weight image slot, filled by bulk copies one conv ahead
+struct TcCtx {                // scalars only (no indexed members): stays in registers
+    uint8_t* wbase;          // double-buffered weight image slot (slot b at wbase + b * wslot), filled one conv ahead
+    uint32_t wslot;
     uint64_t* wfull;         // [2] "image landed" barriers (byte-counted)
-    uint32_t wparity[2];
+    uint32_t wpar;           // bit b = phase parity of wfull[b]
     int toggle;              // slot of the current conv
     uint64_t* bar;           // all MMA groups of this CTA commit here, every commit is waited exactly once
     uint32_t parity;
@@ -203,7 +204,7 @@ struct TcCtx {
 // one thread: start the bulk copy of a conv's image into slot `buf`
 __device__ __forceinline__ void tc_prefetch_image(TcCtx& cx, int buf, const uint8_t* img, uint32_t bytes) {
     tc::mbar_expect_tx(cx.wfull + buf, bytes);
-    tc::bulk_g2s(cx.wbuf[buf], img, bytes, cx.wfull + buf);
+    tc::bulk_g2s(cx.wbase + (size_t)buf * cx.wslot, img, bytes, cx.wfull + buf);
 }
 
 __device__ __forceinline__ void tc_wait(TcCtx& cx) {
