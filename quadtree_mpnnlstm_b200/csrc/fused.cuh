@@ -22,14 +22,18 @@ template <int DC> struct ConvSizes {
     static constexpr int TOTAL = W1 + B1 + W2 + W3 + B3;      // floats per conv in shared memory (multiple of 4)
 };
 
+// counter-based keep mask for attention dropout: same (seed, edge slot, conv) -> same decision in every kernel of the
+// fused family (forward, backward target / source, FFMA or tcgen05).  32-bit mix (murmur3 finaliser) of the slot index
+// and both halves of the seed: a handful of integer instructions per edge.
 __device__ __forceinline__ float fdropout_scale(unsigned long long seed, long long idx, float p) {
     if (p <= 0.f) return 1.f;
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(idx + 1);
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    z ^= z >> 31;
-    const float u = (float)(z >> 40) * (1.0f / 16777216.0f);
-    return (u >= p) ? 1.f / (1.f - p) : 0.f;
+    unsigned int h = (unsigned int)idx * 0x9E3779B1u + (unsigned int)seed;
+    h ^= h >> 16; h *= 0x85EBCA6Bu;
+    h ^= (unsigned int)(seed >> 32);
+    h ^= h >> 13; h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
+    return (u >= p) ? __fdividef(1.f, 1.f - p) : 0.f;
 }
 
 // zero-padded row load; vec = rows are 16-byte aligned and D % 4 == 0
@@ -85,7 +89,12 @@ __device__ __forceinline__ void matvec_acc(float (&y)[R], const float* __restric
     }
 }
 
-__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+// gate nonlinearities on the fast exp / divide units (relative error ~1e-6, far inside the 1e-4 parity bar)
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float ftanh(float x) {
+    const float e = __expf(-2.f * fabsf(x));                    // in (0, 1]: no overflow
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
 
 // LayerNorm over FC register values (biased variance, like torch.nn.LayerNorm)
 __device__ __forceinline__ void ln_stats(const float (&x)[FC], float eps, float& mean, float& rstd) {

@@ -93,7 +93,7 @@ __device__ __forceinline__ void conv_bwd_target(const FusedBwdArgs& a, int i, in
 #pragma unroll
         for (int k = 0; k < DC; ++k) dal = fmaf(dz[k], xj[k], dal);
         dal *= fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
-        const float al = expf(a.logit[(size_t)kk * a.NC + c] - m) * li;
+        const float al = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li;
         tsum = fmaf(al, dal, tsum);
         a.ds[(size_t)kk * a.NC + c] = dal;       // stash, finalised in pass 2
     }
@@ -105,7 +105,7 @@ __device__ __forceinline__ void conv_bwd_target(const FusedBwdArgs& a, int i, in
         float xj[DC];
         load_row<DC>(xj, xin + (size_t)j * ld, D, vec);
         const float a0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
-        const float al = expf(a.logit[(size_t)kk * a.NC + c] - m) * li;
+        const float al = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li;
         const float dsv = al * (a.ds[(size_t)kk * a.NC + c] - tsum);
         a.ds[(size_t)kk * a.NC + c] = dsv;
         const float alk = al * fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
@@ -194,7 +194,7 @@ __device__ __forceinline__ void conv_bwd_source(const FusedBwdArgs& a, int j, in
     const int k1 = a.ptr[j + 1];
     for (int kk = a.ptr[j]; kk < k1; ++kk) {
         const int i = a.nbr[kk], kin = a.kin[kk];
-        const float al = expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
+        const float al = __expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
                          fdropout_scale(a.seed, (long long)kin * a.NC + c, a.drop_p);
         const float dsv = a.ds[(size_t)kin * a.NC + c];
         float g[FC];

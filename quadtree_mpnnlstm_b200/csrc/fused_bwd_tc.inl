@@ -93,7 +93,7 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
     float al4[4], dal4[4];                   // alpha and d alpha of edges 0..3 stay in registers between the passes
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        al4[e] = (k0 + e < k1) ? expf(a.logit[(size_t)(k0 + e) * a.NC + c] - m) * li : 0.f;
+        al4[e] = (k0 + e < k1) ? __expf(a.logit[(size_t)(k0 + e) * a.NC + c] - m) * li : 0.f;
         dal4[e] = 0.f;
     }
     tc::mbar_wait(cx.bar, cx.parity);
@@ -130,7 +130,7 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
         const float a0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
         const float dal = dalpha(kk, xa, a0, a1);
-        tsum = fmaf(expf(a.logit[(size_t)kk * a.NC + c] - m) * li, dal, tsum);
+        tsum = fmaf(__expf(a.logit[(size_t)kk * a.NC + c] - m) * li, dal, tsum);
         a.ds[(size_t)kk * a.NC + c] = dal;
     }
     // pass 2: ds, du = sum ds x_j, z = sum alpha x_j
@@ -168,7 +168,7 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
     for (int kk = k0 + 4; kk < k1; ++kk) {
         load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
         const float a0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
-        accum(kk, xa, a0, a1, expf(a.logit[(size_t)kk * a.NC + c] - m) * li, a.ds[(size_t)kk * a.NC + c]);
+        accum(kk, xa, a0, a1, __expf(a.logit[(size_t)kk * a.NC + c] - m) * li, a.ds[(size_t)kk * a.NC + c]);
     }
     if (valid) {
         store_row<DC + 4>(st.Zs + ((size_t)i * st.G + st.gseg) * (DC + 4), z, true);
@@ -226,7 +226,7 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
         A[FC + L.K1] += dsv;
     };
     auto coef = [&](int i, int kin, float& al, float& dsv) {
-        al = expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
+        al = __expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
              fdropout_scale(a.seed, (long long)kin * a.NC + c, a.drop_p);
         dsv = a.ds[(size_t)kin * a.NC + c];
     };

@@ -62,7 +62,7 @@ __device__ __forceinline__ void conv_accumulate(const FusedFwdArgs& a, int i, in
         for (int k = 0; k < DC; ++k) s = fmaf(u[k], xj[k], s);
         a.logit[(size_t)kk * a.NC + c] = s;
         const float mn = fmaxf(m, s);
-        const float sc = expf(m - mn), p = expf(s - mn);
+        const float sc = __expf(m - mn), p = __expf(s - mn);
         const float pk = p * fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
         l = fmaf(l, sc, p);
         zs = fmaf(zs, sc, pk);
@@ -132,7 +132,7 @@ __device__ __forceinline__ void gate_epilogue(const FusedFwdArgs& a, int i, int 
         load_row<FC>(I, gs, FC, true);            // written by this thread in slots 0 / 1
         load_row<FC>(Fg, gs + FC, FC, true);
 #pragma unroll
-        for (int o = 0; o < FC; ++o) P[o] = tanhf(P[o] + prm[5 * FC + o]);
+        for (int o = 0; o < FC; ++o) P[o] = ftanh(P[o] + prm[5 * FC + o]);
         store_row<FC>(gs + 2 * FC, P, true);
 #pragma unroll
         for (int o = 0; o < FC; ++o) P[o] = fmaf(Fg[o], cp[o], I[o] * P[o]);
@@ -150,7 +150,7 @@ __device__ __forceinline__ void gate_epilogue(const FusedFwdArgs& a, int i, int 
     {
         float Hh[FC];
 #pragma unroll
-        for (int o = 0; o < FC; ++o) Hh[o] = P[o] * tanhf(Cn[o]);
+        for (int o = 0; o < FC; ++o) Hh[o] = P[o] * ftanh(Cn[o]);
         if (a.norm_h) {
             ln_stats(Hh, a.eps, mean, rstd);
 #pragma unroll

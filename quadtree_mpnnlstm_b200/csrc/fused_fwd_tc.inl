@@ -21,7 +21,8 @@ struct TcStep {
     const uint8_t* img; uint32_t bytes;      // this conv's weight image
     const float* xin; int ld, D;             // its input rows
     int c;                                   // conv index in the group (column of logit / mstat / linv)
-    uint32_t pcol;                           // TMEM column of the P block it accumulates into
+    uint32_t pcol;                           // column inside the P block it accumulates into
+    int slot;                                // gate (gate mode) / conv (plain mode) the block belongs to
     bool segA, first, last;                  // first / last conv feeding that block
 };
 
@@ -35,7 +36,7 @@ __device__ __forceinline__ void tc_edge(const FusedFwdArgs& a, int kk, int c, co
     for (int k = 0; k < DC; ++k) s = fmaf(u[k], xj[k], s);
     a.logit[(size_t)kk * a.NC + c] = s;
     const float mn = fmaxf(m, s);
-    const float sc = expf(m - mn), p = expf(s - mn);
+    const float sc = __expf(m - mn), p = __expf(s - mn);
     const float pk = p * fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
     l = fmaf(l, sc, p);
     zs = fmaf(zs, sc, pk);
@@ -62,15 +63,16 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
     // (2) the previous conv's second contraction must be done with the A columns and with the other weight slot
     if (cx.pending) tc_wait(cx);
     if (t == 0 && has_next) tc_prefetch_image(cx, buf ^ 1, nx.img, nx.bytes);      // next conv's image, one conv ahead
-    tc_stage_a<L.K1>(cx.lane_base, x);
+    tc_stage_a_at<L.K1>(cx.lane_off, cx.ah_col, cx.al_col, x);
     tc::tmem_st_wait();
     tc::fence_before_sync();
     __syncthreads();
     if (t == 0) {
         tc::mbar_wait(cx.wfull + buf, (cx.wpar >> buf) & 1u);
         tc::fence_after_sync();
-        tc_mma3(cx.tmem, TC_U, tc::smem_u32(wb + L.W1H), tc::smem_u32(wb + L.W1L), L.N1, L.K1, false);
-        tc_mma3(cx.tmem, st.pcol, tc::smem_u32(wb + L.W3H), tc::smem_u32(wb + L.W3L), FC, L.K1, !st.first);
+        tc_mma3_at(0, cx.u_col, cx.ah_col, cx.al_col, tc::smem_u32(wb + L.W1H), tc::smem_u32(wb + L.W1L), L.N1, L.K1, false);
+        tc_mma3_at(0, cx.p_base + st.pcol, cx.ah_col, cx.al_col, tc::smem_u32(wb + L.W3H), tc::smem_u32(wb + L.W3L), FC, L.K1,
+                   !st.first);
         tc::commit(cx.bar);
     }
     // (3) first pair of neighbour rows: issued before the wait for U
@@ -89,7 +91,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
     {
         constexpr int N8 = (DC + 2 + 7) / 8;
         float tmp[N8 * 8];
-        tc_load_cols<N8>(cx.lane_base, TC_U, tmp);
+        tc_load_cols<N8>(cx.lane_off, cx.u_col, tmp);
         const float* b1 = reinterpret_cast<const float*>(wb + L.B1);
 #pragma unroll
         for (int k = 0; k < DC; ++k) u[k] = tmp[k] + b1[k];
@@ -129,14 +131,14 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
         zz[DC] = ze0 * li;
         zz[DC + 1] = ze1 * li;
         zz[DC + 2] = zs * li;
-        tc_stage_a<L.K2>(cx.lane_base, zz);
+        tc_stage_a_at<L.K2>(cx.lane_off, cx.ah_col, cx.al_col, zz);
     }
     tc::tmem_st_wait();
     tc::fence_before_sync();
     __syncthreads();
     if (t == 0) {
         tc::fence_after_sync();
-        tc_mma3(cx.tmem, st.pcol, tc::smem_u32(wb + L.W2H), tc::smem_u32(wb + L.W2L), FC, L.K2, true);
+        tc_mma3_at(0, cx.p_base + st.pcol, cx.ah_col, cx.al_col, tc::smem_u32(wb + L.W2H), tc::smem_u32(wb + L.W2L), FC, L.K2, true);
         tc::commit(cx.bar);
     }
     cx.pending = true;
@@ -147,7 +149,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
 // P block -> registers, plus the skip biases of the convs that fed it
 __device__ __forceinline__ void tc_collect(TcCtx& cx, uint32_t pcol, float (&P)[FC]) {
     if (cx.pending) tc_wait(cx);
-    tc_load_cols<FC / 8>(cx.lane_base, pcol, P);
+    tc_load_cols<FC / 8>(cx.lane_off, cx.p_base + pcol, P);
 }
 __device__ __forceinline__ void tc_add_bias(float (&P)[FC], const uint8_t* __restrict__ img, int b3_off) {
     const float4* b = reinterpret_cast<const float4*>(img + b3_off);
@@ -172,12 +174,14 @@ __device__ __forceinline__ void tc_fwd_step(const FusedFwdArgs& a, int k, TcStep
         g = st.segA ? s : s + 4 * (r - hasA);
         st.first = r == 0;
         st.last = r == cps - 1;
-        st.pcol = TC_P + (uint32_t)s * FC;
+        st.pcol = 0;
+        st.slot = s;
     } else {
         st.segA = k < a.GA;
         g = st.segA ? k : k - a.GA;
         st.first = st.last = true;
-        st.pcol = TC_P;
+        st.pcol = 0;
+        st.slot = k;
     }
     if (st.segA) {
         st.img = imgA + (size_t)g * LA.BYTES; st.bytes = LA.BYTES; st.xin = a.xa; st.ld = a.lda; st.D = a.DA; st.c = g;
@@ -188,10 +192,10 @@ __device__ __forceinline__ void tc_fwd_step(const FusedFwdArgs& a, int k, TcStep
 }
 
 template <int DAC, int DBC>
-__global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_constant__ FusedFwdArgs a) {
+__global__ void __launch_bounds__(128, 3) fused_fwd_tc_kernel(const __grid_constant__ FusedFwdArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[3];
-    __shared__ uint32_t tmem_slot;
+    __shared__ uint32_t tmem_slot[2];
     constexpr int DA_ = DAC > 0 ? DAC : 4;
     constexpr TcFwdLayout LA(DA_), LB(DBC);
     constexpr int SLOT = (LA.BYTES > LB.BYTES ? LA.BYTES : LB.BYTES);
@@ -204,7 +208,11 @@ __global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_const
         tc::fence_mbar_init();
     }
     __syncwarp();
-    if (warp == 0) tc::tmem_alloc(&tmem_slot, TC_COLS);
+    if (warp == 0) {            // 128 columns (U 48 | A_hi 40 | A_lo 40) + 32 columns (P): 160 per CTA, three CTAs per SM
+        tc::tmem_alloc_only(&tmem_slot[0], 128);
+        tc::tmem_alloc_only(&tmem_slot[1], 32);
+        tc::tmem_relinquish();
+    }
     if (a.mode == 1)
         for (int idx = t; idx < 13 * FC; idx += 128) prm[idx] = a.params[idx];
     tc::fence_before_sync();
@@ -219,8 +227,13 @@ __global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_const
     cx.bar = &bars[0];
     cx.parity = 0;
     cx.pending = false;
-    cx.tmem = tmem_slot;
-    cx.lane_base = cx.tmem + ((uint32_t)(warp * 32) << 16);
+    cx.tmem = tmem_slot[0];
+    cx.lane_off = (uint32_t)(warp * 32) << 16;
+    cx.lane_base = cx.tmem + cx.lane_off;
+    cx.u_col = cx.tmem + 0;
+    cx.ah_col = cx.tmem + 48;
+    cx.al_col = cx.tmem + 88;
+    cx.p_base = tmem_slot[1];
 
     const int ntiles = (a.N + 127) / 128;
     const int nsteps = (a.mode == 1) ? 4 * ((a.GA ? 1 : 0) + (a.GB == 8 ? 2 : 1)) : a.NC;
@@ -250,7 +263,7 @@ __global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_const
             float P[FC];
             tc_collect(cx, st.pcol, P);
             if (a.mode == 1) {
-                const int s = (int)(st.pcol - TC_P) / FC;
+                const int s = st.slot;
                 if constexpr (DAC > 0) {
                     if (a.GA) tc_add_bias(P, reinterpret_cast<const uint8_t*>(a.wa) + (size_t)s * LA.BYTES, LA.B3);
                 }
@@ -279,7 +292,10 @@ __global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_const
     if (cx.pending) tc_wait(cx);
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(cx.tmem, TC_COLS);
+    if (warp == 0) {
+        tc::tmem_dealloc(cx.tmem, 128);
+        tc::tmem_dealloc(cx.p_base, 32);
+    }
 }
 
 template <int DAC, int DBC>
@@ -297,7 +313,7 @@ int launch_fwd_tc(const FusedFwdArgs& a, cudaStream_t st) {
     auto kern = fused_fwd_tc_kernel<DAC, DBC>;
     QMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = cdiv(a.N, 128);
-    const int grid = ntiles < 2 * n_sm ? ntiles : 2 * n_sm;
+    const int grid = ntiles < 3 * n_sm ? ntiles : 3 * n_sm;
     kern<<<grid, 128, smem, st>>>(a);
     QMP_LAUNCH_CHECK("fused_fwd_tc_kernel");
     return 0;

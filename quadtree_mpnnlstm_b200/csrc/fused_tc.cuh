@@ -190,6 +190,8 @@ __device__ __forceinline__ void tc_load_out_edges(TcEdges& te, const int* __rest
 }
 
 struct TcCtx {                // scalars only (no indexed members): stays in registers
+    uint32_t u_col, ah_col, al_col;   // TMEM addresses (allocation base + column) of U and the A operand halves
+    uint32_t p_base;                   // TMEM address of the P block (may be a separate allocation)
     uint8_t* wbase;          // double-buffered weight image slot (slot b at wbase + b * wslot), filled one conv ahead
     uint32_t wslot;
     uint64_t* wfull;         // [2] "image landed" barriers (byte-counted)
@@ -198,7 +200,7 @@ struct TcCtx {                // scalars only (no indexed members): stays in reg
     uint64_t* bar;           // all MMA groups of this CTA commit here, every commit is waited exactly once
     uint32_t parity;
     bool pending;            // a committed group has not been waited yet
-    uint32_t tmem, lane_base;
+    uint32_t tmem, lane_base, lane_off;
 };
 
 // one thread: start the bulk copy of a conv's image into slot `buf`
