@@ -19,7 +19,7 @@ REPO = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libqmp_b200.so")
 HEADER = os.path.join(REPO, "include", "qmp_b200.h")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = (["-DQMP_TIMING_TF32X1"] if os.environ.get("QMP_TIMING_TF32X1") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
 
 REPLACES = {  # entry point -> reference interface it stands in for

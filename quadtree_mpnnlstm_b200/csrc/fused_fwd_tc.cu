@@ -21,6 +21,10 @@ QMP_API int qmp_fused_fwd_tc(int N, const int* in_ptr, const int* in_src, const 
     QMP_REQUIRE(GB >= 1 && DB >= 1 && DB <= 36 && DA >= 0 && DA <= 8 && C >= 1 && C <= FC, "qmp_fused_fwd_tc: unsupported sizes");
     QMP_REQUIRE(mode == 0 || ((GA == 0 || GA == 4) && (GB == 4 || GB == 8) && C == FC), "qmp_fused_fwd_tc: gate mode needs 4 gates");
     QMP_REQUIRE(sharedB || GB == 8 || mode == 0, "qmp_fused_fwd_tc: own-input gate mode needs 8 convs");
+    QMP_REQUIRE(DB % 4 == 0 && ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0 &&
+                    (GA == 0 || (DA % 4 == 0 && lda % 4 == 0 && (reinterpret_cast<uintptr_t>(xa) & 15) == 0)),
+                "qmp_fused_fwd_tc: input rows must be 16-byte aligned with a multiple of 4 columns (pad them)");
+    QMP_REQUIRE(DB == 32 || DB == 36, "qmp_fused_fwd_tc: segment B rows are 32 or 36 floats wide");
     FusedFwdArgs a{};
     a.N = N; a.ptr = in_ptr; a.nbr = in_src; a.ea = ea; a.xa = xa; a.lda = lda; a.DA = DA; a.GA = GA;
     a.wa = reinterpret_cast<const float*>(wa);

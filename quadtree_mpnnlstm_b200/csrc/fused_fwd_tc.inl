@@ -56,10 +56,15 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
     uint8_t* wb = cx.wbase + (size_t)buf * cx.wslot;
     const float* __restrict__ xin = st.xin;
     const int ld = st.ld, D = st.D, c = st.c;
-    const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0);
+    constexpr bool vec = true;                 // the C entry point requires 16-byte aligned rows with D % 4 == 0
     // (1) own row (in flight while the previous conv's second contraction drains)
     float x[L.K1];
-    tc_load_row<L.K1>(x, xin + (size_t)i * ld, D, vec, valid);
+    constexpr bool co = DC == 32;              // coalesced row I/O (fused_tc.cuh) for the 32-float rows (D == 32 required)
+    if constexpr (co) {
+        warp_load_rows32(cx.rtile, xin, ld, valid ? i : -1, x);
+    } else {
+        tc_load_row<L.K1>(x, xin + (size_t)i * ld, D, vec, valid);
+    }
     // (2) the previous conv's second contraction must be done with the A columns and with the other weight slot
     if (cx.pending) tc_wait(cx);
     if (t == 0 && has_next) tc_prefetch_image(cx, buf ^ 1, nx.img, nx.bytes);      // next conv's image, one conv ahead
@@ -78,7 +83,10 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
     // (3) first pair of neighbour rows: issued before the wait for U
     const int k0 = te.k0, k1 = te.k1;
     float xa[DC], xb[DC];
-    if (k0 < k1) {
+    if constexpr (co) {
+        if (__any_sync(0xffffffffu, k0 < k1))
+            warp_load_rows32x2(cx.rtile, xin, ld, k0 < k1 ? te.j[0] : -1, k0 + 1 < k1 ? te.j[1] : -1, xa, xb);
+    } else if (k0 < k1) {
         load_row<DC>(xa, xin + (size_t)te.j[0] * ld, D, vec);
         if (k0 + 1 < k1) load_row<DC>(xb, xin + (size_t)te.j[1] * ld, D, vec);
     }
@@ -103,18 +111,38 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
 #pragma unroll
     for (int k = 0; k < DC; ++k) z[k] = 0.f;
     float m = -INFINITY, l = 0.f, zs = 0.f, ze0 = 0.f, ze1 = 0.f;
-    if (k0 < k1) {                          // edges 0..3: indices and attributes were loaded once per tile
-        tc_edge<DC>(a, k0, c, u, w01, xa, te.e0[0], te.e1[0], z, m, l, zs, ze0, ze1);
-        if (k0 + 2 < k1) load_row<DC>(xa, xin + (size_t)te.j[2] * ld, D, vec);
-        if (k0 + 1 < k1) tc_edge<DC>(a, k0 + 1, c, u, w01, xb, te.e0[1], te.e1[1], z, m, l, zs, ze0, ze1);
-        if (k0 + 3 < k1) load_row<DC>(xb, xin + (size_t)te.j[3] * ld, D, vec);
-        if (k0 + 2 < k1) tc_edge<DC>(a, k0 + 2, c, u, w01, xa, te.e0[2], te.e1[2], z, m, l, zs, ze0, ze1);
-        if (k0 + 3 < k1) tc_edge<DC>(a, k0 + 3, c, u, w01, xb, te.e0[3], te.e1[3], z, m, l, zs, ze0, ze1);
-    }
-    for (int kk = k0 + 4; kk < k1; ++kk) {   // larger in-degrees (quadtree meshes)
-        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
-        const float e0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, e1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
-        tc_edge<DC>(a, kk, c, u, w01, xa, e0, e1, z, m, l, zs, ze0, ze1);
+    if constexpr (co) {
+        {                                   // warp-cooperative gathers: every lane takes part, absent edges load nothing
+            if (k0 < k1) tc_edge<DC>(a, k0, c, u, w01, xa, te.e0[0], te.e1[0], z, m, l, zs, ze0, ze1);
+            if (k0 + 1 < k1) tc_edge<DC>(a, k0 + 1, c, u, w01, xb, te.e0[1], te.e1[1], z, m, l, zs, ze0, ze1);
+            if (__any_sync(0xffffffffu, k0 + 2 < k1)) {
+                warp_load_rows32x2(cx.rtile, xin, ld, k0 + 2 < k1 ? te.j[2] : -1, k0 + 3 < k1 ? te.j[3] : -1, xa, xb);
+                if (k0 + 2 < k1) tc_edge<DC>(a, k0 + 2, c, u, w01, xa, te.e0[2], te.e1[2], z, m, l, zs, ze0, ze1);
+                if (k0 + 3 < k1) tc_edge<DC>(a, k0 + 3, c, u, w01, xb, te.e0[3], te.e1[3], z, m, l, zs, ze0, ze1);
+            }
+            for (int kk = k0 + 4; __any_sync(0xffffffffu, kk < k1); ++kk) {      // larger in-degrees (quadtree meshes)
+                const bool on = kk < k1;
+                warp_load_rows32(cx.rtile, xin, ld, on ? a.nbr[kk] : -1, xa);
+                if (on) {
+                    const float e0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, e1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
+                    tc_edge<DC>(a, kk, c, u, w01, xa, e0, e1, z, m, l, zs, ze0, ze1);
+                }
+            }
+        }
+    } else {
+        if (k0 < k1) {                          // edges 0..3: indices and attributes were loaded once per tile
+            tc_edge<DC>(a, k0, c, u, w01, xa, te.e0[0], te.e1[0], z, m, l, zs, ze0, ze1);
+            if (k0 + 2 < k1) load_row<DC>(xa, xin + (size_t)te.j[2] * ld, D, vec);
+            if (k0 + 1 < k1) tc_edge<DC>(a, k0 + 1, c, u, w01, xb, te.e0[1], te.e1[1], z, m, l, zs, ze0, ze1);
+            if (k0 + 3 < k1) load_row<DC>(xb, xin + (size_t)te.j[3] * ld, D, vec);
+            if (k0 + 2 < k1) tc_edge<DC>(a, k0 + 2, c, u, w01, xa, te.e0[2], te.e1[2], z, m, l, zs, ze0, ze1);
+            if (k0 + 3 < k1) tc_edge<DC>(a, k0 + 3, c, u, w01, xb, te.e0[3], te.e1[3], z, m, l, zs, ze0, ze1);
+        }
+        for (int kk = k0 + 4; kk < k1; ++kk) {   // larger in-degrees (quadtree meshes)
+            load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+            const float e0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, e1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
+            tc_edge<DC>(a, kk, c, u, w01, xa, e0, e1, z, m, l, zs, ze0, ze1);
+        }
     }
     const float li = (l > 0.f) ? 1.f / l : 0.f;
     if (valid) {
@@ -160,6 +188,85 @@ __device__ __forceinline__ void tc_add_bias(float (&P)[FC], const uint8_t* __res
     }
 }
 
+// Gate epilogue of slot s (same math as fused_fwd.inl gate_epilogue) with coalesced row I/O through the warp's row tile
+// and the I / F / C' rows handed from slot to slot through 96 spare TMEM columns instead of global memory.
+// params rows (lstm.cu): 0 wci 1 wcf 2 wco 3 bi 4 bf 5 bc 6 bo 7 gh 8 bh 9 gc 10 bc 11 go 12 bo
+__device__ __forceinline__ void gate_epilogue_tc(TcCtx& cx, const FusedFwdArgs& a, int row0, int i, bool valid, int s,
+                                                 const float* __restrict__ prm, float (&P)[FC]) {
+    const uint32_t stash = cx.stash_col;
+    float* tile = cx.rtile;
+    if (s <= 2) {
+        float cp[FC];
+        if (a.Cprev) warp_load_rows32(tile, a.Cprev, FC, valid ? i : -1, cp);
+        else {
+#pragma unroll
+            for (int o = 0; o < FC; ++o) cp[o] = 0.f;
+        }
+        if (s < 2) {                 // I, F
+            const float* wc = prm + (s == 0 ? 0 : 1) * FC;
+            const float* bb = prm + (s == 0 ? 3 : 4) * FC;
+#pragma unroll
+            for (int o = 0; o < FC; ++o) P[o] = sigm(P[o] + wc[o] * cp[o] + bb[o]);
+            warp_store_rows32(tile, a.gates + s * FC, 4 * FC, row0, a.N, P);
+            tc_store_cols<FC / 8>(cx.lane_off, stash + (uint32_t)s * FC, P);
+            return;
+        }
+        // s == 2: T, then C' = F C + I T
+        float I[FC], Fg[FC];
+        tc_load_cols<FC / 8>(cx.lane_off, stash, I);
+        tc_load_cols<FC / 8>(cx.lane_off, stash + FC, Fg);
+#pragma unroll
+        for (int o = 0; o < FC; ++o) P[o] = ftanh(P[o] + prm[5 * FC + o]);
+        warp_store_rows32(tile, a.gates + 2 * FC, 4 * FC, row0, a.N, P);
+#pragma unroll
+        for (int o = 0; o < FC; ++o) P[o] = fmaf(Fg[o], cp[o], I[o] * P[o]);
+        warp_store_rows32(tile, a.Craw, FC, row0, a.N, P);
+        tc_store_cols<FC / 8>(cx.lane_off, stash + 2 * FC, P);
+        return;
+    }
+    // s == 3: O, H', norms, head
+    float Cn[FC];
+    tc_load_cols<FC / 8>(cx.lane_off, stash + 2 * FC, Cn);
+#pragma unroll
+    for (int o = 0; o < FC; ++o) P[o] = sigm(P[o] + prm[2 * FC + o] * Cn[o] + prm[6 * FC + o]);   // O
+    warp_store_rows32(tile, a.gates + 3 * FC, 4 * FC, row0, a.N, P);
+    if (a.Oout) warp_store_rows32(tile, a.Oout, FC, row0, a.N, P);
+    float mean, rstd;
+    {
+        float Hh[FC];
+#pragma unroll
+        for (int o = 0; o < FC; ++o) Hh[o] = P[o] * ftanh(Cn[o]);
+        if (a.norm_h) {
+            ln_stats(Hh, a.eps, mean, rstd);
+#pragma unroll
+            for (int o = 0; o < FC; ++o) Hh[o] = (Hh[o] - mean) * rstd * prm[7 * FC + o] + prm[8 * FC + o];
+        }
+        warp_store_rows32(tile, a.Hout, FC, row0, a.N, Hh);
+    }
+    if (a.norm_c) {
+        ln_stats(Cn, a.eps, mean, rstd);
+#pragma unroll
+        for (int o = 0; o < FC; ++o) Cn[o] = (Cn[o] - mean) * rstd * prm[9 * FC + o] + prm[10 * FC + o];
+    }
+    warp_store_rows32(tile, a.Cout, FC, row0, a.N, Cn);
+    if (a.head_in) {
+        if (a.norm_o) {
+            ln_stats(P, a.eps, mean, rstd);
+#pragma unroll
+            for (int o = 0; o < FC; ++o) P[o] = (P[o] - mean) * rstd * prm[11 * FC + o] + prm[12 * FC + o];
+        }
+#pragma unroll
+        for (int o = 0; o < FC; ++o) P[o] = fmaxf(P[o], 0.f);
+        if (a.ldh % 4 == 0) warp_store_rows32(tile, a.head_in, a.ldh, row0, a.N, P);
+        if (valid) {
+            float* hr = a.head_in + (size_t)i * a.ldh;
+            if (a.ldh % 4 != 0) store_row<FC>(hr, P, false);
+            if (a.concat) hr[FC] = a.concat[i];
+            for (int k = FC + 1; k < a.ldh; ++k) hr[k] = 0.f;
+        }
+    }
+}
+
 // conv schedule of a tile.  Gate mode: slot s = gate; its convs are [A[s]], B[s], [B[4+s]].  Plain mode: conv k.
 template <int DA_, int DBC>
 __device__ __forceinline__ void tc_fwd_step(const FusedFwdArgs& a, int k, TcStep& st) {
@@ -192,7 +299,7 @@ __device__ __forceinline__ void tc_fwd_step(const FusedFwdArgs& a, int k, TcStep
 }
 
 template <int DAC, int DBC>
-__global__ void __launch_bounds__(128, 3) fused_fwd_tc_kernel(const __grid_constant__ FusedFwdArgs a) {
+__global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_constant__ FusedFwdArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[3];
     __shared__ uint32_t tmem_slot[2];
@@ -208,11 +315,7 @@ __global__ void __launch_bounds__(128, 3) fused_fwd_tc_kernel(const __grid_const
         tc::fence_mbar_init();
     }
     __syncwarp();
-    if (warp == 0) {            // 128 columns (U 48 | A_hi 40 | A_lo 40) + 32 columns (P): 160 per CTA, three CTAs per SM
-        tc::tmem_alloc_only(&tmem_slot[0], 128);
-        tc::tmem_alloc_only(&tmem_slot[1], 32);
-        tc::tmem_relinquish();
-    }
+    if (warp == 0) tc::tmem_alloc(&tmem_slot[0], TC_COLS);    // U 48 | A_hi 40 | A_lo 40 | P 32 | stash 96 (I, F, C')
     if (a.mode == 1)
         for (int idx = t; idx < 13 * FC; idx += 128) prm[idx] = a.params[idx];
     tc::fence_before_sync();
@@ -233,7 +336,9 @@ __global__ void __launch_bounds__(128, 3) fused_fwd_tc_kernel(const __grid_const
     cx.u_col = cx.tmem + 0;
     cx.ah_col = cx.tmem + 48;
     cx.al_col = cx.tmem + 88;
-    cx.p_base = tmem_slot[1];
+    cx.p_base = cx.tmem + 128;
+    cx.stash_col = cx.tmem + 160;
+    cx.rtile = reinterpret_cast<float*>(smem + 2 * SLOT) + 13 * FC + warp * 2 * TC_ROWTILE;
 
     const int ntiles = (a.N + 127) / 128;
     const int nsteps = (a.mode == 1) ? 4 * ((a.GA ? 1 : 0) + (a.GB == 8 ? 2 : 1)) : a.NC;
@@ -269,7 +374,7 @@ __global__ void __launch_bounds__(128, 3) fused_fwd_tc_kernel(const __grid_const
                 }
                 tc_add_bias(P, reinterpret_cast<const uint8_t*>(a.wb) + (size_t)s * LB.BYTES, LB.B3);
                 if (a.GB == 8) tc_add_bias(P, reinterpret_cast<const uint8_t*>(a.wb) + (size_t)(4 + s) * LB.BYTES, LB.B3);
-                if (valid) gate_epilogue(a, i, s, prm, P);
+                gate_epilogue_tc(cx, a, tile * 128 + warp * 32, i, valid, s, prm, P);
             } else {
                 tc_add_bias(P, st.img, st.segA ? LA.B3 : LB.B3);
                 if (valid) {
@@ -292,10 +397,7 @@ __global__ void __launch_bounds__(128, 3) fused_fwd_tc_kernel(const __grid_const
     if (cx.pending) tc_wait(cx);
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) {
-        tc::tmem_dealloc(cx.tmem, 128);
-        tc::tmem_dealloc(cx.p_base, 32);
-    }
+    if (warp == 0) tc::tmem_dealloc(cx.tmem, TC_COLS);
 }
 
 template <int DAC, int DBC>
@@ -303,7 +405,7 @@ int launch_fwd_tc(const FusedFwdArgs& a, cudaStream_t st) {
     constexpr int DA_ = DAC > 0 ? DAC : 4;
     constexpr TcFwdLayout LA(DA_), LB(DBC);
     constexpr int SLOT = (LA.BYTES > LB.BYTES ? LA.BYTES : LB.BYTES);
-    const size_t smem = 2 * (size_t)SLOT + 13 * FC * sizeof(float);
+    const size_t smem = 2 * (size_t)SLOT + (13 * FC + 4 * 2 * TC_ROWTILE) * sizeof(float);
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
@@ -313,7 +415,7 @@ int launch_fwd_tc(const FusedFwdArgs& a, cudaStream_t st) {
     auto kern = fused_fwd_tc_kernel<DAC, DBC>;
     QMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = cdiv(a.N, 128);
-    const int grid = ntiles < 3 * n_sm ? ntiles : 3 * n_sm;
+    const int grid = ntiles < 2 * n_sm ? ntiles : 2 * n_sm;
     kern<<<grid, 128, smem, st>>>(a);
     QMP_LAUNCH_CHECK("fused_fwd_tc_kernel");
     return 0;

@@ -70,8 +70,10 @@ __device__ __forceinline__ void tc_mma3_at(uint32_t tmem, uint32_t dcol, uint32_
         const uint64_t dbl = tc::make_desc(bl_addr + (uint32_t)ks * 256, 128, sbo);
         const uint32_t ah = tmem + ah_col + (uint32_t)ks * 8, al = tmem + al_col + (uint32_t)ks * 8;
         tc::mma_tf32_ts(tmem + dcol, ah, dbh, idesc, (accumulate || ks > 0) ? 1u : 0u);
+#ifndef QMP_TIMING_TF32X1      // timing experiment only (scripts/kernel_times.py): how much of the step is MMA issue
         tc::mma_tf32_ts(tmem + dcol, al, dbh, idesc, 1);
         tc::mma_tf32_ts(tmem + dcol, ah, dbl, idesc, 1);
+#endif
     }
 }
 
@@ -140,6 +142,19 @@ __device__ __forceinline__ void tc_load_cols(uint32_t lane_base, uint32_t col, f
         for (int i = 0; i < 8; ++i) v[q * 8 + i] = __uint_as_float(r[q][i]);
 }
 
+// N8 * 8 values -> columns of this thread's lane (plain fp32, e.g. a stash)
+template <int N8>
+__device__ __forceinline__ void tc_store_cols(uint32_t lane_base, uint32_t col, const float (&v)[N8 * 8]) {
+#pragma unroll
+    for (int q = 0; q < N8; ++q) {
+        uint32_t r[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[q * 8 + i]);
+        tc::tmem_st8(lane_base + col + (uint32_t)q * 8, r);
+    }
+    tc::tmem_st_wait();
+}
+
 // zero-padded row load into K >= D registers; vec = 16-byte aligned rows with D % 4 == 0
 template <int K>
 __device__ __forceinline__ void tc_load_row(float (&x)[K], const float* __restrict__ p, int D, bool vec, bool valid) {
@@ -154,6 +169,85 @@ __device__ __forceinline__ void tc_load_row(float (&x)[K], const float* __restri
 #pragma unroll
         for (int k = 0; k < K; ++k) x[k] = (valid && k < D) ? __ldg(p + k) : 0.f;
     }
+}
+
+// ---- coalesced row I/O for the thread-per-node layout --------------------------------------------------------------
+// A thread that reads "its" 128-byte row with eight 16-byte loads makes the warp touch 32 different cache lines per
+// instruction: 256 L1 tag lookups per 32 rows, and the L1 tag stage (one line per cycle) becomes the bound of the
+// fused kernels (ncu: 31 M tag requests ~ 107 us of a 118 us launch).  These helpers move the same rows with
+// COALESCED instructions -- 8 lanes per row, 4 rows (4 lines) per instruction -- and transpose through a per-warp
+// shared-memory tile (32 rows x 32 floats, 16-byte chunks XOR-swizzled by the row so that both the row-wise writes and
+// the lane-owns-a-row reads are bank-conflict free).  All 32 lanes of the warp must call them together.
+constexpr int TC_ROWTILE = 32 * 32;             // floats per tile
+
+__device__ __forceinline__ float* tc_tile_chunk(float* tile, int r, int c) { return tile + r * 32 + ((c ^ (r & 7)) << 2); }
+
+// this lane's row = base + j * ld (j < 0: zeros); rows are 32 floats, 16-byte aligned
+__device__ __forceinline__ void warp_load_rows32(float* tile, const float* __restrict__ base, int ld, int j, float (&x)[32]) {
+    const int lane = threadIdx.x & 31, c = lane & 7;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int r = 4 * q + (lane >> 3);
+        const int jr = __shfl_sync(0xffffffffu, j, r);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jr >= 0) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)jr * ld) + c);
+        *reinterpret_cast<float4*>(tc_tile_chunk(tile, r, c)) = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(tc_tile_chunk(tile, lane, k));
+        x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
+    }
+    __syncwarp();
+}
+
+// two independent row sets in one go (both sets of loads are in flight together); needs two tiles
+__device__ __forceinline__ void warp_load_rows32x2(float* tile, const float* __restrict__ base, int ld, int j0, int j1,
+                                                   float (&x0)[32], float (&x1)[32]) {
+    const int lane = threadIdx.x & 31, c = lane & 7;
+    float4 v0[8], v1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int r = 4 * q + (lane >> 3);
+        const int ja = __shfl_sync(0xffffffffu, j0, r), jb = __shfl_sync(0xffffffffu, j1, r);
+        v0[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v1[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ja >= 0) v0[q] = __ldg(reinterpret_cast<const float4*>(base + (size_t)ja * ld) + c);
+        if (jb >= 0) v1[q] = __ldg(reinterpret_cast<const float4*>(base + (size_t)jb * ld) + c);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int r = 4 * q + (lane >> 3);
+        *reinterpret_cast<float4*>(tc_tile_chunk(tile, r, c)) = v0[q];
+        *reinterpret_cast<float4*>(tc_tile_chunk(tile + TC_ROWTILE, r, c)) = v1[q];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(tc_tile_chunk(tile, lane, k));
+        const float4 b = *reinterpret_cast<const float4*>(tc_tile_chunk(tile + TC_ROWTILE, lane, k));
+        x0[4 * k] = a.x; x0[4 * k + 1] = a.y; x0[4 * k + 2] = a.z; x0[4 * k + 3] = a.w;
+        x1[4 * k] = b.x; x1[4 * k + 1] = b.y; x1[4 * k + 2] = b.z; x1[4 * k + 3] = b.w;
+    }
+    __syncwarp();
+}
+
+// the warp's 32 consecutive rows row0 .. row0+31 (those < n_rows are written): lane's row x -> base + (row0 + lane) * ld
+__device__ __forceinline__ void warp_store_rows32(float* tile, float* __restrict__ base, int ld, int row0, int n_rows,
+                                                  const float (&x)[32]) {
+    const int lane = threadIdx.x & 31, c = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(tc_tile_chunk(tile, lane, k)) = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int r = 4 * q + (lane >> 3);
+        if (row0 + r < n_rows)
+            *(reinterpret_cast<float4*>(base + (size_t)(row0 + r) * ld) + c) = *reinterpret_cast<const float4*>(tc_tile_chunk(tile, r, c));
+    }
+    __syncwarp();
 }
 
 // the first four in-edges of this thread's node (all of them on a pixel-wise mesh): loaded once per tile
@@ -201,6 +295,8 @@ struct TcCtx {                // scalars only (no indexed members): stays in reg
     uint32_t parity;
     bool pending;            // a committed group has not been waited yet
     uint32_t tmem, lane_base, lane_off;
+    uint32_t stash_col;      // 96 spare TMEM columns (forward: I, F, C' between the gate slots)
+    float* rtile;            // this warp's two row tiles (shared memory) for the coalesced row I/O
 };
 
 // one thread: start the bulk copy of a conv's image into slot `buf`

@@ -189,6 +189,9 @@ class GConvLSTM(nn.Module):
         """The cell as one fused launch per conv layer (csrc/fused_fwd.inl): layer 0 reads X (4 convs) and H
         (4 convs); deeper layers read the previous layer's 8 blocks; the last layer ends in the gate epilogue."""
         S, Cw, Fin = self.n_conv_layers, self.out_channels, self.in_channels
+        if Fin % 4:                  # the kernels take 16-byte rows: zero-pad X (the packed weights are zero there too)
+            X = F.pad(X, (0, 4 - Fin % 4))
+            Fin = X.shape[1]
         p = self.conv_x_i.convolutions[0].dropout if self.training else 0.0
         seed = (lambda: next_seed()) if p > 0 else (lambda: 0)
         dac = _fused.cap_of(Fin, True)
