@@ -33,6 +33,10 @@ QMP_API int qmp_fused_bwd_target_tc(int N, const int* in_ptr, const int* in_src,
                                     float* dUsB, float* dxa, float* dxb, float drop_p, unsigned long long seed, void* stream) {
     if (N <= 0) return 0;
     QMP_REQUIRE(GB >= 1 && DB >= 1 && DB <= 36 && DA >= 0 && DA <= 8 && C >= 1 && C <= FC, "qmp_fused_bwd_target_tc: unsupported sizes");
+    QMP_REQUIRE((DB == 32 || DB == 36) && ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0 &&
+                    (GA == 0 || (DA % 4 == 0 && lda % 4 == 0 && (reinterpret_cast<uintptr_t>(xa) & 15) == 0)) &&
+                    (reinterpret_cast<uintptr_t>(dP) & 15) == 0 && (mode == 0 || lddp % 4 == 0),
+                "qmp_fused_bwd_*_tc: rows must be 16-byte aligned with a multiple of 4 columns (pad them)");
     FusedBwdArgs a{};
     a.N = N; a.ptr = in_ptr; a.nbr = in_src; a.ea = ea; a.xa = xa; a.lda = lda; a.DA = DA; a.GA = GA;
     a.wa = reinterpret_cast<const float*>(wa);
@@ -51,6 +55,10 @@ QMP_API int qmp_fused_bwd_source_tc(int N, const int* out_ptr, const int* out_ds
                                     const float* mstat, const float* linv, const float* ds, float* dxa, float* dxb,
                                     float drop_p, unsigned long long seed, void* stream) {
     if (N <= 0 || (dxa == nullptr && dxb == nullptr)) return 0;
+    QMP_REQUIRE((DB == 32 || DB == 36) && ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0 &&
+                    (GA == 0 || (DA % 4 == 0 && lda % 4 == 0 && (reinterpret_cast<uintptr_t>(xa) & 15) == 0)) &&
+                    (reinterpret_cast<uintptr_t>(dP) & 15) == 0 && (mode == 0 || lddp % 4 == 0),
+                "qmp_fused_bwd_*_tc: rows must be 16-byte aligned with a multiple of 4 columns (pad them)");
     FusedBwdArgs a{};
     a.N = N; a.ptr = out_ptr; a.nbr = out_dst; a.kin = out_kin; a.xa = xa; a.lda = lda; a.DA = DA; a.GA = GA;
     a.wa = reinterpret_cast<const float*>(wa);

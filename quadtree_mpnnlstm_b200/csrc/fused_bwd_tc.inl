@@ -60,11 +60,33 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
     uint8_t* wb = cx.wbase + (size_t)buf * cx.wslot;
     const float* __restrict__ xin = st.xin;
     const int ld = st.ld, D = st.D, c = st.c;
-    const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0);
+    constexpr bool vec = true;                 // the C entry point requires 16-byte aligned rows with D % 4 == 0
+    constexpr bool co = DC == 32;              // coalesced row I/O (fused_tc.cuh) for the 32-float rows
     const bool need_dx = st.dx != nullptr;
+    // neighbour rows: two in flight (xa, xb); absent edges are index -1
+    float xa[DC], xb[DC];
+    auto load_pair = [&](int ja, int jb) {
+        if constexpr (co) {
+            if (__any_sync(0xffffffffu, ja >= 0)) warp_load_rows32x2(cx.rtile, xin, ld, ja, jb, xa, xb);
+        } else {
+            if (ja >= 0) load_row<DC>(xa, xin + (size_t)ja * ld, D, vec);
+            if (jb >= 0) load_row<DC>(xb, xin + (size_t)jb * ld, D, vec);
+        }
+    };
+    auto load_one = [&](int j) {
+        if constexpr (co) warp_load_rows32(cx.rtile, xin, ld, j, xa);
+        else if (j >= 0) load_row<DC>(xa, xin + (size_t)j * ld, D, vec);
+    };
+    auto more = [&](bool pred) {               // loop condition: warp-uniform when the loads are cooperative
+        if constexpr (co) return __any_sync(0xffffffffu, pred) != 0;
+        else return pred;
+    };
     {
         float g[FC];
-        if (valid) load_dP(g, a, i, c);
+        if (a.mode == 1 || a.C == FC) {        // full 32-float gradient rows: coalesced
+            const int slot = (a.mode == 1) ? ((c < a.GA) ? c : ((c - a.GA) & 3)) : c;
+            warp_load_rows32(cx.rtile_g, a.dP + (size_t)slot * FC, a.lddp, valid ? i : -1, g);
+        } else if (valid) load_dP(g, a, i, c);
         else {
 #pragma unroll
             for (int o = 0; o < FC; ++o) g[o] = 0.f;
@@ -84,11 +106,9 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         tc::commit(cx.bar);
     }
     const int k0 = te.k0, k1 = te.k1;
-    float xa[DC], xb[DC];
-    if (k0 < k1) {
-        load_row<DC>(xa, xin + (size_t)te.j[0] * ld, D, vec);
-        if (k0 + 1 < k1) load_row<DC>(xb, xin + (size_t)te.j[1] * ld, D, vec);
-    }
+    const int j0 = k0 < k1 ? te.j[0] : -1, j1 = k0 + 1 < k1 ? te.j[1] : -1, j2 = k0 + 2 < k1 ? te.j[2] : -1,
+              j3 = k0 + 3 < k1 ? te.j[3] : -1;
+    load_pair(j0, j1);
     const float m = valid ? a.mstat[(size_t)i * a.NC + c] : 0.f, li = valid ? a.linv[(size_t)i * a.NC + c] : 0.f;
     float al4[4], dal4[4];                   // alpha and d alpha of edges 0..3 stay in registers between the passes
 #pragma unroll
@@ -116,18 +136,17 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         for (int k = 0; k < DC; ++k) dal = fmaf(dz[k], xj[k], dal);
         return dal * fdropout_scale(a.seed, (long long)e * a.NC + c, a.drop_p);
     };
-    if (k0 < k1) {
-        dal4[0] = dalpha(k0, xa, te.e0[0], te.e1[0]);
-        if (k0 + 2 < k1) load_row<DC>(xa, xin + (size_t)te.j[2] * ld, D, vec);
-        if (k0 + 1 < k1) dal4[1] = dalpha(k0 + 1, xb, te.e0[1], te.e1[1]);
-        if (k0 + 3 < k1) load_row<DC>(xb, xin + (size_t)te.j[3] * ld, D, vec);
-        if (k0 + 2 < k1) dal4[2] = dalpha(k0 + 2, xa, te.e0[2], te.e1[2]);
-        if (k0 + 3 < k1) dal4[3] = dalpha(k0 + 3, xb, te.e0[3], te.e1[3]);
+    if (j0 >= 0) dal4[0] = dalpha(k0, xa, te.e0[0], te.e1[0]);
+    if (j1 >= 0) dal4[1] = dalpha(k0 + 1, xb, te.e0[1], te.e1[1]);
+    load_pair(j2, j3);
+    if (j2 >= 0) dal4[2] = dalpha(k0 + 2, xa, te.e0[2], te.e1[2]);
+    if (j3 >= 0) dal4[3] = dalpha(k0 + 3, xb, te.e0[3], te.e1[3]);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) tsum = fmaf(al4[e], dal4[e], tsum);
-    }
-    for (int kk = k0 + 4; kk < k1; ++kk) {   // larger in-degrees: d alpha stashed in ds
-        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+    for (int e = 0; e < 4; ++e) tsum = fmaf(al4[e], dal4[e], tsum);
+    for (int kk = k0 + 4; more(kk < k1); ++kk) {   // larger in-degrees: d alpha stashed in ds
+        const bool on = kk < k1;
+        load_one(on ? a.nbr[kk] : -1);
+        if (!on) continue;
         const float a0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
         const float dal = dalpha(kk, xa, a0, a1);
         tsum = fmaf(__expf(a.logit[(size_t)kk * a.NC + c] - m) * li, dal, tsum);
@@ -154,19 +173,17 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         z[DC + 1] = fmaf(alk, a1, z[DC + 1]);
         z[DC + 2] += alk;
     };
-    if (k0 < k1) {
-        if (k0 + 2 < k1) {                   // xa / xb hold edges 2, 3: finish them first, then re-gather 0, 1 (L1 hits)
-            if (k0 + 4 < k1) load_row<DC>(xa, xin + (size_t)te.j[2] * ld, D, vec);   // the long-degree loop reused xa
-            accum(k0 + 2, xa, te.e0[2], te.e1[2], al4[2], dal4[2]);
-            load_row<DC>(xa, xin + (size_t)te.j[0] * ld, D, vec);
-            if (k0 + 3 < k1) accum(k0 + 3, xb, te.e0[3], te.e1[3], al4[3], dal4[3]);
-            load_row<DC>(xb, xin + (size_t)te.j[1] * ld, D, vec);
-        }
-        accum(k0, xa, te.e0[0], te.e1[0], al4[0], dal4[0]);
-        if (k0 + 1 < k1) accum(k0 + 1, xb, te.e0[1], te.e1[1], al4[1], dal4[1]);
-    }
-    for (int kk = k0 + 4; kk < k1; ++kk) {
-        load_row<DC>(xa, xin + (size_t)a.nbr[kk] * ld, D, vec);
+    // xa / xb hold edges 2, 3 (when they exist and no long-degree loop reused xa): finish them, then re-gather 0, 1
+    if (more(k0 + 4 < k1)) load_pair(j2, j3);
+    if (j2 >= 0) accum(k0 + 2, xa, te.e0[2], te.e1[2], al4[2], dal4[2]);
+    if (j3 >= 0) accum(k0 + 3, xb, te.e0[3], te.e1[3], al4[3], dal4[3]);
+    if (more(j2 >= 0)) load_pair(j0, j1);     // nodes with at most two in-edges still hold edges 0, 1
+    if (j0 >= 0) accum(k0, xa, te.e0[0], te.e1[0], al4[0], dal4[0]);
+    if (j1 >= 0) accum(k0 + 1, xb, te.e0[1], te.e1[1], al4[1], dal4[1]);
+    for (int kk = k0 + 4; more(kk < k1); ++kk) {
+        const bool on = kk < k1;
+        load_one(on ? a.nbr[kk] : -1);
+        if (!on) continue;
         const float a0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
         accum(kk, xa, a0, a1, __expf(a.logit[(size_t)kk * a.NC + c] - m) * li, a.ds[(size_t)kk * a.NC + c]);
     }
@@ -191,7 +208,9 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
             tc_wait(cx);
             float dx[L.K1];
             tc_load_cols<L.K1 / 8>(cx.lane_base, st.pcol, dx);
-            if (valid) {
+            if constexpr (co) {
+                warp_store_rows32(cx.rtile, st.dx, st.lddx, (i & ~31), a.N, dx);
+            } else if (valid) {
                 float* row = st.dx + (size_t)i * st.lddx;
 #pragma unroll
                 for (int k = 0; k < L.K1; ++k)
@@ -213,7 +232,10 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
     uint8_t* wb = cx.wbase + (size_t)buf * cx.wslot;
     const float* __restrict__ xin = st.xin;
     const int ld = st.ld, D = st.D, c = st.c;
-    const bool vec = (D % 4 == 0) && (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(xin) & 15) == 0);
+    constexpr bool vec = true;
+    constexpr bool co = DC == 32;
+    const bool gfull = a.mode == 1 || a.C == FC;                 // full 32-float gradient rows
+    const int gslot = (a.mode == 1) ? ((c < a.GA) ? c : ((c - a.GA) & 3)) : c;
     float A[L.KS];
 #pragma unroll
     for (int k = 0; k < L.KS; ++k) A[k] = 0.f;
@@ -231,30 +253,32 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
         dsv = a.ds[(size_t)kin * a.NC + c];
     };
     // out-edges 0..3: targets and in-CSR slots were loaded once per tile (te.j = target, te.e0 = slot as int bits)
-#pragma unroll
-    for (int e0 = 0; e0 < 4; e0 += 2) {
-        if (k0 + e0 < k1) {
-            const int i0 = te.j[e0], kin0 = __float_as_int(te.e0[e0]);
-            const bool two = k0 + e0 + 1 < k1;
-            const int i1 = two ? te.j[e0 + 1] : i0, kin1 = two ? __float_as_int(te.e0[e0 + 1]) : kin0;
-            float g0[FC], x0[DC], g1[FC], x1[DC], al0, ds0, al1, ds1;
-            load_dP(g0, a, i0, c);
-            load_row<DC>(x0, xin + (size_t)i0 * ld, D, vec);
-            load_dP(g1, a, i1, c);
-            load_row<DC>(x1, xin + (size_t)i1 * ld, D, vec);
-            coef(i0, kin0, al0, ds0);
-            coef(i1, kin1, al1, ds1);
-            edge(i0, kin0, g0, x0, al0, ds0);
-            if (two) edge(i1, kin1, g1, x1, al1, ds1);
+    // one out-edge at a time: the gradient row of its target and the target's input row travel together
+    auto one_edge = [&](bool on, int i, int kin) {
+        float g[FC], xi[DC];
+        if (co && gfull) {
+            if constexpr (co) warp_load_rows32_ab(cx.rtile, a.dP + (size_t)gslot * FC, a.lddp, xin, ld, i, g, xi);
+        } else {
+            if (on) load_dP(g, a, i, c);
+            if constexpr (co) warp_load_rows32(cx.rtile, xin, ld, i, xi);
+            else if (on) load_row<DC>(xi, xin + (size_t)i * ld, D, vec);
         }
+        if (on) {
+            float al, dsv;
+            coef(i, kin, al, dsv);
+            edge(i, kin, g, xi, al, dsv);
+        }
+    };
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const bool on = k0 + e < k1;
+        bool any = on;
+        if constexpr (co) any = __any_sync(0xffffffffu, on) != 0;
+        if (any) one_edge(on, on ? te.j[e] : -1, __float_as_int(te.e0[e]));
     }
-    for (int kk = k0 + 4; kk < k1; ++kk) {
-        const int i = a.nbr[kk], kin = a.kin[kk];
-        float g[FC], xi[DC], al, dsv;
-        load_dP(g, a, i, c);
-        load_row<DC>(xi, xin + (size_t)i * ld, D, vec);
-        coef(i, kin, al, dsv);
-        edge(i, kin, g, xi, al, dsv);
+    for (int kk = k0 + 4; co ? (__any_sync(0xffffffffu, kk < k1) != 0) : (kk < k1); ++kk) {
+        const bool on = kk < k1;
+        one_edge(on, on ? a.nbr[kk] : -1, on ? a.kin[kk] : 0);
     }
     if (cx.pending) tc_wait(cx);
     if (t == 0 && has_next) tc_prefetch_image(cx, buf ^ 1, nx.img, nx.bytes);
@@ -273,7 +297,13 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
         tc_wait(cx);
         float dx[L.K1];
         tc_load_cols<L.K1 / 8>(cx.lane_base, st.pcol, dx);
-        if (valid) {
+        if constexpr (co) {                      // dx_j += ... : coalesced read-modify-write of the warp's 32 rows
+            float cur[L.K1];
+            warp_load_rows32(cx.rtile, st.dx, st.lddx, valid ? j : -1, cur);
+#pragma unroll
+            for (int k = 0; k < L.K1; ++k) dx[k] += cur[k];
+            warp_store_rows32(cx.rtile, st.dx, st.lddx, (j & ~31), a.N, dx);
+        } else if (valid) {
             float* row = st.dx + (size_t)j * st.lddx;
 #pragma unroll
             for (int k = 0; k < L.K1; ++k)
@@ -316,6 +346,9 @@ __global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_const
     cx.pending = false;
     cx.tmem = tmem_slot;
     cx.lane_base = cx.tmem + ((uint32_t)(warp * 32) << 16);
+    cx.lane_off = (uint32_t)(warp * 32) << 16;
+    cx.rtile = reinterpret_cast<float*>(smem + 2 * SLOT) + warp * 2 * TC_ROWTILE;
+    cx.rtile_g = cx.rtile;
 
     const int ntiles = (a.N + 127) / 128;
     // source side: only the convs whose input needs a gradient
@@ -362,7 +395,7 @@ int launch_bwd_tc(const FusedBwdArgs& a, cudaStream_t st) {
     constexpr int BA = KIND == 1 ? TcBwdTLayout(DA_).BYTES : TcBwdSLayout(DA_).BYTES;
     constexpr int BB = KIND == 1 ? TcBwdTLayout(DBC).BYTES : TcBwdSLayout(DBC).BYTES;
     constexpr int SLOT = BA > BB ? BA : BB;
-    const size_t smem = 2 * (size_t)SLOT;
+    const size_t smem = 2 * (size_t)SLOT + 4 * 2 * TC_ROWTILE * sizeof(float);
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;

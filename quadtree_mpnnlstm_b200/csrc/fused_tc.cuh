@@ -233,6 +233,40 @@ __device__ __forceinline__ void warp_load_rows32x2(float* tile, const float* __r
     __syncwarp();
 }
 
+// the same row index in two different arrays (e.g. gradient row and input row of one node); needs two tiles
+__device__ __forceinline__ void warp_load_rows32_ab(float* tile, const float* __restrict__ baseA, int ldA,
+                                                    const float* __restrict__ baseB, int ldB, int j, float (&xA)[32],
+                                                    float (&xB)[32]) {
+    const int lane = threadIdx.x & 31, c = lane & 7;
+    float4 v0[8], v1[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int r = 4 * q + (lane >> 3);
+        const int jr = __shfl_sync(0xffffffffu, j, r);
+        v0[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        v1[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (jr >= 0) {
+            v0[q] = __ldg(reinterpret_cast<const float4*>(baseA + (size_t)jr * ldA) + c);
+            v1[q] = __ldg(reinterpret_cast<const float4*>(baseB + (size_t)jr * ldB) + c);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int r = 4 * q + (lane >> 3);
+        *reinterpret_cast<float4*>(tc_tile_chunk(tile, r, c)) = v0[q];
+        *reinterpret_cast<float4*>(tc_tile_chunk(tile + TC_ROWTILE, r, c)) = v1[q];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(tc_tile_chunk(tile, lane, k));
+        const float4 b = *reinterpret_cast<const float4*>(tc_tile_chunk(tile + TC_ROWTILE, lane, k));
+        xA[4 * k] = a.x; xA[4 * k + 1] = a.y; xA[4 * k + 2] = a.z; xA[4 * k + 3] = a.w;
+        xB[4 * k] = b.x; xB[4 * k + 1] = b.y; xB[4 * k + 2] = b.z; xB[4 * k + 3] = b.w;
+    }
+    __syncwarp();
+}
+
 // the warp's 32 consecutive rows row0 .. row0+31 (those < n_rows are written): lane's row x -> base + (row0 + lane) * ld
 __device__ __forceinline__ void warp_store_rows32(float* tile, float* __restrict__ base, int ld, int row0, int n_rows,
                                                   const float (&x)[32]) {
@@ -296,6 +330,7 @@ struct TcCtx {                // scalars only (no indexed members): stays in reg
     bool pending;            // a committed group has not been waited yet
     uint32_t tmem, lane_base, lane_off;
     uint32_t stash_col;      // 96 spare TMEM columns (forward: I, F, C' between the gate slots)
+    float* rtile_g;          // row tile for gradient rows (may alias rtile)
     float* rtile;            // this warp's two row tiles (shared memory) for the coalesced row I/O
 };
 
