@@ -311,9 +311,15 @@ def run_gpu(args):
             rate, dt, done, what = cpu_oracle_rate(os.cpu_count() or 1, seconds_target=15.0)
             line["cpu_baseline"] = {"value": rate, "unit": "graph-frames/s", "cores": os.cpu_count() or 1,
                                     "kind": "port", "sample": what}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL teardown with a captured graph still holding the communicator hung for the full time limit on a 2-GPU
+        # box (the JSON line had already been printed): synchronise, meet once more, and leave without it.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
