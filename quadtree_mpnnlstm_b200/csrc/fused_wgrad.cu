@@ -34,9 +34,17 @@ constexpr int WG_MAXCONV = 12;
 constexpr int WG_BIT = 3;                       // B items per thread: 16 node groups x (<= 20 chunks) / 128 threads
 constexpr uint32_t WG_TMEM_COLS = 256, WG_AHI = 128, WG_ALO = 192;
 
+// One reduction problem = one or two convs ("parts") that share the gradient rows g (in gate mode conv_x_g and conv_h_g
+// feed the same gate, so their g is the same dP block): rows of A = [dU_0 | dU_1 | g], columns of B =
+// [x_0 | 1 0 0 0 | Z_0 | x_1 | Z_1].  Merging halves the MMA count of the decoder cell (issue cost is flat in N).
+struct WgPart {
+    const float* x; const float* zs; const float* dus; float* gw;
+    int ldx, ldz, D, DC;
+};
 struct WgConv {
-    const float* x; const float* zs; const float* dus; const float* g; float* gw;
-    int ldx, ldz, ldg, gvalid, D, DC, cta0, nctas;
+    WgPart p[2];
+    const float* g;
+    int nparts, ldg, gvalid, cta0, nctas;
 };
 struct WgArgs {
     int N, nconv;
@@ -71,8 +79,13 @@ __global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant_
     int ci = 0;
     while (ci + 1 < a.nconv && (int)blockIdx.x >= a.c[ci].cta0 + a.c[ci].nctas) ++ci;
     const WgConv& cv = a.c[ci];
-    const int DC = cv.DC, D = cv.D;
-    const int qx = DC / 4, qb = qx + 1 + (DC + 4) / 4;           // B chunks: x | ones | Z
+    const bool two = cv.nparts == 2;
+    const int DC0 = cv.p[0].DC, DC1 = two ? cv.p[1].DC : 0;
+    // A rows
+    const int RA1 = DC0 + 4, RG = RA1 + (two ? DC1 + 4 : 0);
+    // B chunks (16 bytes = 4 columns): x_0 | ones | Z_0 | x_1 | Z_1
+    const int q_one = DC0 / 4, q_z0 = q_one + 1, q_x1 = q_z0 + (DC0 + 4) / 4, q_z1 = q_x1 + DC1 / 4;
+    const int qb = two ? q_z1 + (DC1 + 4) / 4 : q_x1;
     const int NB = (qb * 4 + 15) / 16 * 16;
     uint8_t* b_hi = smem;
     uint8_t* b_lo = smem + (NB / 8) * WG_SBO;
@@ -91,12 +104,14 @@ __global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant_
     const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
     const uint32_t idesc = tc::make_idesc_tf32(128, NB);
 
-    // A: this thread's component of [dU | g]
+    // A: this thread's component of [dU_0 | dU_1 | g]
     const float* a_src = nullptr;
     int a_ld = 0;
-    if (t < DC + 4) { a_src = cv.dus + t; a_ld = cv.ldz; }
-    else if (t < DC + 4 + FC && t - (DC + 4) < cv.gvalid) { a_src = cv.g + (t - (DC + 4)); a_ld = cv.ldg; }
-    const bool vx = (cv.ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cv.x) & 15) == 0);
+    if (t < RA1) { a_src = cv.p[0].dus + t; a_ld = cv.p[0].ldz; }
+    else if (t < RG) { a_src = cv.p[1].dus + (t - RA1); a_ld = cv.p[1].ldz; }
+    else if (t < RG + FC && t - RG < cv.gvalid) { a_src = cv.g + (t - RG); a_ld = cv.ldg; }
+    const bool vx0 = (cv.p[0].ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cv.p[0].x) & 15) == 0);
+    const bool vx1 = two && (cv.p[1].ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cv.p[1].x) & 15) == 0);
     const int ntiles = (a.N + WG_KT - 1) / WG_KT;
     const int items = (WG_KT / 4) * qb;
 
@@ -120,9 +135,11 @@ __global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant_
                 for (int j = 0; j < 4; ++j) {
                     const int i = n0 + kg * 4 + j;
                     if (i < a.N) {
-                        if (q < qx) vb[it][j] = wg_load4(cv.x + (size_t)i * cv.ldx + q * 4, D - q * 4, vx);
-                        else if (q == qx) vb[it][j].x = 1.f;
-                        else vb[it][j] = wg_load4(cv.zs + (size_t)i * cv.ldz + (q - qx - 1) * 4, 4, true);
+                        if (q < q_one) vb[it][j] = wg_load4(cv.p[0].x + (size_t)i * cv.p[0].ldx + q * 4, cv.p[0].D - q * 4, vx0);
+                        else if (q == q_one) vb[it][j].x = 1.f;
+                        else if (q < q_x1) vb[it][j] = wg_load4(cv.p[0].zs + (size_t)i * cv.p[0].ldz + (q - q_z0) * 4, 4, true);
+                        else if (q < q_z1) vb[it][j] = wg_load4(cv.p[1].x + (size_t)i * cv.p[1].ldx + (q - q_x1) * 4, cv.p[1].D - (q - q_x1) * 4, vx1);
+                        else vb[it][j] = wg_load4(cv.p[1].zs + (size_t)i * cv.p[1].ldz + (q - q_z1) * 4, 4, true);
                     }
                 }
             }
@@ -193,25 +210,40 @@ __global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant_
         tc::mbar_wait(&bar, parity);
         tc::fence_after_sync();
         // flush: thread t owns accumulator row t.  Pack offsets (fused.cuh): W1 | b1 | W2 | W3 | b3
-        const int o1 = (DC + 2) * DC, o2 = o1 + DC + 4, o3 = o2 + FC * (DC + 4), o4 = o3 + FC * DC;
-        const bool du_row = t < DC + 2;
-        const int o = t - (DC + 4);
-        const bool g_row = o >= 0 && o < FC && o < cv.gvalid;
-        float* gw = cv.gw;
-        for (int c0 = 0; c0 < qb * 4; c0 += 8) {
-            float r[8];
-            tc::tmem_ld8(lane_base + (uint32_t)c0, r);
+        // row roles: 0 = dU row of part 0, 1 = dU row of part 1, 2 = g row, 3 = nothing
+        int role = 3, r = 0;
+        if (t < DC0 + 2) { role = 0; r = t; }
+        else if (two && t >= RA1 && t < RA1 + DC1 + 2) { role = 1; r = t - RA1; }
+        else if (t >= RG && t < RG + FC && t - RG < cv.gvalid) { role = 2; r = t - RG; }
+        const int o1a = (DC0 + 2) * DC0, o2a = o1a + DC0 + 4, o3a = o2a + FC * (DC0 + 4), o4a = o3a + FC * DC0;
+        const int o1b = (DC1 + 2) * DC1, o2b = o1b + DC1 + 4, o3b = o2b + FC * (DC1 + 4), o4b = o3b + FC * DC1;
+        float* gwa = cv.p[0].gw;
+        float* gwb = two ? cv.p[1].gw : nullptr;
+        const int c_one = q_one * 4, c_z0 = q_z0 * 4, c_x1 = q_x1 * 4, c_z1 = q_z1 * 4, c_end = qb * 4;
+        for (int c0 = 0; c0 < c_end; c0 += 8) {
+            float v[8];
+            tc::tmem_ld8(lane_base + (uint32_t)c0, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int col = c0 + i;
-                if (col < DC) {
-                    if (du_row) atomicAdd(gw + t * DC + col, r[i]);
-                    else if (g_row) atomicAdd(gw + o3 + o * DC + col, r[i]);
-                } else if (col == DC) {
-                    if (du_row) atomicAdd(gw + o1 + t, r[i]);
-                    else if (g_row) atomicAdd(gw + o4 + o, r[i]);
-                } else if (col >= DC + 4 && col < 2 * DC + 8) {
-                    if (g_row) atomicAdd(gw + o2 + o * (DC + 4) + (col - DC - 4), r[i]);
+                if (col >= c_end || role == 3) continue;
+                if (col < c_one) {                                   // x_0
+                    if (role == 0) atomicAdd(gwa + r * DC0 + col, v[i]);
+                    else if (role == 2) atomicAdd(gwa + o3a + r * DC0 + col, v[i]);
+                } else if (col == c_one) {                           // ones
+                    if (role == 0) atomicAdd(gwa + o1a + r, v[i]);
+                    else if (role == 1) atomicAdd(gwb + o1b + r, v[i]);
+                    else {
+                        atomicAdd(gwa + o4a + r, v[i]);
+                        if (two) atomicAdd(gwb + o4b + r, v[i]);
+                    }
+                } else if (col >= c_z0 && col < c_x1) {              // Z_0
+                    if (role == 2) atomicAdd(gwa + o2a + r * (DC0 + 4) + (col - c_z0), v[i]);
+                } else if (col >= c_x1 && col < c_z1) {              // x_1
+                    if (role == 1) atomicAdd(gwb + r * DC1 + (col - c_x1), v[i]);
+                    else if (role == 2) atomicAdd(gwb + o3b + r * DC1 + (col - c_x1), v[i]);
+                } else if (col >= c_z1) {                            // Z_1
+                    if (role == 2) atomicAdd(gwb + o2b + r * (DC1 + 4) + (col - c_z1), v[i]);
                 }
             }
         }
@@ -244,44 +276,69 @@ QMP_API int qmp_fused_wgrad(int N, const float* xa, int lda, int DA, int GA, con
     }
     WgArgs a{};
     a.N = N;
-    a.nconv = NC;
     const int ntiles = cdiv(N, WG_KT);
-    int wsum = 0, w[WG_MAXCONV], nbmax = 16;
-    for (int c = 0; c < NC; ++c) {
-        const int DC = c < GA ? dac : dbc;
-        w[c] = 16 + DC / 4 + 1 + (DC + 4) / 4;
-        wsum += w[c];
-        const int nb = ((DC / 4 + 1 + (DC + 4) / 4) * 4 + 15) / 16 * 16;
-        nbmax = nb > nbmax ? nb : nbmax;
-    }
-    const int budget = 2 * n_sm;
-    int cta = 0;
-    for (int c = 0; c < NC; ++c) {
-        WgConv& v = a.c[c];
+    auto fill_part = [&](WgPart& p, int c) {
         const bool segA = c < GA;
         const int g = segA ? c : c - GA;
-        v.DC = segA ? dac : dbc;
-        v.D = segA ? DA : DB;
-        const int G = segA ? GA : GB, W = v.DC + 4;
-        v.x = segA ? xa : xb + (sharedB ? 0 : (size_t)g * DB);
-        v.ldx = segA ? lda : ldb;
-        v.zs = (segA ? ZsA : ZsB) + (size_t)g * W;
-        v.dus = (segA ? dUsA : dUsB) + (size_t)g * W;
-        v.ldz = G * W;
-        if (mode == 1) {
-            v.g = dP + (size_t)(segA ? c : (g & 3)) * FC;
+        p.DC = segA ? dac : dbc;
+        p.D = segA ? DA : DB;
+        const int G = segA ? GA : GB, W = p.DC + 4;
+        p.x = segA ? xa : xb + (sharedB ? 0 : (size_t)g * DB);
+        p.ldx = segA ? lda : ldb;
+        p.zs = (segA ? ZsA : ZsB) + (size_t)g * W;
+        p.dus = (segA ? dUsA : dUsB) + (size_t)g * W;
+        p.ldz = G * W;
+        const int total = (p.DC + 2) * p.DC + (p.DC + 4) + FC * (p.DC + 4) + FC * p.DC + FC;
+        p.gw = (segA ? gwa : gwb) + (size_t)g * total;
+    };
+    // gate mode with one narrow (X) and one wide (H) conv per gate: the pair shares the gate's gradient rows -> one problem
+    const bool merge = mode == 1 && GA == 4 && GB == 4;
+    int nprob = 0;
+    int w[WG_MAXCONV], wsum = 0, nbmax = 16;
+    if (merge) {
+        for (int s = 0; s < 4; ++s) {
+            WgConv& v = a.c[nprob++];
+            v.nparts = 2;
+            fill_part(v.p[0], s);
+            fill_part(v.p[1], GA + s);
+            v.g = dP + (size_t)s * FC;
             v.gvalid = FC;
-        } else {
-            v.g = dP + (size_t)c * C;
-            v.gvalid = C;
+            v.ldg = lddp;
         }
-        v.ldg = lddp;
-        const int total = (v.DC + 2) * v.DC + (v.DC + 4) + FC * (v.DC + 4) + FC * v.DC + FC;
-        v.gw = (segA ? gwa : gwb) + (size_t)g * total;
-        int n = (int)((long long)budget * w[c] / wsum);
+    } else {
+        for (int c = 0; c < NC; ++c) {
+            WgConv& v = a.c[nprob++];
+            v.nparts = 1;
+            fill_part(v.p[0], c);
+            v.p[1] = v.p[0];
+            if (mode == 1) {
+                v.g = dP + (size_t)(c < GA ? c : ((c - GA) & 3)) * FC;
+                v.gvalid = FC;
+            } else {
+                v.g = dP + (size_t)c * C;
+                v.gvalid = C;
+            }
+            v.ldg = lddp;
+        }
+    }
+    a.nconv = nprob;
+    for (int k = 0; k < nprob; ++k) {
+        const WgConv& v = a.c[k];
+        int qb = v.p[0].DC / 4 + 1 + (v.p[0].DC + 4) / 4;
+        if (v.nparts == 2) qb += v.p[1].DC / 4 + (v.p[1].DC + 4) / 4;
+        w[k] = 16 + qb;
+        wsum += w[k];
+        const int nb = (qb * 4 + 15) / 16 * 16;
+        nbmax = nb > nbmax ? nb : nbmax;
+    }
+    QMP_REQUIRE(nbmax <= 128, "qmp_fused_wgrad: problem too wide for the accumulator block");
+    const int budget = 2 * n_sm;
+    int cta = 0;
+    for (int k = 0; k < nprob; ++k) {
+        int n = (int)((long long)budget * w[k] / wsum);
         n = n < 1 ? 1 : (n > ntiles ? ntiles : n);
-        v.cta0 = cta;
-        v.nctas = n;
+        a.c[k].cta0 = cta;
+        a.c[k].nctas = n;
         cta += n;
     }
     const size_t smem = (size_t)2 * (nbmax / 8) * WG_SBO;
