@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import torch
 
-from .graph_functions import flatten
+from .graph_functions import flatten, unflatten
 
 
 def shard_launch_dates(n_dates, rank, world, seed=0):
@@ -46,10 +46,19 @@ class TrainStep:
     def _step(self, x, y, concat):
         for p in self.params:
             p.grad = None
-        out, _ = self.model(x, y, concat, teacher_forcing_ratio=0, mask=self.mask, graph_structure=self.graph_structure)
-        mapping = self.model.graph.mapping
-        y_nodes = flatten(y, mapping, self.model.graph.n_pixels_per_node, self.mask)   # == y[:, ~mask] on a pixel mesh
-        loss = torch.nn.functional.mse_loss(torch.stack(out), y_nodes)
+        out, maps = self.model(x, y, concat, teacher_forcing_ratio=0, mask=self.mask, graph_structure=self.graph_structure)
+        if self.model.thresh == -float("inf") or self.graph_structure is not None:
+            # static mesh: compare on the nodes (== y[:, ~mask] on a pixel mesh)
+            mapping = self.model.graph.mapping
+            y_nodes = flatten(y, mapping, self.model.graph.n_pixels_per_node, self.mask)
+            loss = torch.nn.functional.mse_loss(torch.stack(out), y_nodes)
+        else:
+            # dynamic quadtree: the mesh differs per forecast step -> unpool every step and compare the unmasked pixels,
+            # as the reference trainer does (model/mpnnlstm.py:243-246)
+            shape = tuple(x.shape[1:3])
+            y_hat = torch.stack([unflatten(out[t], maps[t], shape, self.mask) for t in range(len(out))])
+            keep = self._keep_mask(x.device)
+            loss = torch.nn.functional.mse_loss(y_hat[:, keep], y[:, keep])
         loss.backward()
         if self.world > 1:
             import torch.distributed as dist
@@ -62,6 +71,13 @@ class TrainStep:
         torch.nn.utils.clip_grad_norm_(self.params, max_norm=self.max_norm)
         self.opt.step()
         return loss.detach()
+
+    def _keep_mask(self, device):
+        if getattr(self, "_keep", None) is None or self._keep.device != device:
+            import numpy as np
+            m = self.mask if self.mask is not None else np.zeros(1, bool)
+            self._keep = torch.from_numpy(~np.asarray(m, dtype=bool)).to(device)
+        return self._keep
 
     def _drop_autograd_leftovers(self):
         """Packed-parameter caches and the model's mesh state keep the previous step's autograd graph alive;
