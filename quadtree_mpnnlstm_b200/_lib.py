@@ -98,6 +98,8 @@ def lib():
         L.qmp_quadtree_pyramid_cells.argtypes = [_I, _I, _I]
         L.qmp_set_tensor_cores.restype = _I
         L.qmp_set_tensor_cores.argtypes = [_I]
+        L.qmp_set_fused_paired.restype = _I
+        L.qmp_set_fused_paired.argtypes = [_I]
         L.qmp_fused_tc_image_bytes.restype = _L
         L.qmp_fused_tc_image_bytes.argtypes = [_I, _I]
         for name, sig in SIGNATURES.items():
@@ -144,4 +146,4 @@ def call(name, *args):
 
 
 def exported_symbols():
-    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes"] + list(SIGNATURES)
+    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired"] + list(SIGNATURES)

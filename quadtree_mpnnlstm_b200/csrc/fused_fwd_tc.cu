@@ -6,8 +6,21 @@ extern template int launch_fwd_tc<0, 32>(const FusedFwdArgs&, cudaStream_t);
 extern template int launch_fwd_tc<0, 36>(const FusedFwdArgs&, cudaStream_t);
 extern template int launch_fwd_tc<4, 32>(const FusedFwdArgs&, cudaStream_t);
 extern template int launch_fwd_tc<8, 32>(const FusedFwdArgs&, cudaStream_t);
+template <int DAC> int launch_fwd_pw(const FusedFwdArgs&, cudaStream_t);          // fused_fwd_pw.inl (two threads per node)
+extern template int launch_fwd_pw<0>(const FusedFwdArgs&, cudaStream_t);
+extern template int launch_fwd_pw<4>(const FusedFwdArgs&, cudaStream_t);
+extern template int launch_fwd_pw<8>(const FusedFwdArgs&, cudaStream_t);
+static int g_paired = 1;
 }  // namespace qmp
 using namespace qmp;
+
+// 1 (default): groups of 32-wide convs run the paired-warp kernel (two threads per node); 2: also groups with narrow X
+// convs; 0: always one thread per node.  Returns the old value.  Both compute the same thing; the switch exists for A/B timing and cross-checks.
+QMP_API int qmp_set_fused_paired(int enable) {
+    const int old = g_paired;
+    g_paired = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+    return old;
+}
 
 // Same contract as qmp_fused_fwd, on the tensor cores: wa / wb are the weight IMAGES built by qmp_fused_pack_tc
 // (kind 0) from the padded packs, [GA, image bytes(cap DA)] and [GB, image bytes(cap DB)].
@@ -37,6 +50,14 @@ QMP_API int qmp_fused_fwd_tc(int N, const int* in_ptr, const int* in_src, const 
     cudaStream_t st = (cudaStream_t)stream;
     const int dac = (GA == 0) ? 0 : (DA <= 4 ? 4 : 8);
     const int dbc = (DB <= 32) ? 32 : 36;
+    // Groups made of 32-wide convs only (encoder layers >= 1, decoder head fc_out2): the paired-warp kernel, two threads
+    // per node (measured 127 / 133 us against 148 / 154 us).  With narrow X convs in the group (g_paired == 2 forces it)
+    // the second warp of a pair idles through them and the one-thread-per-node kernel is as fast (133 vs 139 us).
+    if (dbc == 32 && ((g_paired == 1 && GA == 0) || g_paired == 2)) {
+        if (dac == 0) return launch_fwd_pw<0>(a, st);
+        if (dac == 4) return launch_fwd_pw<4>(a, st);
+        return launch_fwd_pw<8>(a, st);
+    }
     if (dac == 0 && dbc == 32) return launch_fwd_tc<0, 32>(a, st);
     if (dac == 0 && dbc == 36) return launch_fwd_tc<0, 36>(a, st);
     if (dac == 4 && dbc == 32) return launch_fwd_tc<4, 32>(a, st);

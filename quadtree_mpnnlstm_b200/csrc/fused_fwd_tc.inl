@@ -47,9 +47,11 @@ __device__ __forceinline__ void tc_edge(const FusedFwdArgs& a, int kk, int c, co
     m = mn;
 }
 
+// `active` = false: this thread only takes part in the barriers / waits (paired-warp kernel: the second warp of a
+// pair idles through the narrow X convs); it must then be called with valid = false and an empty edge list.
 template <int DC>
 __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, int i, bool valid, const TcEdges& te,
-                                            const TcStep& st, const TcStep& nx, bool has_next) {
+                                            const TcStep& st, const TcStep& nx, bool has_next, bool active = true) {
     constexpr TcFwdLayout L(DC);
     const int t = threadIdx.x;
     const int buf = cx.toggle;
@@ -68,7 +70,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
     // (2) the previous conv's second contraction must be done with the A columns and with the other weight slot
     if (cx.pending) tc_wait(cx);
     if (t == 0 && has_next) tc_prefetch_image(cx, buf ^ 1, nx.img, nx.bytes);      // next conv's image, one conv ahead
-    tc_stage_a_at<L.K1>(cx.lane_off, cx.ah_col, cx.al_col, x);
+    if (active) tc_stage_a_at<L.K1>(cx.lane_off, cx.ah_col, cx.al_col, x);
     tc::tmem_st_wait();
     tc::fence_before_sync();
     __syncthreads();
@@ -99,7 +101,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
     {
         constexpr int N8 = (DC + 2 + 7) / 8;
         float tmp[N8 * 8];
-        tc_load_cols<N8>(cx.lane_off, cx.u_col, tmp);
+        if (active) tc_load_cols<N8>(cx.lane_off, cx.u_col, tmp);
         const float* b1 = reinterpret_cast<const float*>(wb + L.B1);
 #pragma unroll
         for (int k = 0; k < DC; ++k) u[k] = tmp[k] + b1[k];
@@ -159,7 +161,7 @@ __device__ __forceinline__ void conv_fwd_tc(TcCtx& cx, const FusedFwdArgs& a, in
         zz[DC] = ze0 * li;
         zz[DC + 1] = ze1 * li;
         zz[DC + 2] = zs * li;
-        tc_stage_a_at<L.K2>(cx.lane_off, cx.ah_col, cx.al_col, zz);
+        if (active) tc_stage_a_at<L.K2>(cx.lane_off, cx.ah_col, cx.al_col, zz);
     }
     tc::tmem_st_wait();
     tc::fence_before_sync();
