@@ -83,7 +83,7 @@ def test_gcn_conv(be, d_in, d_out, self_loops):
 @pytest.mark.parametrize("conv,n_conv_layers,f_in,hid", [("TransformerConv", 1, 4, 32), ("TransformerConv", 3, 8, 32),
                                                          ("ChebConv", 1, 4, 16), ("ChebConv", 2, 4, 16),
                                                          ("GCNConv", 2, 4, 16), ("TransformerConv", 2, 5, 8)])
-@pytest.mark.parametrize("path", ["tc", "ffma", "modular"])
+@pytest.mark.parametrize("path", ["tc", "tc_pw", "tc_1t", "ffma", "modular"])
 def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     import quadtree_mpnnlstm_b200.model as M
     import quadtree_mpnnlstm_b200.fused as FZ
@@ -93,9 +93,14 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     fused = path != "modular"
     if path != "tc" and not fusable:
         pytest.skip("only one path exists for this configuration")
+    if path in ("tc_pw", "tc_1t"):            # force the paired-warp / the one-thread-per-node forward kernel everywhere
+        if be.name != "cuda":
+            pytest.skip("kernel variants exist on the device only")
+        old = _lib.lib().qmp_set_fused_paired(2 if path == "tc_pw" else 0)
+        monkeypatch.setattr(FZ, "_restore_paired", old, raising=False)
     monkeypatch.setattr(FZ, "ENABLED", fused)
-    monkeypatch.setattr(FZ, "TC_FWD", path == "tc")
-    monkeypatch.setattr(FZ, "TC_BWD", path == "tc")
+    monkeypatch.setattr(FZ, "TC_FWD", path.startswith("tc"))
+    monkeypatch.setattr(FZ, "TC_BWD", path.startswith("tc"))
     n_fused = lambda: _lib.CALL_COUNTS.get("qmp_fused_fwd", 0) + _lib.CALL_COUNTS.get("qmp_fused_fwd_tc", 0)
     calls_before = n_fused()
     ei, ea, n = _graph(4, use_edge_attrs=(conv == "TransformerConv"))
@@ -133,6 +138,8 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     # H=None / C=None defaults to zeros like the reference
     oa0 = ref(X, ei, ea)
     ob0 = gpu(be.dev(X), be.dev(ei), be.dev(ea) if ea is not None else None)
+    if path in ("tc_pw", "tc_1t"):
+        _lib.lib().qmp_set_fused_paired(1)
     assert rel_err(ob0[1], oa0[1]) < TOL
 
 
