@@ -55,6 +55,8 @@ SIGNATURES = {
     "qmp_fused_pack_tc": "piiipp",
     "qmp_fused_bwd_target_tc": "ippppiiippiiiipiipippppppppppfup",
     "qmp_fused_bwd_source_tc": "ippppiiippiiiipiipippppppfup",
+    "qmp_fused_pack_cell": "pppp",
+    "qmp_fused_cell_fwd": "ippppipippp" "iiif" "pppppp" "i" "pppp" "fup",
 }
 
 
@@ -67,6 +69,7 @@ KERNELS_PER_CALL = {
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
     "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
     "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1, "qmp_fused_bwd_target_tc": 1, "qmp_fused_bwd_source_tc": 1,
+    "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1,
 }
 CALL_COUNTS = {}
 
@@ -102,6 +105,8 @@ def lib():
         L.qmp_set_fused_paired.argtypes = [_I]
         L.qmp_fused_tc_image_bytes.restype = _L
         L.qmp_fused_tc_image_bytes.argtypes = [_I, _I]
+        L.qmp_fused_cell_image_bytes.restype = _L
+        L.qmp_fused_cell_image_bytes.argtypes = []
         for name, sig in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = _I
@@ -146,4 +151,4 @@ def call(name, *args):
 
 
 def exported_symbols():
-    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired"] + list(SIGNATURES)
+    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes"] + list(SIGNATURES)

@@ -19,7 +19,7 @@ REPO = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libqmp_b200.so")
 HEADER = os.path.join(REPO, "include", "qmp_b200.h")
 
-NVCC_FLAGS = (["-DQMP_TIMING_TF32X1"] if os.environ.get("QMP_TIMING_TF32X1") else []) + (["-DQMP_PW_TRACE"] if os.environ.get("QMP_PW_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+NVCC_FLAGS = os.environ.get("QMP_EXTRA_FLAGS", "").split() + (["-DQMP_TIMING_TF32X1"] if os.environ.get("QMP_TIMING_TF32X1") else []) + (["-DQMP_PW_TRACE"] if os.environ.get("QMP_PW_TRACE") else []) + (["-DQMP_CELL_TRACE"] if os.environ.get("QMP_CELL_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
 
 REPLACES = {  # entry point -> reference interface it stands in for
@@ -57,6 +57,9 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_fused_pack_tc": "(weight images for the tcgen05 fused kernels: hi / lo TF32 split, canonical K-major layout)",
     "qmp_fused_tc_image_bytes": "(size of one conv's weight image)",
     "qmp_fused_wgrad": "autograd weight gradients of the above (tcgen05 3xTF32 reduction over the mesh nodes)",
+    "qmp_fused_cell_fwd": "model/model.py:394-463 GConvLSTM.forward of the decoder cell (4 X convs + 4 H convs, gates, norms, head input) -- one persistent launch, gates batched on tcgen05, edge phase 8 lanes per node",
+    "qmp_fused_pack_cell": "(weight image of qmp_fused_cell_fwd: the eight convs of the decoder cell side by side)",
+    "qmp_fused_cell_image_bytes": "(size of that image)",
     "qmp_set_fused_paired": "(switch: two threads per node (paired warps) or one in the tcgen05 fused kernels)",
     "qmp_set_tensor_cores": "(switch: tcgen05 3xTF32 contractions on/off; parity tests run both)",
     "qmp_tc_probe3": "(test hook: issue cost of small tcgen05 MMAs)",

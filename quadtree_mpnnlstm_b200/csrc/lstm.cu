@@ -268,6 +268,158 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(LstmArgs a) {
         }
 }
 
+// ---- C == 32: gate backward in OCTET layout -- 8 lanes per node, 4 channels (one float4) per lane, 4 nodes per warp
+// instruction.  Same math as lstm_bwd_kernel<1>; rows move as 16-byte accesses, the LayerNorm statistics are 3-step
+// reductions and a lane keeps its 13 x 4 parameter-gradient accumulators in registers over all its nodes.
+__device__ __forceinline__ float oct_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v + __shfl_xor_sync(0xffffffffu, v, 4);
+}
+__device__ __forceinline__ void f4(float (&v)[4], const float4 q) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(-2.f * fabsf(x));
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
+
+// y = LN(x) * gamma + beta over the 32 channels of an octet: xhat of this lane's 4 channels and rstd
+__device__ __forceinline__ float oct_ln_fwd(const float (&x)[4], float eps, float (&xh)[4]) {
+    const float mean = oct_sum((x[0] + x[1]) + (x[2] + x[3])) * (1.f / 32.f);
+    float d[4], v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        d[k] = x[k] - mean;
+        v = fmaf(d[k], d[k], v);
+    }
+    const float rstd = rsqrtf(oct_sum(v) * (1.f / 32.f) + eps);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xh[k] = d[k] * rstd;
+    return rstd;
+}
+// dx given dy (in place), accumulating dgamma / dbeta
+__device__ __forceinline__ void oct_ln_bwd(const float (&xh)[4], float (&dy)[4], const float (&gamma)[4], float rstd,
+                                           float (&dgamma)[4], float (&dbeta)[4]) {
+    float g[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        dgamma[k] = fmaf(dy[k], xh[k], dgamma[k]);
+        dbeta[k] += dy[k];
+        g[k] = dy[k] * gamma[k];
+        s1 += g[k];
+        s2 = fmaf(g[k], xh[k], s2);
+    }
+    s1 = oct_sum(s1) * (1.f / 32.f);
+    s2 = oct_sum(s2) * (1.f / 32.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dy[k] = rstd * (g[k] - s1 - xh[k] * s2);
+}
+
+__global__ void __launch_bounds__(256) lstm_bwd_oct_kernel(LstmArgs a) {
+    __shared__ float s_dp[P_COUNT * 32];
+    for (int t = threadIdx.x; t < P_COUNT * 32; t += blockDim.x) s_dp[t] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, o8 = lane >> 3, l8 = lane & 7;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    float prm[P_COUNT][4], dprm[P_COUNT][4];
+#pragma unroll
+    for (int p = 0; p < P_COUNT; ++p) {
+        f4(prm[p], ldg4(a.params + p * 32 + 4 * l8));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dprm[p][k] = 0.f;
+    }
+    const int npass = (a.N + 3) / 4;
+    for (int ps = warp; ps < npass; ps += nwarps) {
+        const int i = 4 * ps + o8;
+        const bool valid = i < a.N;
+        const size_t r32 = (size_t)i * 32 + 4 * l8;
+        const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+        float I[4], F[4], T[4], O[4], Cn[4], cp[4], dH[4], dC[4], dO[4], dhd[4];
+        {
+            const float* gs = a.gates + (size_t)i * 128 + 4 * l8;
+            f4(I, valid ? ldg4(gs) : zero);
+            f4(F, valid ? ldg4(gs + 32) : zero);
+            f4(T, valid ? ldg4(gs + 64) : zero);
+            f4(O, valid ? ldg4(gs + 96) : zero);
+            f4(Cn, valid ? ldg4(a.Craw + r32) : zero);
+            f4(cp, (valid && a.Cprev) ? ldg4(a.Cprev + r32) : zero);
+            f4(dH, (valid && a.dHout) ? ldg4(a.dHout + r32) : zero);
+            f4(dC, (valid && a.dCout) ? ldg4(a.dCout + r32) : zero);
+            f4(dO, (valid && a.dOdirect) ? ldg4(a.dOdirect + r32) : zero);
+            f4(dhd, (valid && a.dHead) ? ldg4(a.dHead + (size_t)i * a.lddh + 4 * l8) : zero);
+        }
+        float tc[4], H[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            tc[k] = fast_tanh(Cn[k]);
+            H[k] = O[k] * tc[k];
+        }
+        float xh[4];
+        if (a.norm_h) {                          // dH arrives w.r.t. LN_h(H')
+            const float rstd = oct_ln_fwd(H, a.eps, xh);
+            oct_ln_bwd(xh, dH, prm[P_GH], rstd, dprm[P_GH], dprm[P_BH]);
+        }
+        if (a.norm_c) {
+            const float rstd = oct_ln_fwd(Cn, a.eps, xh);
+            oct_ln_bwd(xh, dC, prm[P_GC], rstd, dprm[P_GC], dprm[P_BCN]);
+        }
+        if (a.dHead) {                           // head_in[:, :C] = relu(LN_o(O))
+            if (a.norm_o) {
+                const float rstd = oct_ln_fwd(O, a.eps, xh);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dhd[k] = (fmaf(xh[k], prm[P_GO][k], prm[P_BON][k]) > 0.f) ? dhd[k] : 0.f;
+                oct_ln_bwd(xh, dhd, prm[P_GO], rstd, dprm[P_GO], dprm[P_BON]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dhd[k] = (O[k] > 0.f) ? dhd[k] : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) dO[k] += dhd[k];
+        }
+        float dI[4], dF[4], dT[4], dOp[4], dCp[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dOt = fmaf(dH[k], tc[k], dO[k]);
+            dOp[k] = dOt * O[k] * (1.f - O[k]);
+            const float dCn = dC[k] + dH[k] * O[k] * (1.f - tc[k] * tc[k]) + dOp[k] * prm[P_WCO][k];
+            dI[k] = dCn * T[k] * I[k] * (1.f - I[k]);
+            dF[k] = dCn * cp[k] * F[k] * (1.f - F[k]);
+            dT[k] = dCn * I[k] * (1.f - T[k] * T[k]);
+            dCp[k] = dCn * F[k] + dI[k] * prm[P_WCI][k] + dF[k] * prm[P_WCF][k];
+            dprm[P_WCI][k] = fmaf(dI[k], cp[k], dprm[P_WCI][k]);
+            dprm[P_WCF][k] = fmaf(dF[k], cp[k], dprm[P_WCF][k]);
+            dprm[P_WCO][k] = fmaf(dOp[k], Cn[k], dprm[P_WCO][k]);
+            dprm[P_BI][k] += dI[k];
+            dprm[P_BF][k] += dF[k];
+            dprm[P_BC][k] += dT[k];
+            dprm[P_BO][k] += dOp[k];
+        }
+        if (valid) {
+            float* dpr = a.dP + (size_t)i * a.lddp + 4 * l8;
+            *reinterpret_cast<float4*>(dpr) = make_float4(dI[0], dI[1], dI[2], dI[3]);
+            *reinterpret_cast<float4*>(dpr + 32) = make_float4(dF[0], dF[1], dF[2], dF[3]);
+            *reinterpret_cast<float4*>(dpr + 64) = make_float4(dT[0], dT[1], dT[2], dT[3]);
+            *reinterpret_cast<float4*>(dpr + 96) = make_float4(dOp[0], dOp[1], dOp[2], dOp[3]);
+            if (a.dCprev) *reinterpret_cast<float4*>(a.dCprev + r32) = make_float4(dCp[0], dCp[1], dCp[2], dCp[3]);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < P_COUNT; ++p)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float v = dprm[p][k];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (o8 == 0) atomicAdd(&s_dp[p * 32 + 4 * l8 + k], v);
+        }
+    __syncthreads();
+    if (a.dparams)
+        for (int t = threadIdx.x; t < P_COUNT * 32; t += blockDim.x) {
+            const float v = s_dp[t];
+            if (v != 0.f) atomicAdd(&a.dparams[t], v);
+        }
+}
+
 // decoder head tail (model/seq2seq.py:167-178, 427-428): out = tanh(drop(y)) + x0 [-> sigmoid];
 // x_next = [out, x[:, 1:]]
 __global__ void head_finish_fwd_kernel(const float* __restrict__ y, const float* __restrict__ x, int N, int F, int binary,
@@ -365,6 +517,14 @@ QMP_API int qmp_lstm_gates_bwd(int N, int C, const float* gates, const float* Cr
     a.params = params; a.norm_h = norm_h; a.norm_c = norm_c; a.norm_o = norm_o; a.eps = eps; a.dHout = dHout;
     a.dCout = dCout; a.dOdirect = dOdirect; a.dHead = dHead; a.lddh = lddh; a.dP = dP; a.lddp = lddp;
     a.dCprev = dCprev; a.dparams = dparams;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (C == 32 && lddp % 4 == 0 && (!dHead || lddh % 4 == 0) && al16(gates) && al16(Craw) && al16(Cprev) && al16(params) &&
+        al16(dHout) && al16(dCout) && al16(dOdirect) && al16(dHead) && al16(dP) && al16(dCprev)) {
+        const int want = (N + 31) / 32;          // 8 warps x 4 nodes per pass
+        lstm_bwd_oct_kernel<<<want < 148 * 2 ? want : 148 * 2, 256, 0, (cudaStream_t)stream>>>(a);
+        QMP_LAUNCH_CHECK("qmp_lstm_gates_bwd");
+        return 0;
+    }
 #define CALL(QQ) lstm_bwd_kernel<QQ><<<lstm_grid(N), 256, 0, (cudaStream_t)stream>>>(a)
     QMP_DISPATCH_QC(C, CALL);
 #undef CALL

@@ -17,6 +17,7 @@ ENABLED = True      # tests flip this to cross-check the fused kernels against t
 TC_WGRAD = True     # weight gradients: one tcgen05 launch per group (False: ten FFMA reductions, the cross-check)
 TC_BWD = True       # backward (target / source side) on tcgen05 (csrc/fused_bwd_tc.inl); False: fp32-FFMA kernels
 TC_FWD = True       # forward on tcgen05 (csrc/fused_fwd_tc.inl); False: the fp32-FFMA kernel (csrc/fused_fwd.inl)
+CELL_FWD = True     # decoder cell (4 X convs + 4 H convs, gate mode): the persistent gates-batched kernel (csrc/fused_cell_fwd.cu)
 _f32 = torch.float32
 
 
@@ -83,6 +84,28 @@ def tc_image(w, DC, kind=0):
     return img
 
 
+_cell_cache = {}
+
+
+def cell_image(wa, wb):
+    """uint8 image of the decoder cell's eight convs (qmp_fused_pack_cell; layout csrc/fused_cell.cuh), cached per pack pair."""
+    key = (wa.data_ptr(), wb.data_ptr(), wa._version, wb._version)
+    hit = _cell_cache.get(key)
+    if hit is not None and hit[0] is wa and hit[1] is wb:
+        return hit[2]
+    img = torch.empty(int(_lib.lib().qmp_fused_cell_image_bytes()), dtype=torch.uint8, device=wb.device)
+    _lib.call("qmp_fused_pack_cell", wa.detach().contiguous(), wb.detach().contiguous(), img)
+    if len(_cell_cache) > 64:
+        _cell_cache.clear()
+    _cell_cache[key] = (wa, wb, img)
+    return img
+
+
+def is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb):
+    return (mode == 1 and GA == 4 and GB == 4 and sharedB and DA == 4 and DB == 32 and C == FC and xa is not None
+            and xa.shape[1] % 4 == 0 and xb.shape[1] % 4 == 0)
+
+
 class FusedGroupFn(torch.autograd.Function):
     """One fused launch: segment A (xa, wa: GA convs on a narrow shared input) + segment B (xb, wb: GB convs),
     mode 1 -> LSTM gates (+ norms, head input), mode 0 -> plain conv outputs [N, (GA+GB)*C]."""
@@ -114,15 +137,21 @@ class FusedGroupFn(torch.autograd.Function):
         cc = concat.contiguous().reshape(-1) if (want_head and concat is not None) else None
         prm = params.contiguous() if params is not None else None
         entry, wa_k, wb_k = "qmp_fused_fwd", wa, wb
-        if TC_FWD:
+        if TC_FWD and CELL_FWD and is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb):
+            _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, xa.shape[1], xb, xb.shape[1],
+                      cell_image(wa, wb), Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps), gates, Craw, O, H, Cn, head,
+                      HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
+            entry = None
+        elif TC_FWD:
             entry = "qmp_fused_fwd_tc"
             wa_k = tc_image(wa, cap_of(DA, True)) if GA else None
             wb_k = tc_image(wb, cap_of(DB, False))
-        _lib.call(entry, N, csr.in_ptr, csr.in_src, csr.edge_attr_in,
-                  xa, xa.shape[1] if xa is not None else 0, DA, GA, wa_k,
-                  xb, xb.shape[1], DB, GB, int(sharedB), wb_k,
-                  mode, int(relu_out), C, out, NC * C, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps),
-                  gates, Craw, O, H, Cn, head, HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
+        if entry is not None:
+            _lib.call(entry, N, csr.in_ptr, csr.in_src, csr.edge_attr_in,
+                      xa, xa.shape[1] if xa is not None else 0, DA, GA, wa_k,
+                      xb, xb.shape[1], DB, GB, int(sharedB), wb_k,
+                      mode, int(relu_out), C, out, NC * C, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps),
+                      gates, Craw, O, H, Cn, head, HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
         ctx.save_for_backward(xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out if relu_out else None)
         ctx.csr, ctx.cfg = csr, cfg
         ctx.concat_shape = tuple(concat.shape) if concat is not None else None

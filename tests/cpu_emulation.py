@@ -609,6 +609,26 @@ def qmp_fused_fwd_tc(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb, DB, GB
                   GB, sharedB, _pack_from_image(wb, GB, _cap(DB, False)), *rest)
 
 
+def _total(DC):
+    return (DC + 2) * DC + DC + 4 + _FC * (DC + 4) + _FC * DC + _FC
+
+
+def qmp_fused_pack_cell(packA, packB, out):
+    """Emulated cell image = the raw bytes of the two packs (the emulated kernel unpacks them again)."""
+    na, nb = 4 * _total(4) * 4, 4 * _total(32) * 4
+    out[:na] = flat(packA, 4 * _total(4)).contiguous().view(torch.uint8)
+    out[na:na + nb] = flat(packB, 4 * _total(32)).contiguous().view(torch.uint8)
+
+
+def qmp_fused_cell_fwd(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, Cprev, params, norm_h, norm_c, norm_o, eps, gates, Craw,
+                       Oout, Hout, Cout, head_in, ldh, concat, logit, mstat, linv, drop_p, seed):
+    na, nb = 4 * _total(4) * 4, 4 * _total(32) * 4
+    wa = image[:na].contiguous().view(torch.float32).view(4, _total(4))
+    wb = image[na:na + nb].contiguous().view(torch.float32).view(4, _total(32))
+    qmp_fused_fwd(N, in_ptr, in_src, ea, xa, lda, 4, 4, wa, xb, ldb, 32, 4, 1, wb, 1, 0, _FC, None, 8 * _FC, Cprev, params, norm_h,
+                  norm_c, norm_o, eps, gates, Craw, Oout, Hout, Cout, head_in, ldh, concat, logit, mstat, linv, drop_p, seed)
+
+
 def _bwd_pack_from_image(img, G, DC):
     """Backward pack (W1 | b1 | W1T | W2T | W3T) rebuilt from the forward pack stored in an emulated image."""
     if img is None:
@@ -675,6 +695,10 @@ class Emulated:
             @staticmethod
             def qmp_quadtree_pyramid_cells(n, m, s):
                 return 1
+
+            @staticmethod
+            def qmp_fused_cell_image_bytes():
+                return 4 * 4 * (_total(4) + _total(32))
 
         _lib.call = call
         _lib.lib = lambda: _FakeLib

@@ -98,10 +98,11 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
             pytest.skip("kernel variants exist on the device only")
         old = _lib.lib().qmp_set_fused_paired(2 if path == "tc_pw" else 0)
         monkeypatch.setattr(FZ, "_restore_paired", old, raising=False)
+        monkeypatch.setattr(FZ, "CELL_FWD", False)       # ... also where the decoder-cell kernel would take over
     monkeypatch.setattr(FZ, "ENABLED", fused)
     monkeypatch.setattr(FZ, "TC_FWD", path.startswith("tc"))
     monkeypatch.setattr(FZ, "TC_BWD", path.startswith("tc"))
-    n_fused = lambda: _lib.CALL_COUNTS.get("qmp_fused_fwd", 0) + _lib.CALL_COUNTS.get("qmp_fused_fwd_tc", 0)
+    n_fused = lambda: sum(_lib.CALL_COUNTS.get(k, 0) for k in ("qmp_fused_fwd", "qmp_fused_fwd_tc", "qmp_fused_cell_fwd"))
     calls_before = n_fused()
     ei, ea, n = _graph(4, use_edge_attrs=(conv == "TransformerConv"))
     torch.manual_seed(11)
@@ -253,3 +254,54 @@ def test_fused_wgrad_kernel(be, N, DA, GA, DB, GB, shared, mode, C):
         got = (gwa if segA else gwb)[g].double().cpu()
         err = float((got - ref).abs().max() / ref.abs().max())
         assert err < 2e-5, f"conv {c}: rel err {err}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,drop_p,with_c", [(1, 0.0, True), (130, 0.0, False), (5001, 0.1, True), (47200, 0.0, True)])
+def test_decoder_cell_kernel_matches_per_conv_kernel(N, drop_p, with_c):
+    """qmp_fused_cell_fwd (gates batched, 8 lanes per node, persistent) against qmp_fused_fwd_tc (one conv at a time, one
+    thread per node) on the same inputs: ragged in-degrees 0..9 (several edge quads per node, isolated nodes), partial
+    tiles, several tiles per CTA, attention dropout with the shared counter-based mask.  Every output and every tensor
+    saved for the backward pass must agree (both are 3xTF32 + fp32; only summation orders differ)."""
+    from quadtree_mpnnlstm_b200 import _lib, fused as FZ
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(N)
+    deg = torch.randint(0, 10, (N,), generator=g)
+    if N > 20000:
+        deg = deg.clamp(max=4)
+    ptr = torch.zeros(N + 1, dtype=torch.int32)
+    ptr[1:] = deg.cumsum(0).int()
+    E = int(ptr[-1])
+    nbr = torch.randint(0, N, (max(E, 1),), generator=g).int()
+    ea = torch.rand(max(E, 1), 2, generator=g)
+    xa, xb, Cp = torch.randn(N, 4, generator=g), torch.randn(N, 32, generator=g), torch.randn(N, 32, generator=g)
+    wa = torch.randn(4, FZ.conv_total(4), generator=g) * 0.3
+    wb = torch.randn(4, FZ.conv_total(32), generator=g) * 0.2
+    prm = torch.randn(13, 32, generator=g) * 0.5
+    concat = torch.randn(N, generator=g)
+    ptr, nbr, ea, xa, xb, Cp, wa, wb, prm, concat = (t.to(dev) for t in (ptr, nbr, ea, xa, xb, Cp, wa, wb, prm, concat))
+    Cp = Cp if with_c else None
+
+    def outputs():
+        z = lambda *s: torch.full(s, float("nan"), device=dev)
+        return dict(gates=z(N, 128), Craw=z(N, 32), O=z(N, 32), H=z(N, 32), C=z(N, 32), head=z(N, 36), logit=z(max(E, 1), 8),
+                    mstat=z(N, 8), linv=z(N, 8))
+
+    a, b = outputs(), outputs()
+    seed = 1234567
+    _lib.call("qmp_fused_fwd_tc", N, ptr, nbr, ea, xa, 4, 4, 4, FZ.tc_image(wa, 4), xb, 32, 32, 4, 1, FZ.tc_image(wb, 32), 1, 0, 32,
+              None, 256, Cp, prm, 1, 1, 1, 1e-5, a["gates"], a["Craw"], a["O"], a["H"], a["C"], a["head"], 36, concat, a["logit"],
+              a["mstat"], a["linv"], drop_p, seed)
+    _lib.call("qmp_fused_cell_fwd", N, ptr, nbr, ea, xa, 4, xb, 32, FZ.cell_image(wa, wb), Cp, prm, 1, 1, 1, 1e-5, b["gates"],
+              b["Craw"], b["O"], b["H"], b["C"], b["head"], 36, concat, b["logit"], b["mstat"], b["linv"], drop_p, seed)
+    torch.cuda.synchronize()
+    for k in a:
+        va, vb = a[k], b[k]
+        if k == "logit":
+            va, vb = va[:E], vb[:E]
+        if k == "mstat":                      # -inf for isolated nodes in both
+            assert torch.equal(torch.isinf(va), torch.isinf(vb)), k
+            va, vb = torch.nan_to_num(va, neginf=0.0), torch.nan_to_num(vb, neginf=0.0)
+        assert not torch.isnan(vb).any(), f"{k}: unwritten / NaN entries"
+        err = float((va - vb).abs().max()) / max(float(va.abs().max()), 1e-6) if va.numel() else 0.0
+        assert err < 2e-5, f"{k}: {err}"
