@@ -89,11 +89,22 @@ __device__ __forceinline__ void matvec_acc(float (&y)[R], const float* __restric
     }
 }
 
-// gate nonlinearities on the fast exp / divide units (relative error ~1e-6, far inside the 1e-4 parity bar)
-__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float ftanh(float x) {
-    const float e = __expf(-2.f * fabsf(x));                    // in (0, 1]: no overflow
-    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+// gate nonlinearities straight on the MUFU units (ex2.approx / rcp.approx, relative error ~2^-22, far inside the 1e-4
+// parity bar): 4 / 5 instructions instead of the ~13 / ~16 of __expf + __fdividef with their range handling.
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_exp(float x) { return fast_ex2(x * 1.4426950408889634f); }      // exp(-inf) = 0
+__device__ __forceinline__ float sigm(float x) { return fast_rcp(1.f + fast_ex2(x * -1.4426950408889634f)); }
+__device__ __forceinline__ float ftanh(float x) {               // 1 - 2 / (1 + e^2x): saturates cleanly at +-1
+    return fmaf(-2.f, fast_rcp(1.f + fast_ex2(x * 2.8853900817779268f)), 1.f);
 }
 
 // LayerNorm over FC register values (biased variance, like torch.nn.LayerNorm)

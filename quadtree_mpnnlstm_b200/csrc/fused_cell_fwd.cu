@@ -207,7 +207,7 @@ __device__ __forceinline__ void cell_xconv(const FusedFwdArgs& a, const uint8_t*
         const float s = fmaf(u[3], xj.w, fmaf(u[2], xj.z, fmaf(u[1], xj.y, fmaf(u[0], xj.x, fmaf(u[4], ev.x, u[5] * ev.y)))));
         a.logit[(size_t)kk * 8 + cg] = s;
         const float mn = fmaxf(m, s);
-        const float sc = __expf(m - mn), pe = __expf(s - mn);
+        const float sc = fast_exp(m - mn), pe = fast_exp(s - mn);
         const float pk = pe * fdropout_scale(a.seed, (long long)kk * 8 + cg, a.drop_p);
         l = fmaf(l, sc, pe);
         zs = fmaf(zs, sc, pk);
@@ -229,7 +229,7 @@ __device__ __forceinline__ void cell_xconv(const FusedFwdArgs& a, const uint8_t*
         if (a.ea) ev = __ldg(reinterpret_cast<const float2*>(a.ea) + kk);
         edge(kk, xj, ev);
     }
-    const float li = (l > 0.f) ? 1.f / l : 0.f;
+    const float li = (l > 0.f) ? fast_rcp(l) : 0.f;
     if (valid) {
         a.mstat[(size_t)i * 8 + cg] = m;
         a.linv[(size_t)i * 8 + cg] = li;
@@ -450,8 +450,8 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
                     float gm = fmaxf(s, __shfl_xor_sync(0xffffffffu, s, 1));
                     gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 2));
                     const float mn = fmaxf(m[r], gm);
-                    sc[r] = (mn == -INFINITY) ? 1.f : __expf(m[r] - mn);
-                    const float pe = on ? __expf(s - mn) : 0.f;
+                    sc[r] = (mn == -INFINITY) ? 1.f : fast_exp(m[r] - mn);
+                    const float pe = on ? fast_exp(s - mn) : 0.f;
                     pk[r] = pe * fdropout_scale(a.seed, (long long)kk * 8 + c, a.drop_p);
                     l[r] = fmaf(l[r], sc[r], quad_sum(pe));
                     zs[r] = fmaf(zs[r], sc[r], quad_sum(pk[r]));
@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
             float li[2];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-                li[r] = (l[r] > 0.f) ? 1.f / l[r] : 0.f;
+                li[r] = (l[r] > 0.f) ? fast_rcp(l[r]) : 0.f;
                 if (valid && e4 == 0) {
                     a.mstat[(size_t)i * 8 + 4 + 2 * r + cc] = m[r];
                     a.linv[(size_t)i * 8 + 4 + 2 * r + cc] = li[r];
@@ -526,11 +526,14 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
         cell_load_own(ow, a, next0 + nrow, nrow < ncount, cg);
         cell_load_idx(ix, a, next0, ncount, warp, o8, e4);
         float4 cp4[2];
+        float cct[2];
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             const int ln = 4 * (warp + 16 * p) + o8;
             cp4[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cct[p] = 0.f;
             if (ln < tcount && a.Cprev) cp4[p] = __ldg(reinterpret_cast<const float4*>(a.Cprev + (size_t)(tile0 + ln) * FC) + l8);
+            if (ln < tcount && a.concat && l8 == 0) cct[p] = __ldg(a.concat + tile0 + ln);
         }
         if (next >= 0) cell_xconv(a, smem, exch, next0 + nrow, nrow < ncount, nrow, cg);
         CELL_MARK(5);
@@ -635,9 +638,13 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
                     if (a.head_in) {
                         float* hr = a.head_in + i * a.ldh;
                         st4(hr + 4 * l8, fmaxf(O[p][0], 0.f), fmaxf(O[p][1], 0.f), fmaxf(O[p][2], 0.f), fmaxf(O[p][3], 0.f));
-                        if (l8 == 0) {
-                            if (a.concat) hr[FC] = a.concat[i];
-                            for (int k = FC + 1; k < a.ldh; ++k) hr[k] = 0.f;
+                        if (l8 == 0) {                    // column 32: concat layer (left alone when absent), then zero pads
+                            if (a.ldh == FC + 4 && a.concat) {
+                                st4(hr + FC, cct[p], 0.f, 0.f, 0.f);
+                            } else {
+                                if (a.concat) hr[FC] = cct[p];
+                                for (int k = FC + 1; k < a.ldh; ++k) hr[k] = 0.f;
+                            }
                         }
                     }
                 }

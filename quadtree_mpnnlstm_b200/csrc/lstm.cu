@@ -315,19 +315,22 @@ __device__ __forceinline__ void oct_ln_bwd(const float (&xh)[4], float (&dy)[4],
     for (int k = 0; k < 4; ++k) dy[k] = rstd * (g[k] - s1 - xh[k] * s2);
 }
 
-__global__ void __launch_bounds__(256) lstm_bwd_oct_kernel(LstmArgs a) {
+__global__ void __launch_bounds__(256, 2) lstm_bwd_oct_kernel(LstmArgs a) {
     __shared__ float s_dp[P_COUNT * 32];
-    for (int t = threadIdx.x; t < P_COUNT * 32; t += blockDim.x) s_dp[t] = 0.f;
+    __shared__ __align__(16) float s_prm[P_COUNT * 32];
+    for (int t = threadIdx.x; t < P_COUNT * 32; t += blockDim.x) {
+        s_dp[t] = 0.f;
+        s_prm[t] = a.params[t];
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, o8 = lane >> 3, l8 = lane & 7;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    float prm[P_COUNT][4], dprm[P_COUNT][4];
+    float dprm[P_COUNT][4];
 #pragma unroll
-    for (int p = 0; p < P_COUNT; ++p) {
-        f4(prm[p], ldg4(a.params + p * 32 + 4 * l8));
+    for (int p = 0; p < P_COUNT; ++p)
 #pragma unroll
         for (int k = 0; k < 4; ++k) dprm[p][k] = 0.f;
-    }
+    auto PRM = [&](int p, float (&v)[4]) { f4(v, *reinterpret_cast<const float4*>(s_prm + p * 32 + 4 * l8)); };
     const int npass = (a.N + 3) / 4;
     for (int ps = warp; ps < npass; ps += nwarps) {
         const int i = 4 * ps + o8;
@@ -356,19 +359,26 @@ __global__ void __launch_bounds__(256) lstm_bwd_oct_kernel(LstmArgs a) {
         }
         float xh[4];
         if (a.norm_h) {                          // dH arrives w.r.t. LN_h(H')
+            float g[4];
+            PRM(P_GH, g);
             const float rstd = oct_ln_fwd(H, a.eps, xh);
-            oct_ln_bwd(xh, dH, prm[P_GH], rstd, dprm[P_GH], dprm[P_BH]);
+            oct_ln_bwd(xh, dH, g, rstd, dprm[P_GH], dprm[P_BH]);
         }
         if (a.norm_c) {
+            float g[4];
+            PRM(P_GC, g);
             const float rstd = oct_ln_fwd(Cn, a.eps, xh);
-            oct_ln_bwd(xh, dC, prm[P_GC], rstd, dprm[P_GC], dprm[P_BCN]);
+            oct_ln_bwd(xh, dC, g, rstd, dprm[P_GC], dprm[P_BCN]);
         }
         if (a.dHead) {                           // head_in[:, :C] = relu(LN_o(O))
             if (a.norm_o) {
+                float g[4], b[4];
+                PRM(P_GO, g);
+                PRM(P_BON, b);
                 const float rstd = oct_ln_fwd(O, a.eps, xh);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) dhd[k] = (fmaf(xh[k], prm[P_GO][k], prm[P_BON][k]) > 0.f) ? dhd[k] : 0.f;
-                oct_ln_bwd(xh, dhd, prm[P_GO], rstd, dprm[P_GO], dprm[P_BON]);
+                for (int k = 0; k < 4; ++k) dhd[k] = (fmaf(xh[k], g[k], b[k]) > 0.f) ? dhd[k] : 0.f;
+                oct_ln_bwd(xh, dhd, g, rstd, dprm[P_GO], dprm[P_BON]);
             } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) dhd[k] = (O[k] > 0.f) ? dhd[k] : 0.f;
@@ -376,16 +386,19 @@ __global__ void __launch_bounds__(256) lstm_bwd_oct_kernel(LstmArgs a) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) dO[k] += dhd[k];
         }
-        float dI[4], dF[4], dT[4], dOp[4], dCp[4];
+        float dI[4], dF[4], dT[4], dOp[4], dCp[4], wci[4], wcf[4], wco[4];
+        PRM(P_WCI, wci);
+        PRM(P_WCF, wcf);
+        PRM(P_WCO, wco);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float dOt = fmaf(dH[k], tc[k], dO[k]);
             dOp[k] = dOt * O[k] * (1.f - O[k]);
-            const float dCn = dC[k] + dH[k] * O[k] * (1.f - tc[k] * tc[k]) + dOp[k] * prm[P_WCO][k];
+            const float dCn = dC[k] + dH[k] * O[k] * (1.f - tc[k] * tc[k]) + dOp[k] * wco[k];
             dI[k] = dCn * T[k] * I[k] * (1.f - I[k]);
             dF[k] = dCn * cp[k] * F[k] * (1.f - F[k]);
             dT[k] = dCn * I[k] * (1.f - T[k] * T[k]);
-            dCp[k] = dCn * F[k] + dI[k] * prm[P_WCI][k] + dF[k] * prm[P_WCF][k];
+            dCp[k] = dCn * F[k] + dI[k] * wci[k] + dF[k] * wcf[k];
             dprm[P_WCI][k] = fmaf(dI[k], cp[k], dprm[P_WCI][k]);
             dprm[P_WCF][k] = fmaf(dF[k], cp[k], dprm[P_WCF][k]);
             dprm[P_WCO][k] = fmaf(dOp[k], Cn[k], dprm[P_WCO][k]);
