@@ -18,6 +18,7 @@
 //
 // Reference: GConvLSTM.forward (model/model.py:394-463) around PyG TransformerConv (model/model.py:51), Decoder norms
 // and head input (model/seq2seq.py:138-165).
+#include <stdlib.h>
 #include "fused_fwd.inl"
 #include "fused_cell.cuh"
 
@@ -171,20 +172,27 @@ __device__ __forceinline__ void cell_stage_own(const CellOwn& ow, uint32_t base,
 }
 
 // X conv cg of node i (row nrow of the tile): plain FFMA, online segment softmax; aggregates -> exchange columns 36..43
-__device__ __forceinline__ void cell_xconv(const FusedFwdArgs& a, const uint8_t* smem, float* exch, int i, bool valid, int nrow, int cg) {
+struct CellXIdx {               // X conv of one node: in-edge range and the sources of its first four in-edges
+    int k0, k1, jn[4];
+};
+__device__ __forceinline__ void cell_xconv_idx(CellXIdx& xi, const FusedFwdArgs& a, int i, bool valid) {
+    xi.k0 = valid ? __ldg(a.ptr + i) : 0;
+    xi.k1 = valid ? __ldg(a.ptr + i + 1) : 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) xi.jn[e] = (xi.k0 + e < xi.k1) ? __ldg(a.nbr + xi.k0 + e) : -1;
+}
+
+__device__ __forceinline__ void cell_xconv(const FusedFwdArgs& a, const uint8_t* smem, float* exch, int i, bool valid, int nrow, int cg,
+                                           const CellXIdx& xix) {
     using L = CellLayout;
     float4 xi = make_float4(0.f, 0.f, 0.f, 0.f);
-    int k0 = 0, k1 = 0;
-    if (valid) {
-        xi = __ldg(reinterpret_cast<const float4*>(a.xa + (size_t)i * a.lda));
-        k0 = __ldg(a.ptr + i);
-        k1 = __ldg(a.ptr + i + 1);
-    }
+    if (valid) xi = __ldg(reinterpret_cast<const float4*>(a.xa + (size_t)i * a.lda));
+    const int k0 = xix.k0, k1 = xix.k1;
     int jn[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) jn[e] = xix.jn[e];
     float2 evn[4];
     float4 xn[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) jn[e] = (k0 + e < k1) ? __ldg(a.nbr + k0 + e) : -1;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
         evn[e] = make_float2(0.f, 0.f);
@@ -270,8 +278,37 @@ __device__ __forceinline__ void cell_issue_g1(uint32_t tmem, const uint8_t* smem
 // Software pipeline of a CTA over its tiles (tensor pipe and SIMT phases of consecutive tiles overlap):
 //   ... | U dump(t) | edge phase(t) | stage z(t) | G2(t) issued || X convs(t+1), row / index prefetch(t+1) || P dump(t) |
 //       stage [h|x](t+1) | G1(t+1) issued || gate epilogue(t) || U dump(t+1) | ...
+// tiles of a CTA: it owns the Q consecutive nodes from blockIdx.x * Q and walks them in R tiles of T0 (+ / - stagger) nodes
+struct CellTiling {
+    int Q, R, T0, stagger;
+};
+// Tile r of this CTA: first node and node count.  With R == 3 the tile sizes are T0 + d, T0, T0 - d rotated by blockIdx.x % 3,
+// so neighbouring SMs drift out of phase and their store-heavy epilogues do not all hit L2 / HBM in the same microsecond.
+__device__ __forceinline__ void cell_tile(const CellTiling& tl, int N, int r, int& start, int& count) {
+    const int beg = (int)blockIdx.x * tl.Q;
+    int end = beg + tl.Q;
+    if (end > N) end = N;
+    int s0 = beg;
+    int size = tl.T0;
+    if (tl.R == 3 && tl.stagger > 0) {
+        const int rot = (int)(blockIdx.x % 3);
+        const int d0 = (rot == 0) ? tl.stagger : (rot == 1 ? 0 : -tl.stagger);           // sizes of tiles 0, 1, 2:
+        const int d1 = (rot == 0) ? 0 : (rot == 1 ? -tl.stagger : tl.stagger);            // rot 0: +d 0 -d, rot 1: 0 -d +d,
+        const int d2 = -d0 - d1;                                                          // rot 2: -d +d 0
+        if (r >= 1) s0 += tl.T0 + d0;
+        if (r >= 2) s0 += tl.T0 + d1;
+        size += (r == 0) ? d0 : (r == 1 ? d1 : d2);
+    } else {
+        s0 += r * tl.T0;
+    }
+    start = s0;
+    count = end - s0;
+    if (count > size) count = size;
+    if (count < 0) count = 0;
+}
+
 __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const __grid_constant__ FusedFwdArgs a,
-                                                                         const uint8_t* __restrict__ img, int T) {
+                                                                         const uint8_t* __restrict__ img, const CellTiling tl) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[2];                 // 0: MMA groups (every commit is waited once by every thread), 1: image landed
     __shared__ uint32_t tmem_slot;
@@ -304,10 +341,13 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
     const int cc = l8 >> 2, e4 = l8 & 3;                       // (conv of the pair, edge of the quad) role in the softmax stage
     const float* b1h = reinterpret_cast<const float*>(smem + L::B1H);
     const float* b3s = reinterpret_cast<const float*>(smem + L::B3S);
-    const int ntiles = (a.N + T - 1) / T;
     uint32_t par = 0;
-    int tile = blockIdx.x;
-    if (tile >= ntiles) tile = -1;
+    int tile = 0;                                              // tile (round) index of this CTA, -1: none left
+    {
+        int s0, c0;
+        cell_tile(tl, a.N, 0, s0, c0);
+        if (c0 <= 0) tile = -1;
+    }
     if (warp == CELL_WORKERS / 32) {
         // ---- the MMA warp: one lane issues every tcgen05.mma of the CTA, in step with the workers' barriers (an issuing
         // thread is held for the ~90 cycles each MMA occupies the tensor pipe; the workers must not be)
@@ -316,8 +356,9 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
         if (lane == 0 && tile >= 0) cell_issue_g1(tmem, smem, &bars[0]);
         __syncwarp();
         while (tile >= 0) {
-            int next = tile + (int)gridDim.x;
-            if (next >= ntiles) next = -1;
+            int next = tile + 1, ns0, nc0;
+            cell_tile(tl, a.N, next, ns0, nc0);
+            if (next >= tl.R || nc0 <= 0) next = -1;
             cell_sync();                                       // U dumped
             cell_sync();                                       // edge phase done
             cell_sync();                                       // z rows staged
@@ -343,11 +384,14 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
     CellIdx ix;
     {   // prologue: the first tile's X convs, [h|x] rows and first contraction
         CellOwn ow;
-        const int tile0 = tile * T, tcount = tile < 0 ? 0 : ((a.N - tile0 < T) ? a.N - tile0 : T);
+        int tile0 = 0, tcount = 0;
+        if (tile >= 0) cell_tile(tl, a.N, 0, tile0, tcount);
         cell_load_own(ow, a, tile0 + nrow, nrow < tcount, cg);
         cell_load_idx(ix, a, tile0, tcount, warp, o8, e4);
+        CellXIdx xix;
+        cell_xconv_idx(xix, a, tile0 + nrow, nrow < tcount);
         tc::mbar_wait(&bars[1], 0);                            // weights in shared memory
-        cell_xconv(a, smem, exch, tile0 + nrow, nrow < tcount, nrow, cg);
+        cell_xconv(a, smem, exch, tile0 + nrow, nrow < tcount, nrow, cg, xix);
         cell_stage_own(ow, lane_addr + TM_R0, cg);
         tc::fence_before_sync();
         cell_sync();
@@ -355,12 +399,16 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
     }
 
     while (tile >= 0) {
-        const int tile0 = tile * T;
-        const int tcount = (a.N - tile0 < T) ? a.N - tile0 : T;
-        int next = tile + (int)gridDim.x;
-        if (next >= ntiles) next = -1;
-        const int next0 = next * T, ncount = next < 0 ? 0 : ((a.N - next0 < T) ? a.N - next0 : T);
+        int tile0, tcount, next = tile + 1, next0, ncount;
+        cell_tile(tl, a.N, tile, tile0, tcount);
+        cell_tile(tl, a.N, next, next0, ncount);
+        if (next >= tl.R || ncount <= 0) {
+            next = -1;
+            ncount = 0;
+        }
         CELL_MARK(1);
+        CellXIdx xix;                                          // next tile's X convs: indices now, rows and math under G2
+        cell_xconv_idx(xix, a, next0 + nrow, nrow < ncount);
         tc::mbar_wait(&bars[0], par);                          // G1(tile): U and the skip part of P
         par ^= 1;
         tc::fence_after_sync();
@@ -535,7 +583,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
             if (ln < tcount && a.Cprev) cp4[p] = __ldg(reinterpret_cast<const float4*>(a.Cprev + (size_t)(tile0 + ln) * FC) + l8);
             if (ln < tcount && a.concat && l8 == 0) cct[p] = __ldg(a.concat + tile0 + ln);
         }
-        if (next >= 0) cell_xconv(a, smem, exch, next0 + nrow, nrow < ncount, nrow, cg);
+        if (next >= 0) cell_xconv(a, smem, exch, next0 + nrow, nrow < ncount, nrow, cg, xix);
         CELL_MARK(5);
         tc::mbar_wait(&bars[0], par);                          // G2(tile)
         par ^= 1;
@@ -733,6 +781,8 @@ extern "C" __attribute__((visibility("default"))) int qmpx_cell_cta_dump(unsigne
 }
 #endif
 
+static int g_cell_stagger = -1;        // nodes; QMP_CELL_STAGGER overrides the default (timing experiments)
+
 // Bytes of the decoder-cell weight image.
 QMP_API long long qmp_fused_cell_image_bytes(void) { return CellLayout::BYTES; }
 
@@ -772,14 +822,18 @@ QMP_API int qmp_fused_cell_fwd(int N, const int* in_ptr, const int* in_src, cons
         QMP_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
         QMP_CUDA(cudaFuncSetAttribute(fused_cell_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CELL_SMEM));
     }
-    // tiles of T <= 128 nodes sized so that every CTA runs the same number of (equally full) tiles
+    // every CTA owns Q consecutive nodes and walks them in R equally full tiles of <= 128 nodes (cell_tile)
+    if (g_cell_stagger < 0) {
+        const char* e = getenv("QMP_CELL_STAGGER");
+        g_cell_stagger = e ? atoi(e) : 0;      // measured: 0, 12 and 20 nodes give the same 58 us (the epilogue is not a chip-wide store burst)
+    }
     const int G = cdiv(N, 128) < n_sm ? cdiv(N, 128) : n_sm;
-    const int R = cdiv(N, 128 * (long long)G);
-    int T = (cdiv(N, (long long)R * G) + 3) & ~3;
-    if (T > 128) T = 128;
-    const int ntiles = cdiv(N, T);
-    fused_cell_fwd_kernel<<<ntiles < G ? ntiles : G, CELL_THREADS, CELL_SMEM, (cudaStream_t)stream>>>(
-        a, reinterpret_cast<const uint8_t*>(image), T);
+    CellTiling tl;
+    tl.Q = (cdiv(N, G) + 3) & ~3;
+    tl.R = cdiv(tl.Q, 128);
+    tl.T0 = (cdiv(tl.Q, tl.R) + 3) & ~3;
+    tl.stagger = 128 - tl.T0 < g_cell_stagger ? (128 - tl.T0) & ~3 : g_cell_stagger;
+    fused_cell_fwd_kernel<<<cdiv(N, tl.Q), CELL_THREADS, CELL_SMEM, (cudaStream_t)stream>>>(a, reinterpret_cast<const uint8_t*>(image), tl);
     QMP_LAUNCH_CHECK("fused_cell_fwd_kernel");
     return 0;
 }
