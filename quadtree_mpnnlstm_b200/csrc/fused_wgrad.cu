@@ -31,7 +31,7 @@ constexpr int WG_KT = 64;                       // nodes per tile (K of the tile
 constexpr int WG_KC = WG_KT / 4;                // 16-byte K chunks per B row
 constexpr int WG_SBO = WG_KC * 128 + 16;        // bytes between consecutive 8-row blocks of B (padded)
 constexpr int WG_MAXCONV = 12;
-constexpr int WG_BIT = 3;                       // B items per thread: 16 node groups x (<= 20 chunks) / 128 threads
+constexpr int WG_BIT = 2;                       // B items per thread: 16 node groups x (<= 32 chunks) / 256 threads
 constexpr uint32_t WG_TMEM_COLS = 256, WG_AHI = 128, WG_ALO = 192;
 
 // One reduction problem = one or two convs ("parts") that share the gradient rows g (in gate mode conv_x_g and conv_h_g
@@ -71,7 +71,13 @@ __device__ __forceinline__ void wg_st_split(uint8_t* hi, uint8_t* lo, uint32_t o
     *reinterpret_cast<float4*>(lo + off) = l;
 }
 
-__global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant__ WgArgs a) {
+constexpr int WG_WORKERS = 256;                 // 8 staging warps: warps w and w + 4 share TMEM lane quarter w, each takes half of a tile's nodes
+constexpr int WG_THREADS = WG_WORKERS + 32;     // + the warp that issues the MMAs
+constexpr int WG_KH = WG_KT / 2;                // nodes per tile staged by one thread
+__device__ __forceinline__ void wg_sync() { asm volatile("bar.sync 0, %0;" ::"n"(WG_THREADS) : "memory"); }
+__device__ __forceinline__ void wg_sync_workers() { asm volatile("bar.sync 1, %0;" ::"n"(WG_WORKERS) : "memory"); }
+
+__global__ void __launch_bounds__(WG_THREADS, 2) fused_wgrad_kernel(const __grid_constant__ WgArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -96,37 +102,38 @@ __global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant_
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, WG_TMEM_COLS);
-    for (int idx = t; idx < 2 * (NB / 8) * WG_SBO / 16; idx += 128) reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = t; idx < 2 * (NB / 8) * WG_SBO / 16; idx += WG_THREADS) reinterpret_cast<float4*>(smem)[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
     tc::fence_before_sync();
-    __syncthreads();
+    wg_sync();
     tc::fence_after_sync();
     const uint32_t tmem = tmem_slot;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t idesc = tc::make_idesc_tf32(128, NB);
 
     // A: this thread's component of [dU_0 | dU_1 | g]
+    const int tr = t & 127, half = (t >> 7) & 1;          // A row (= TMEM lane) and node half of this thread
     const float* a_src = nullptr;
     int a_ld = 0;
-    if (t < RA1) { a_src = cv.p[0].dus + t; a_ld = cv.p[0].ldz; }
-    else if (t < RG) { a_src = cv.p[1].dus + (t - RA1); a_ld = cv.p[1].ldz; }
-    else if (t < RG + FC && t - RG < cv.gvalid) { a_src = cv.g + (t - RG); a_ld = cv.ldg; }
+    if (tr < RA1) { a_src = cv.p[0].dus + tr; a_ld = cv.p[0].ldz; }
+    else if (tr < RG) { a_src = cv.p[1].dus + (tr - RA1); a_ld = cv.p[1].ldz; }
+    else if (tr < RG + FC && tr - RG < cv.gvalid) { a_src = cv.g + (tr - RG); a_ld = cv.ldg; }
     const bool vx0 = (cv.p[0].ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cv.p[0].x) & 15) == 0);
     const bool vx1 = two && (cv.p[1].ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(cv.p[1].x) & 15) == 0);
     const int ntiles = (a.N + WG_KT - 1) / WG_KT;
     const int items = (WG_KT / 4) * qb;
 
-    float va[WG_KT];
+    float va[WG_KH];
     float4 vb[WG_BIT][4];
     auto fetch = [&](int tile) {
         const int n0 = tile * WG_KT;
 #pragma unroll
-        for (int k = 0; k < WG_KT; ++k) {
-            const int i = n0 + k;
+        for (int k = 0; k < WG_KH; ++k) {
+            const int i = n0 + half * WG_KH + k;
             va[k] = (a_src != nullptr && i < a.N) ? __ldg(a_src + (size_t)i * a_ld) : 0.f;
         }
 #pragma unroll
         for (int it = 0; it < WG_BIT; ++it) {
-            const int idx = t + 128 * it;
+            const int idx = t + WG_WORKERS * it;
 #pragma unroll
             for (int j = 0; j < 4; ++j) vb[it][j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (idx < items) {
@@ -148,7 +155,7 @@ __global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant_
     auto stage = [&]() {
         // A -> TMEM lane t, columns = nodes (hi at WG_AHI, lo at WG_ALO)
 #pragma unroll
-        for (int k0 = 0; k0 < WG_KT; k0 += 8) {
+        for (int k0 = 0; k0 < WG_KH; k0 += 8) {
             uint32_t h[8], l[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -157,13 +164,13 @@ __global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant_
                 h[i] = __float_as_uint(hi);
                 l[i] = __float_as_uint(lo);
             }
-            tc::tmem_st8(lane_base + WG_AHI + (uint32_t)k0, h);
-            tc::tmem_st8(lane_base + WG_ALO + (uint32_t)k0, l);
+            tc::tmem_st8(lane_base + WG_AHI + (uint32_t)(half * WG_KH + k0), h);
+            tc::tmem_st8(lane_base + WG_ALO + (uint32_t)(half * WG_KH + k0), l);
         }
         // B -> shared memory, K-major: element (n, node k) at (n/8)*SBO + (k/4)*128 + (n%8)*16 + (k%4)*4
 #pragma unroll
         for (int it = 0; it < WG_BIT; ++it) {
-            const int idx = t + 128 * it;
+            const int idx = t + WG_WORKERS * it;
             if (idx < items) {
                 const int kg = idx / qb, q = idx - kg * qb;
                 const int n = q * 4;
@@ -179,77 +186,97 @@ __global__ void __launch_bounds__(128) fused_wgrad_kernel(const __grid_constant_
 
     uint32_t parity = 0, acc = 0;
     int tile = (int)blockIdx.x - cv.cta0;
-    if (tile < ntiles) fetch(tile);
-    for (; tile < ntiles; tile += cv.nctas) {
-        if (acc) {                       // the previous tile's MMAs must have read the operands before they are overwritten
-            tc::mbar_wait(&bar, parity);
-            parity ^= 1;
-            tc::fence_after_sync();
-        }
-        stage();
-        tc::fence_async_smem();
-        tc::fence_before_sync();
-        __syncthreads();
-        tc::fence_after_sync();
-        if (t == 0) {
+    if (warp == WG_WORKERS / 32) {
+        // ---- the MMA warp: an issuing thread is held for the ~90 cycles each MMA occupies the tensor pipe; the staging
+        // warps must not be (they fetch the next tile's rows meanwhile)
+        for (; tile < ntiles; tile += cv.nctas) {
+            wg_sync();                                         // operands of this tile staged
+            if ((t & 31) == 0) {
+                tc::fence_after_sync();
 #pragma unroll 1
-            for (int ks = 0; ks < WG_KT / 8; ++ks) {
-                const uint64_t dbh = tc::make_desc(tc::smem_u32(b_hi) + (uint32_t)ks * 256, 128, WG_SBO);
-                const uint64_t dbl = tc::make_desc(tc::smem_u32(b_lo) + (uint32_t)ks * 256, 128, WG_SBO);
-                const uint32_t ah = tmem + WG_AHI + (uint32_t)ks * 8, al = tmem + WG_ALO + (uint32_t)ks * 8;
-                tc::mma_tf32_ts(tmem, ah, dbh, idesc, (acc | ks) ? 1u : 0u);
-                tc::mma_tf32_ts(tmem, al, dbh, idesc, 1);
-                tc::mma_tf32_ts(tmem, ah, dbl, idesc, 1);
+                for (int ks = 0; ks < WG_KT / 8; ++ks) {
+                    const uint64_t dbh = tc::make_desc(tc::smem_u32(b_hi) + (uint32_t)ks * 256, 128, WG_SBO);
+                    const uint64_t dbl = tc::make_desc(tc::smem_u32(b_lo) + (uint32_t)ks * 256, 128, WG_SBO);
+                    const uint32_t ah = tmem + WG_AHI + (uint32_t)ks * 8, al = tmem + WG_ALO + (uint32_t)ks * 8;
+                    tc::mma_tf32_ts(tmem, ah, dbh, idesc, (acc | ks) ? 1u : 0u);
+                    tc::mma_tf32_ts(tmem, al, dbh, idesc, 1);
+                    tc::mma_tf32_ts(tmem, ah, dbl, idesc, 1);
+                }
+                tc::commit(&bar);
             }
-            tc::commit(&bar);
+            __syncwarp();
+            acc = 1;
         }
-        acc = 1;
-        if (tile + cv.nctas < ntiles) fetch(tile + cv.nctas);     // next tile's rows fly while the tensor core works
-    }
-    if (acc) {
-        tc::mbar_wait(&bar, parity);
-        tc::fence_after_sync();
-        // flush: thread t owns accumulator row t.  Pack offsets (fused.cuh): W1 | b1 | W2 | W3 | b3
-        // row roles: 0 = dU row of part 0, 1 = dU row of part 1, 2 = g row, 3 = nothing
-        int role = 3, r = 0;
-        if (t < DC0 + 2) { role = 0; r = t; }
-        else if (two && t >= RA1 && t < RA1 + DC1 + 2) { role = 1; r = t - RA1; }
-        else if (t >= RG && t < RG + FC && t - RG < cv.gvalid) { role = 2; r = t - RG; }
-        const int o1a = (DC0 + 2) * DC0, o2a = o1a + DC0 + 4, o3a = o2a + FC * (DC0 + 4), o4a = o3a + FC * DC0;
-        const int o1b = (DC1 + 2) * DC1, o2b = o1b + DC1 + 4, o3b = o2b + FC * (DC1 + 4), o4b = o3b + FC * DC1;
-        float* gwa = cv.p[0].gw;
-        float* gwb = two ? cv.p[1].gw : nullptr;
-        const int c_one = q_one * 4, c_z0 = q_z0 * 4, c_x1 = q_x1 * 4, c_z1 = q_z1 * 4, c_end = qb * 4;
-        for (int c0 = 0; c0 < c_end; c0 += 8) {
-            float v[8];
-            tc::tmem_ld8(lane_base + (uint32_t)c0, v);
+    } else {
+        if (tile < ntiles) fetch(tile);
+        for (; tile < ntiles; tile += cv.nctas) {
+            if (acc) {                   // the previous tile's MMAs must have read the operands before they are overwritten
+                tc::mbar_wait(&bar, parity);
+                parity ^= 1;
+                tc::fence_after_sync();
+            }
+            stage();
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            wg_sync();
+            acc = 1;
+            if (tile + cv.nctas < ntiles) fetch(tile + cv.nctas);     // next tile's rows fly while the tensor core works
+        }
+        if (acc) {
+            tc::mbar_wait(&bar, parity);
+            tc::fence_after_sync();
+            // flush.  Accumulator row t (thread t's TMEM lane) -> shared memory, then warps walk the rows with their lanes
+            // along the columns so that one reduction instruction touches 4 sectors instead of 32 (the L2 atomic units
+            // see 8x fewer transactions).  Pack offsets (fused.cuh): W1 | b1 | W2 | W3 | b3
+            const int c_one = q_one * 4, c_z0 = q_z0 * 4, c_x1 = q_x1 * 4, c_z1 = q_z1 * 4, c_end = qb * 4;
+            float* ds = reinterpret_cast<float*>(smem);                     // [128][c_end + 1], the operand tiles are dead
+            const int ldd = c_end + 1;
+            for (int c0 = 8 * half; c0 < c_end; c0 += 16) {                 // the two warps of a lane quarter alternate column blocks
+                float v[8];
+                tc::tmem_ld8(lane_base + (uint32_t)c0, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int col = c0 + i;
-                if (col >= c_end || role == 3) continue;
-                if (col < c_one) {                                   // x_0
-                    if (role == 0) atomicAdd(gwa + r * DC0 + col, v[i]);
-                    else if (role == 2) atomicAdd(gwa + o3a + r * DC0 + col, v[i]);
-                } else if (col == c_one) {                           // ones
-                    if (role == 0) atomicAdd(gwa + o1a + r, v[i]);
-                    else if (role == 1) atomicAdd(gwb + o1b + r, v[i]);
-                    else {
-                        atomicAdd(gwa + o4a + r, v[i]);
-                        if (two) atomicAdd(gwb + o4b + r, v[i]);
+                for (int i = 0; i < 8; ++i)
+                    if (c0 + i < c_end) ds[tr * ldd + c0 + i] = v[i];
+            }
+            wg_sync_workers();
+            const int o1a = (DC0 + 2) * DC0, o2a = o1a + DC0 + 4, o3a = o2a + FC * (DC0 + 4), o4a = o3a + FC * DC0;
+            const int o1b = (DC1 + 2) * DC1, o2b = o1b + DC1 + 4, o3b = o2b + FC * (DC1 + 4), o4b = o3b + FC * DC1;
+            float* gwa = cv.p[0].gw;
+            float* gwb = two ? cv.p[1].gw : nullptr;
+            const int lane = t & 31;
+            for (int row = warp; row < RG + FC; row += WG_WORKERS / 32) {
+                // row roles: 0 = dU row of part 0, 1 = dU row of part 1, 2 = g row, 3 = nothing
+                int role = 3, r = 0;
+                if (row < DC0 + 2) { role = 0; r = row; }
+                else if (two && row >= RA1 && row < RA1 + DC1 + 2) { role = 1; r = row - RA1; }
+                else if (row >= RG && row - RG < cv.gvalid) { role = 2; r = row - RG; }
+                if (role == 3) continue;
+                for (int col = lane; col < c_end; col += 32) {
+                    const float v = ds[row * ldd + col];
+                    if (col < c_one) {                                   // x_0
+                        if (role == 0) atomicAdd(gwa + r * DC0 + col, v);
+                        else if (role == 2) atomicAdd(gwa + o3a + r * DC0 + col, v);
+                    } else if (col == c_one) {                           // ones
+                        if (role == 0) atomicAdd(gwa + o1a + r, v);
+                        else if (role == 1) atomicAdd(gwb + o1b + r, v);
+                        else {
+                            atomicAdd(gwa + o4a + r, v);
+                            if (two) atomicAdd(gwb + o4b + r, v);
+                        }
+                    } else if (col >= c_z0 && col < c_x1) {              // Z_0
+                        if (role == 2) atomicAdd(gwa + o2a + r * (DC0 + 4) + (col - c_z0), v);
+                    } else if (col >= c_x1 && col < c_z1) {              // x_1
+                        if (role == 1) atomicAdd(gwb + r * DC1 + (col - c_x1), v);
+                        else if (role == 2) atomicAdd(gwb + o3b + r * DC1 + (col - c_x1), v);
+                    } else if (col >= c_z1) {                            // Z_1
+                        if (role == 2) atomicAdd(gwb + o2b + r * (DC1 + 4) + (col - c_z1), v);
                     }
-                } else if (col >= c_z0 && col < c_x1) {              // Z_0
-                    if (role == 2) atomicAdd(gwa + o2a + r * (DC0 + 4) + (col - c_z0), v[i]);
-                } else if (col >= c_x1 && col < c_z1) {              // x_1
-                    if (role == 1) atomicAdd(gwb + r * DC1 + (col - c_x1), v[i]);
-                    else if (role == 2) atomicAdd(gwb + o3b + r * DC1 + (col - c_x1), v[i]);
-                } else if (col >= c_z1) {                            // Z_1
-                    if (role == 2) atomicAdd(gwb + o2b + r * (DC1 + 4) + (col - c_z1), v[i]);
                 }
             }
         }
     }
     tc::fence_before_sync();
-    __syncthreads();
+    wg_sync();
     if (warp == 0) tc::tmem_dealloc(tmem, WG_TMEM_COLS);
 }
 
@@ -341,13 +368,14 @@ QMP_API int qmp_fused_wgrad(int N, const float* xa, int lda, int DA, int GA, con
         a.c[k].nctas = n;
         cta += n;
     }
-    const size_t smem = (size_t)2 * (nbmax / 8) * WG_SBO;
+    size_t smem = (size_t)2 * (nbmax / 8) * WG_SBO;
+    if (smem < (size_t)128 * (nbmax + 1) * sizeof(float)) smem = (size_t)128 * (nbmax + 1) * sizeof(float);   // flush tile
     static size_t smem_set = 0;
     if (smem > smem_set) {
         QMP_CUDA(cudaFuncSetAttribute(fused_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_set = smem;
     }
-    fused_wgrad_kernel<<<cta, 128, smem, (cudaStream_t)stream>>>(a);
+    fused_wgrad_kernel<<<cta, WG_THREADS, smem, (cudaStream_t)stream>>>(a);
     QMP_LAUNCH_CHECK("fused_wgrad_kernel");
     return 0;
 }
