@@ -160,7 +160,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 def cell_roofline(model, csr, dev, iters=20):
-    """Time the dominant kernel of the step -- the fused decoder-cell forward (qmp_fused_fwd_tc: 8 TransformerConvs'
+    """Time the roofline kernel of the step -- the decoder-cell forward (qmp_fused_cell_fwd: 8 TransformerConvs'
     message passing over the CSR + their gate contractions on tcgen05 + the LSTM gate epilogue, ONE launch per
     forecast step) -- alone with CUDA events on the launching stream, flushing L2 between launches.
     Algorithmic bytes per launch: DESIGN.md section 5 (inputs X, H, C + CSR + edge attributes; outputs O, H', C',
@@ -170,8 +170,8 @@ def cell_roofline(model, csr, dev, iters=20):
     cell = model.decoder.rnns[0]
     F_in = cell.in_channels
     with torch.no_grad():
-        wa = fused.tc_image(fused.pack_fused(cell._convs("x", 0), fused.cap_of(F_in, True)), fused.cap_of(F_in, True))
-        wb = fused.tc_image(fused.pack_fused(cell._convs("h", 0), C), C)
+        pa, pb = fused.pack_fused(cell._convs("x", 0), fused.cap_of(F_in, True)), fused.pack_fused(cell._convs("h", 0), C)
+        img = fused.cell_image(pa, pb)
         prm = cell._gate_params(-1, model.decoder.norm_h, model.decoder.norm_c, model.decoder.norm_o).contiguous()
     f32 = dict(dtype=torch.float32, device=dev)
     X, Hs, Cs, cc = torch.randn(N, F_in, **f32), torch.randn(N, C, **f32), torch.randn(N, C, **f32), torch.randn(N, **f32)
@@ -185,9 +185,8 @@ def cell_roofline(model, csr, dev, iters=20):
         flush.zero_()
         if k >= 3:
             ev[k - 3][0].record()
-        _lib.call("qmp_fused_fwd_tc", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, X, F_in, F_in, 4, wa, Hs, C, C, 4, 1, wb,
-                  1, 0, C, None, 8 * C, Cs, prm, 1, 1, 1, 1e-5, gates, Craw, O, Hn, Cn, head, fused.HEADW, cc, logit, ms, li,
-                  0.0, 0)
+        _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, X, F_in, Hs, C, img, Cs, prm, 1, 1, 1, 1e-5,
+                  gates, Craw, O, Hn, Cn, head, fused.HEADW, cc, logit, ms, li, 0.0, 0)
         if k >= 3:
             ev[k - 3][1].record()
     torch.cuda.synchronize()
@@ -302,7 +301,7 @@ def run_gpu(args):
                 "e2e": {"value": e2e, "unit": "graph-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
                 "clocks": clocks.summary(),
-                "roofline": {"bound": "hbm", "kernel": "fused_fwd_tc_kernel<4,32> (decoder cell forward: 8 convs' message "
+                "roofline": {"bound": "hbm", "kernel": "fused_cell_fwd_kernel (decoder cell forward: 8 convs' message "
                                                          "passing + tcgen05 gate contractions + LSTM epilogue, one launch)",
                              "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                              "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes": k_bytes,

@@ -11,7 +11,7 @@ if [ $rc -eq 0 ]; then
       python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
   echo "ncu launches rc=$?"; tail -2 gpurun_out/ncu_launch.log
   python scripts/kernel_times.py 2 3 > gpurun_out/plain2.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:fused_fwd_tc_kernel -s 36 -c 1 -o gpurun_out/prof_fwd_tc \
+  ncu --set full --clock-control none --import-source on -k regex:fused_cell_fwd_kernel -s 4 -c 1 -o gpurun_out/prof_cell \
       python scripts/kernel_times.py 2 3 > gpurun_out/ncu_full.log 2>&1
   echo "ncu full rc=$?"
 fi
