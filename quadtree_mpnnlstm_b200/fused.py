@@ -84,6 +84,59 @@ def tc_image(w, DC, kind=0):
     return img
 
 
+class _Holder:
+    """Gradient accumulator of a weight pack shared by the FusedGroupFn calls of one forward pass."""
+    __slots__ = ("acc", "handed")
+
+    def __init__(self, like):
+        self.acc = torch.zeros_like(like)
+        self.handed = False
+
+
+class _GradAccum(torch.autograd.Function):
+    """Identity on a pack that many FusedGroupFn calls of one forward pass consume (one per timestep).  The consumers
+    accumulate their gradients of the pack IN PLACE in ``holder.acc`` (the weight-gradient and gate-backward kernels add
+    with reductions); only the first consumer to run in the backward pass hands ``acc`` to autograd, the others return
+    None.  Autograd runs this node once, after all of them, with the complete sum: no per-timestep zero fill and no
+    per-timestep gradient-accumulation add (11 small launches per decoder frame before)."""
+
+    @staticmethod
+    def forward(ctx, pack, holder):
+        ctx.holder = holder
+        return pack.clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        h = ctx.holder
+        out = grad.clone()
+        h.acc.zero_()                 # ready for another backward pass over the same graph
+        h.handed = False
+        return out, None
+
+
+ACC_HITS = 0        # consumers that accumulated into a shared holder (tests check the path is taken)
+
+
+def shared_pack(pack):
+    """``pack`` routed through _GradAccum when it needs a gradient (training), unchanged otherwise."""
+    if not (torch.is_grad_enabled() and pack.requires_grad):
+        return pack
+    holder = _Holder(pack)
+    out = _GradAccum.apply(pack, holder)
+    out._qmp_acc = holder
+    return out
+
+
+def hand_over(holder, grad):
+    """What a consumer returns to autograd for a pack: the accumulator once, None afterwards."""
+    if holder is None:
+        return grad
+    if holder.handed:
+        return None
+    holder.handed = True
+    return holder.acc
+
+
 _cell_cache = {}
 
 
@@ -153,6 +206,8 @@ class FusedGroupFn(torch.autograd.Function):
                       mode, int(relu_out), C, out, NC * C, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps),
                       gates, Craw, O, H, Cn, head, HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
         ctx.save_for_backward(xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out if relu_out else None)
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero-filled tensors
+        ctx.holders = tuple(getattr(t, "_qmp_acc", None) if t is not None else None for t in (wa, wb, prm))
         ctx.csr, ctx.cfg = csr, cfg
         ctx.concat_shape = tuple(concat.shape) if concat is not None else None
         if mode == 1:

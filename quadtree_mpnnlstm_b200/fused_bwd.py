@@ -60,8 +60,13 @@ def _weight_grads(gw, DC, D, G, x, ldx, shared, Zs, dUs, ldz, dP, lddp, dp_off, 
 
 
 def fused_group_backward(ctx, *grads):
-    from .fused import HEADW, cap_of
+    from .fused import HEADW, cap_of, hand_over
+    from . import fused as _fz
+    if all(g is None for g in grads):
+        return (None,) * 9
     xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out_relu = ctx.saved_tensors
+    ha, hb, hp = ctx.holders
+    _fz.ACC_HITS += sum(h is not None for h in (ha, hb, hp))
     csr = ctx.csr
     (DA, GA, DB, GB, sharedB, mode, relu_out, C, norm_h, norm_c, norm_o, want_head, eps, drop_p, seed) = ctx.cfg
     N = xb.shape[0]
@@ -76,7 +81,7 @@ def fused_group_backward(ctx, *grads):
         dO, dH, dC, dHead = (c_(g) for g in grads)
         dP = torch.empty(N, 4 * FC, dtype=_f32, device=dev)
         dCprev = torch.empty(N, FC, dtype=_f32, device=dev) if (Cp is not None and ctx.needs_input_grad[4]) else None
-        dparams = torch.zeros(13, FC, dtype=_f32, device=dev)
+        dparams = hp.acc if hp is not None else torch.zeros(13, FC, dtype=_f32, device=dev)
         _lib.call("qmp_lstm_gates_bwd", N, FC, gates, Craw, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps), dH, dC,
                   dO, dHead, HEADW, dP, 4 * FC, dCprev, dparams)
         if dHead is not None and ctx.concat_shape is not None and ctx.needs_input_grad[6]:
@@ -120,8 +125,8 @@ def fused_group_backward(ctx, *grads):
         _lib.call("qmp_fused_bwd_source_tc" if tcb else "qmp_fused_bwd_source", N, csr.out_ptr, csr.out_dst, csr.out_kin, xa, lda, DA, GA, pa, xb, ldb, DB, GB,
                   int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, dxa, dxb, float(drop_p), int(seed))
 
-    gwa = torch.zeros_like(wa) if GA else None
-    gwb = torch.zeros_like(wb)
+    gwa = (ha.acc if ha is not None else torch.zeros_like(wa)) if GA else None
+    gwb = hb.acc if hb is not None else torch.zeros_like(wb)
     if _f.TC_WGRAD:
         _lib.call("qmp_fused_wgrad", N, xa, lda, DA, GA, xb, ldb, DB, GB, int(sharedB), mode, C, dP, lddp, ZsA, dUsA, ZsB,
                   dUsB, gwa, gwb)
@@ -139,4 +144,5 @@ def fused_group_backward(ctx, *grads):
         if GA:
             _weight_grads(gwa, DAC, DA, GA, xa, lda, True, ZsA, dUsA, GA * (DAC + 4), dP, lddp, 0, C, C, N)
         _weight_grads(gwb, DBC, DB, GB, xb, ldb, sharedB, ZsB, dUsB, GB * (DBC + 4), dP, lddp, GA * C, C, C, N)
-    return dxa, gwa, dxb, gwb, dCprev, dparams, dconcat, None, None
+    return (dxa, hand_over(ha, gwa) if GA else None, dxb, hand_over(hb, gwb), dCprev,
+            hand_over(hp, dparams) if dparams is not None else None, dconcat, None, None)

@@ -135,8 +135,8 @@ class Decoder(torch.nn.Module):
             sd = (lambda: next_seed()) if p > 0 else (lambda: 0)
             if _fused.ENABLED and self.hidden_size == _fused.FC and head.shape[1] == _fused.HEADW:
                 # two fused launches (csrc/fused_fwd.inl): fc_out1 on the 36-wide padded head rows, relu; fc_out2 -> 1
-                w1 = self._cached("ffc1", epoch, lambda: _fused.pack_fused([self.fc_out1], _fused.HEADW))
-                w2 = self._cached("ffc2", epoch, lambda: _fused.pack_fused([self.fc_out2], _fused.FC))
+                w1 = self._cached("ffc1", epoch, lambda: _fused.shared_pack(_fused.pack_fused([self.fc_out1], _fused.HEADW)))
+                w2 = self._cached("ffc2", epoch, lambda: _fused.shared_pack(_fused.pack_fused([self.fc_out2], _fused.FC)))
                 tail = (False, False, False, False, 1e-5, float(p))
                 h1 = _fused.FusedGroupFn.apply(None, None, head, w1, None, None, None, csr,
                                                (0, 0, _fused.HEADW, 1, True, 0, True, _fused.FC) + tail + (sd(),))

@@ -79,7 +79,10 @@ def test_ice_like_pixelwise_transformer(be, path, monkeypatch):
     mask = ((rr - H / 2) ** 2 / (H / 2.2) ** 2 + (cc - W / 2) ** 2 / (W / 2.5) ** 2) > 1
     kw = dict(hidden_size=32, dropout=0.0, thresh=-np.inf, input_timesteps=4, input_features=8, output_timesteps=6,
               n_layers=1, n_conv_layers=3, convolution_type="TransformerConv", transform_func=dist_from_05)
+    hits = FZ.ACC_HITS
     _run_pair(be, kw, x, y, cl, mask)
+    if path != "modular":       # weight / gate-parameter gradients accumulate in place across the timesteps (fused._GradAccum)
+        assert FZ.ACC_HITS > hits, "the shared gradient accumulators must be the path that runs"
 
 
 def test_mnist_like_dynamic_quadtree_cheb(be):
