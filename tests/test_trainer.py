@@ -1,0 +1,123 @@
+"""Trainer: NextFramePredictorS2S + DeviceWindowDataset against the UNMODIFIED reference trainer
+(model/mpnnlstm.py, build container only) on the CPU emulation, and eager vs CUDA-graph steps on the B200."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import moving_blob
+
+
+def _cube(T, H, W, c, seed=3):
+    rng = np.random.default_rng(seed)
+    x = moving_blob(rng, T, H, W)
+    if c > 1:
+        x = np.concatenate([x, rng.random((T, H, W, c - 1)).astype(np.float32) * 0.5], -1)
+    return x.astype(np.float32)
+
+
+class _RefDataset(torch.utils.data.Dataset):
+    """What ice_dataset.py serves: materialised windows + int64-ns launch dates."""
+
+    def __init__(self, cube, t_in, t_out, times, idx):
+        self.x = [cube[a:a + t_in] for a in idx]
+        self.y = [cube[a + t_in:a + t_in + t_out][..., :1] for a in idx]
+        self.d = [times[a + t_in] for a in idx]
+        self.image_shape = cube.shape[1:3]
+
+    def __len__(self):
+        return len(self.x)
+
+    def __getitem__(self, i):
+        return self.x[i], self.y[i], self.d[i]
+
+
+def test_trainer_matches_reference_trainer(be, tmp_path, monkeypatch):
+    from oracle import ref_loader
+    if be.name != "cpu" or not ref_loader.reference_available():
+        pytest.skip("runs against the unmodified reference trainer on the CPU emulation (build container only)")
+    import importlib
+    ref_loader.load_reference()
+    R = importlib.import_module("model.mpnnlstm")
+    import quadtree_mpnnlstm_b200 as q
+    monkeypatch.chdir(tmp_path)                              # both trainers write runs/ (TensorBoard)
+    T_in, T_out, H, W, c = 3, 3, 16, 20, 2
+    cube = _cube(14, H, W, c)
+    times = (np.datetime64("2015-03-01").astype("datetime64[ns]").astype("int64") + np.arange(14, dtype=np.int64) * 86_400_000_000_000)
+    mask = np.zeros((H, W), bool)
+    mask[:3, :5] = True
+    mask[10:, 15:] = True
+    clim = torch.from_numpy(np.random.default_rng(5).random((1, 366, H, W)).astype(np.float32))
+    kw = dict(hidden_size=8, dropout=0.0, n_layers=1, n_conv_layers=1)
+    args = dict(thresh=0.1, experiment_name="t", input_features=c, input_timesteps=T_in, output_timesteps=T_out)
+    torch.manual_seed(4)
+    ref = R.NextFramePredictorS2S(device=torch.device("cpu"), model_kwargs=kw, **args)
+    mine = q.NextFramePredictorS2S(device=be.device, model_kwargs=kw, **args)
+    mine.model.load_state_dict(ref.model.state_dict())
+    tr_idx, te_idx = [0, 2, 4], [6, 7]
+    mk = lambda idx: torch.utils.data.DataLoader(_RefDataset(cube, T_in, T_out, times, idx), batch_size=1, shuffle=False)
+    ref.model.train()
+    ref.train(mk(tr_idx), mk(te_idx), clim, n_epochs=2, lr=0.01, lr_decay=0.5, mask=mask, truncated_backprop=0)
+    dcube = be.dev(torch.from_numpy(cube))
+    ds = lambda idx: q.DeviceWindowDataset(dcube, T_in, T_out, times=times, indices=idx)
+    mine.model.train()
+    mine.train(ds(tr_idx), ds(te_idx), be.dev(clim), n_epochs=2, lr=0.01, lr_decay=0.5, mask=mask, truncated_backprop=0)
+    assert np.allclose(mine.train_loss, ref.train_loss, rtol=2e-3), (mine.train_loss, ref.train_loss)
+    assert np.allclose(mine.test_loss, ref.test_loss, rtol=2e-3), (mine.test_loss, ref.test_loss)
+    assert list(mine.loss.columns) == list(ref.loss.columns)
+    assert mine.scheduler.get_last_lr() == ref.scheduler.get_last_lr()
+    ref.model.eval(); mine.model.eval()
+    pa = ref.predict(mk(te_idx), clim, mask=mask)
+    pb = mine.predict(ds(te_idx), be.dev(clim), mask=mask)
+    assert pa.shape == pb.shape == (2, T_out, H, W, 1)
+    assert np.array_equal(np.isnan(pa), np.isnan(pb))
+    assert np.nanmax(np.abs(pa - pb)) < 2e-3
+    mine.save(str(tmp_path))
+    again = q.NextFramePredictorS2S(device=be.device, model_kwargs=kw, **args)
+    again.load(str(tmp_path))
+    assert all(torch.equal(a, b) for a, b in zip(again.model.state_dict().values(), mine.model.state_dict().values()))
+    with pytest.raises(NotImplementedError):
+        mine.train(ds(tr_idx), ds(te_idx), be.dev(clim), n_epochs=1, mask=mask, truncated_backprop=2)
+
+
+def test_device_window_dataset_layout():
+    import quadtree_mpnnlstm_b200 as q
+    cube = torch.arange(10 * 2 * 3 * 2, dtype=torch.float32).reshape(10, 2, 3, 2)
+    ds = q.DeviceWindowDataset(cube, 3, 2, y_channels=(0,))
+    assert len(ds) == 6 and ds.dataset.image_shape == (2, 3)
+    x, y, d = ds.window(4)
+    assert x.shape == (1, 3, 2, 3, 2) and y.shape == (1, 2, 2, 3, 1) and d.dtype == torch.int64 and d.shape == (1,)
+    assert torch.equal(x[0], cube[4:7]) and torch.equal(y[0], cube[7:9][..., :1])
+    assert int(d) == 7 * 86_400_000_000_000
+    assert x.untyped_storage().data_ptr() == cube.untyped_storage().data_ptr(), "windows are views of the cube"
+    assert [int(w[2]) // 86_400_000_000_000 for w in ds] == [3, 4, 5, 6, 7, 8]
+
+
+@pytest.mark.gpu
+def test_trainer_cuda_graph_step_matches_eager(tmp_path, monkeypatch):
+    """Pixel-wise mesh (the ice_exp default): the captured optimizer step and the eager one give the same losses, and
+    the StepLR schedule reaches the captured Adam through its device-resident learning rate."""
+    import quadtree_mpnnlstm_b200 as q
+    monkeypatch.chdir(tmp_path)
+    dev = torch.device("cuda")
+    T_in, T_out, H, W, c = 3, 4, 24, 28, 2
+    cube = torch.from_numpy(_cube(20, H, W, c)).to(dev)
+    rr, cc = np.mgrid[0:H, 0:W]
+    mask = ((rr - H / 2) ** 2 / (H / 2.2) ** 2 + (cc - W / 2) ** 2 / (W / 2.5) ** 2) > 1
+    clim = torch.rand(1, 366, H, W, device=dev)
+    kw = dict(hidden_size=32, dropout=0.0, n_layers=1, n_conv_layers=1, convolution_type="TransformerConv")
+    args = dict(thresh=-np.inf, experiment_name="g", input_features=c, input_timesteps=T_in, output_timesteps=T_out, device=dev,
+                model_kwargs=kw)
+    torch.manual_seed(2)
+    a = q.NextFramePredictorS2S(**args)
+    b = q.NextFramePredictorS2S(use_cuda_graph=True, **args)
+    b.model.load_state_dict(a.model.state_dict())
+    ds = lambda idx: q.DeviceWindowDataset(cube, T_in, T_out, indices=idx)
+    for m in (a, b):
+        m.model.train()
+        m.train(ds(list(range(8))), ds([9, 10]), clim, n_epochs=4, lr=0.01, lr_decay=0.5, mask=mask, truncated_backprop=0)
+    assert b._graph_step is not None and b._graph_step.graph is not None, "the CUDA-graph step must be the path that runs"
+    assert np.allclose(a.train_loss, b.train_loss, rtol=5e-3), (a.train_loss, b.train_loss)
+    assert np.allclose(a.test_loss, b.test_loss, rtol=5e-3), (a.test_loss, b.test_loss)
+    assert a.train_loss[-1] < a.train_loss[0]
