@@ -30,7 +30,7 @@ def load_reference():
         if p not in sys.path:
             sys.path.insert(0, p)
     cached = sys.modules.get("model")
-    if cached is not None and not getattr(cached, "__file__", "").startswith(REFERENCE_ROOT) \
+    if cached is not None and not (getattr(cached, "__file__", None) or "").startswith(REFERENCE_ROOT) \
             and REFERENCE_ROOT not in "".join(getattr(cached, "__path__", [])):
         raise RuntimeError("a different top-level 'model' package is already imported")
     ns = types.SimpleNamespace()

@@ -17,6 +17,7 @@ ENABLED = True      # tests flip this to cross-check the fused kernels against t
 TC_WGRAD = True     # weight gradients: one tcgen05 launch per group (False: ten FFMA reductions, the cross-check)
 TC_BWD = True       # backward (target / source side) on tcgen05 (csrc/fused_bwd_tc.inl); False: fp32-FFMA kernels
 TC_FWD = True       # forward on tcgen05 (csrc/fused_fwd_tc.inl); False: the fp32-FFMA kernel (csrc/fused_fwd.inl)
+SCALAR_HEAD = True  # decoder head's fc_out2 (hidden -> 1 channel): scalar query / key / value kernels (csrc/tconv1.cu)
 CELL_FWD = True     # decoder cell (4 X convs + 4 H convs, gate mode): the persistent gates-batched kernel (csrc/fused_cell_fwd.cu)
 _f32 = torch.float32
 
@@ -218,3 +219,44 @@ class FusedGroupFn(torch.autograd.Function):
     def backward(ctx, *grads):
         from .fused_bwd import fused_group_backward
         return fused_group_backward(ctx, *grads)
+
+
+# ---- one-output-channel TransformerConv (the decoder's fc_out2) ---------------------------------------------------------
+def pack_tconv1(conv):
+    """P [136] = Wq | Wk | Wv | Ws (32 each) | bq bk bv bs | we0 we1 | 0 0 from a PyG-named TransformerConv(32 -> 1)
+    (layout: csrc/tconv1.cu).  No 1/sqrt(C) factor: C = 1."""
+    assert conv.out_channels == 1 and conv.in_channels == FC
+    v = lambda t: t.reshape(-1)
+    return torch.cat([v(conv.lin_query.weight), v(conv.lin_key.weight), v(conv.lin_value.weight), v(conv.lin_skip.weight),
+                      v(conv.lin_query.bias), v(conv.lin_key.bias), v(conv.lin_value.bias), v(conv.lin_skip.bias),
+                      v(conv.lin_edge.weight), conv.lin_edge.weight.new_zeros(2)]).contiguous()
+
+
+class ScalarTConvFn(torch.autograd.Function):
+    """out [N, 1] = TransformerConv(32 -> 1)(x) on the scalar-record kernels (qmp_tconv1_fwd / qmp_tconv1_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, P, csr, drop_p, seed):
+        N = x.shape[0]
+        x = x.contiguous()
+        P = P.contiguous()
+        s4 = torch.empty(N, 4, dtype=_f32, device=x.device)
+        out = torch.empty(N, 1, dtype=_f32, device=x.device)
+        _lib.call("qmp_tconv1_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, x, x.shape[1], P, s4, out, float(drop_p), int(seed))
+        ctx.save_for_backward(x, P, s4)
+        ctx.csr, ctx.drop_p, ctx.seed = csr, float(drop_p), int(seed)
+        ctx.holder = getattr(P, "_qmp_acc", None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        global ACC_HITS
+        x, P, s4 = ctx.saved_tensors
+        N, csr, h = x.shape[0], ctx.csr, ctx.holder
+        ACC_HITS += h is not None
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gP = (h.acc if h is not None else torch.zeros_like(P)) if ctx.needs_input_grad[1] else None
+        ds4 = torch.empty(N, 4, dtype=_f32, device=x.device)
+        _lib.call("qmp_tconv1_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, x, x.shape[1], P, s4, g.contiguous(), ds4, dx,
+                  x.shape[1], gP, ctx.drop_p, ctx.seed)
+        return dx, (hand_over(h, gP) if gP is not None else None), None, None, None

@@ -140,6 +140,10 @@ class Decoder(torch.nn.Module):
                 tail = (False, False, False, False, 1e-5, float(p))
                 h1 = _fused.FusedGroupFn.apply(None, None, head, w1, None, None, None, csr,
                                                (0, 0, _fused.HEADW, 1, True, 0, True, _fused.FC) + tail + (sd(),))
+                if _fused.SCALAR_HEAD and self.fc_out2.out_channels == 1:
+                    # one output channel: scalar query / key / value records instead of 32-wide rows (csrc/tconv1.cu)
+                    P2 = self._cached("ftc1", epoch, lambda: _fused.shared_pack(_fused.pack_tconv1(self.fc_out2)))
+                    return _fused.ScalarTConvFn.apply(h1, P2, csr, float(p), sd())
                 return _fused.FusedGroupFn.apply(None, None, h1, w2, None, None, None, csr,
                                                  (0, 0, _fused.FC, 1, True, 0, False, 1) + tail + (sd(),))
             pk1 = self._cached("fc1", epoch, lambda: pack_tconv([self.fc_out1]))

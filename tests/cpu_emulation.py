@@ -629,6 +629,49 @@ def qmp_fused_cell_fwd(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, Cprev, pa
                   norm_c, norm_o, eps, gates, Craw, Oout, Hout, Cout, head_in, ldh, concat, logit, mstat, linv, drop_p, seed)
 
 
+def _tconv1_common(N, in_ptr, in_src, ea, x, ldx, P, drop_p):
+    assert drop_p == 0.0
+    E, ti, sj = _edge_lists(N, in_ptr, in_src)
+    X = rows(x, N, ldx, 32)
+    p = flat(P, 136)
+    W4, b, we = p[:128].view(4, 32), p[128:132], p[132:134]
+    S = X @ W4.T + b
+    EA = flat(ea, 2 * E).view(E, 2) if ea is not None else torch.zeros(E, 2)
+    e = EA @ we
+    s = S[ti, 0] * (S[sj, 1] + e)
+    m = torch.full((N,), -float("inf")).scatter_reduce(0, ti, s, "amax", include_self=True)
+    pe = torch.exp(s - m[ti])
+    l = torch.zeros(N).index_add(0, ti, pe)
+    al = pe / l[ti]
+    return E, ti, sj, X, W4, S, EA, e, al
+
+
+def qmp_tconv1_fwd(N, in_ptr, in_src, ea, x, ldx, P, s4, out, drop_p, seed):
+    E, ti, sj, X, W4, S, EA, e, al = _tconv1_common(N, in_ptr, in_src, ea, x, ldx, P, drop_p)
+    flat(s4, 4 * N).view(N, 4).copy_(S)
+    flat(out, N).copy_(torch.zeros(N).index_add(0, ti, al * (S[sj, 2] + e)) + S[:, 3])
+
+
+def qmp_tconv1_bwd(N, in_ptr, in_src, ea, x, ldx, P, s4, g, ds4, dx, lddx, gP, drop_p, seed):
+    E, ti, sj, X, W4, S, EA, e, al = _tconv1_common(N, in_ptr, in_src, ea, x, ldx, P, drop_p)
+    gv = flat(g, N)
+    key, val = S[sj, 1] + e, S[sj, 2] + e
+    dal = gv[ti] * val
+    tsum = torch.zeros(N).index_add(0, ti, al * dal)
+    dsv = al * (dal - tsum[ti])
+    dkey, dval = dsv * S[ti, 0], al * gv[ti]
+    D = torch.stack([torch.zeros(N).index_add(0, ti, dsv * key), torch.zeros(N).index_add(0, sj, dkey),
+                     torch.zeros(N).index_add(0, sj, dval), gv], dim=1)
+    flat(ds4, 4 * N).view(N, 4).copy_(D)
+    if dx is not None:
+        rows(dx, N, lddx, 32).copy_(D @ W4)
+    if gP is not None:
+        gp = flat(gP, 136)
+        gp[:128] += (D.T @ X).reshape(-1)
+        gp[128:132] += D.sum(0)
+        gp[132:134] += ((dkey + dval)[:, None] * EA).sum(0)
+
+
 def _bwd_pack_from_image(img, G, DC):
     """Backward pack (W1 | b1 | W1T | W2T | W3T) rebuilt from the forward pack stored in an emulated image."""
     if img is None:

@@ -305,3 +305,34 @@ def test_decoder_cell_kernel_matches_per_conv_kernel(N, drop_p, with_c):
         assert not torch.isnan(vb).any(), f"{k}: unwritten / NaN entries"
         err = float((va - vb).abs().max()) / max(float(va.abs().max()), 1e-6) if va.numel() else 0.0
         assert err < 2e-5, f"{k}: {err}"
+
+
+@pytest.mark.parametrize("quadtree", [True, False])
+def test_scalar_transformer_conv_matches_oracle(be, quadtree):
+    """TransformerConv(32 -> 1) (the decoder's fc_out2) on the scalar-record kernels (csrc/tconv1.cu) against the oracle's PyG
+    restatement: output, input gradient, every parameter gradient."""
+    from quadtree_mpnnlstm_b200 import convs as C, fused as FZ
+    from quadtree_mpnnlstm_b200.graph_csr import get_csr
+    from oracle import convs_ref as R
+    ei, ea, n = _graph(7, quadtree=quadtree)
+    torch.manual_seed(3)
+    ref = R.TransformerConv(32, 1, heads=1, concat=False, beta=False, dropout=0.1, edge_dim=2, bias=True, root_weight=True)
+    mod = be.dev(C.TransformerConv(32, 1, heads=1, concat=False, beta=False, dropout=0.1, edge_dim=2, bias=True, root_weight=True))
+    mod.load_state_dict(ref.state_dict())
+    ref.eval()
+    x = torch.randn(n, 32)
+    xa = x.clone().requires_grad_(True)
+    xb = be.dev(x.clone()).requires_grad_(True)
+    ya = ref(xa, ei, ea)
+    csr = get_csr(be.dev(ei), be.dev(ea), n)
+    yb = FZ.ScalarTConvFn.apply(xb, FZ.pack_tconv1(mod), csr, 0.0, 0)
+    assert yb.shape == (n, 1) and rel_err(yb, ya) < TOL
+    w = torch.randn(n, 1)
+    (ya * w).sum().backward()
+    (yb * be.dev(w)).sum().backward()
+    assert rel_err(xb.grad, xa.grad) < 1e-4
+    for (k, pa), (_, pb) in zip(ref.named_parameters(), mod.named_parameters()):
+        ga = pa.grad if pa.grad is not None else torch.zeros_like(pa)
+        gb = pb.grad if pb.grad is not None else torch.zeros_like(pb)
+        diff = float((ga - gb.cpu()).abs().max())
+        assert diff / max(float(ga.abs().max()), 1e-3) < 2e-4 or diff < 2e-5, f"grad {k}: {diff}"
