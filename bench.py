@@ -186,7 +186,7 @@ def cell_roofline(model, csr, dev, iters=20):
         if k >= 3:
             ev[k - 3][0].record()
         _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, X, F_in, Hs, C, img, Cs, prm, 1, 1, 1, 1e-5,
-                  gates, Craw, O, Hn, Cn, head, fused.HEADW, cc, logit, ms, li, 0.0, 0)
+                  gates, Craw, O, Hn, Cn, head, fused.HEADW, cc, logit, ms, li, None, 0.0, 0)
         if k >= 3:
             ev[k - 3][1].record()
     torch.cuda.synchronize()

@@ -56,9 +56,11 @@ SIGNATURES = {
     "qmp_fused_bwd_target_tc": "ippppiiippiiiipiipippppppppppfup",
     "qmp_fused_bwd_source_tc": "ippppiiippiiiipiipippppppfup",
     "qmp_fused_pack_cell": "pppp",
+    "qmp_fused_pack_cell_bwd": "pppp",
+    "qmp_fused_cell_bwd": "ipppp" "i" "p" "i" "ppp" "i" "ppp" "pppp" "pp" "fup",
     "qmp_tconv1_fwd": "ipppp" "i" "ppp" "fup",
     "qmp_tconv1_bwd": "ipppp" "i" "ppppp" "i" "p" "fup",
-    "qmp_fused_cell_fwd": "ippppipippp" "iiif" "pppppp" "i" "pppp" "fup",
+    "qmp_fused_cell_fwd": "ippppipippp" "iiif" "pppppp" "i" "ppppp" "fup",
 }
 
 
@@ -71,7 +73,7 @@ KERNELS_PER_CALL = {
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
     "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
     "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1, "qmp_fused_bwd_target_tc": 1, "qmp_fused_bwd_source_tc": 1,
-    "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1, "qmp_tconv1_fwd": 2, "qmp_tconv1_bwd": 2,
+    "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1, "qmp_tconv1_fwd": 2, "qmp_tconv1_bwd": 2, "qmp_fused_pack_cell_bwd": 1, "qmp_fused_cell_bwd": 1,
 }
 CALL_COUNTS = {}
 
@@ -109,6 +111,8 @@ def lib():
         L.qmp_fused_tc_image_bytes.argtypes = [_I, _I]
         L.qmp_fused_cell_image_bytes.restype = _L
         L.qmp_fused_cell_image_bytes.argtypes = []
+        L.qmp_fused_cell_bwd_image_bytes.restype = _L
+        L.qmp_fused_cell_bwd_image_bytes.argtypes = []
         for name, sig in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = _I
@@ -153,4 +157,4 @@ def call(name, *args):
 
 
 def exported_symbols():
-    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes"] + list(SIGNATURES)
+    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes"] + list(SIGNATURES)

@@ -60,6 +60,9 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_fused_cell_fwd": "model/model.py:394-463 GConvLSTM.forward of the decoder cell (4 X convs + 4 H convs, gates, norms, head input) -- one persistent launch, gates batched on tcgen05, edge phase 8 lanes per node",
     "qmp_fused_pack_cell": "(weight image of qmp_fused_cell_fwd: the eight convs of the decoder cell side by side)",
     "qmp_fused_cell_image_bytes": "(size of that image)",
+    "qmp_fused_cell_bwd": "autograd of qmp_fused_cell_fwd w.r.t. X and H (target and source side of every edge in one persistent launch) + rows for qmp_fused_wgrad",
+    "qmp_fused_pack_cell_bwd": "(weight image of qmp_fused_cell_bwd)",
+    "qmp_fused_cell_bwd_image_bytes": "(size of that image)",
     "qmp_tconv1_fwd": "PyG TransformerConv(hidden, 1) = the decoder's fc_out2 (model/seq2seq.py:117-121, 182-187): scalar query / key / value records",
     "qmp_tconv1_bwd": "autograd of the above (input gradient + parameter gradients)",
     "qmp_set_fused_paired": "(switch: two threads per node (paired warps) or one in the tcgen05 fused kernels)",

@@ -24,108 +24,10 @@
 
 namespace qmp {
 
-constexpr int CELL_WORKERS = 512, CELL_THREADS = CELL_WORKERS + 32;   // 16 worker warps + the warp that issues the MMAs
-constexpr int XS = 44;                        // exchange row stride in floats (conflict-free for thread-per-row 16-byte accesses)
-constexpr int XPLANE = 128 * XS;              // one plane = 128 node rows; four planes (conv / gate)
 constexpr uint32_t TM_P = 0;                  // P accumulators of the four gates, 128 columns
 constexpr uint32_t TM_R0 = 128, TM_RW = 96;   // A operand regions R_g = TM_R0 + g * TM_RW (hi 48 | lo 48); R_0 also holds [h|x] (hi 40 | lo 40)
 constexpr uint32_t TM_U = 320;                // U of the four H convs, 160 columns, aliases R_2 / R_3 (dead before they are staged)
 constexpr size_t CELL_SMEM = CellLayout::BYTES + (13 * FC + 4 * XPLANE) * sizeof(float);
-
-#ifdef QMP_CELL_TRACE
-// timeline of CTA 0 (threads 0 and 160): (tag, clock) pairs, read back by qmpx_cell_trace_dump (scripts/cell_trace.py)
-__device__ float g_cell_trace[2][2048];
-__device__ unsigned long long g_cell_cta[256][4];      // per CTA: globaltimer at entry, after the prologue, at the last tile's end, at exit
-__device__ __forceinline__ unsigned long long cell_gtime() {
-    unsigned long long v;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(v));
-    return v;
-}
-#define CELL_CTA(k) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_cell_cta[blockIdx.x][k] = cell_gtime(); } while (0)
-#define CELL_MARK(tag)                                                                       \
-    do {                                                                                     \
-        if (blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == 512)) {                   \
-            float* tr__ = g_cell_trace[threadIdx.x ? 1 : 0];                                 \
-            const int n__ = (int)tr__[0];                                                    \
-            if (n__ < 1000) {                                                                \
-                tr__[1 + 2 * n__] = (float)(tag);                                            \
-                tr__[2 + 2 * n__] = (float)((unsigned)clock64() & 0xFFFFFFu);                \
-                tr__[0] = (float)(n__ + 1);                                                  \
-            }                                                                                \
-        }                                                                                    \
-    } while (0)
-#else
-#define CELL_MARK(tag) do { } while (0)
-#define CELL_CTA(k) do { } while (0)
-#endif
-
-__device__ __forceinline__ void cell_stage8(uint32_t hi_addr, uint32_t lo_addr, const float (&v)[8]) {
-    uint32_t h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float hi, lo;
-        tc::split_tf32(v[i], hi, lo);
-        h[i] = __float_as_uint(hi);
-        l[i] = __float_as_uint(lo);
-    }
-    tc::tmem_st8(hi_addr, h);
-    tc::tmem_st8(lo_addr, l);
-}
-
-__device__ __forceinline__ void ld8(float (&v)[8], const float* p) {
-    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
-}
-
-// sum over the 8 lanes of an octet of eight values per lane; lane l of the octet ends with the total of v[l]
-__device__ __forceinline__ float octet_reduce8(const float (&v)[8], int l8) {
-    const bool b2 = l8 & 4, b1 = l8 & 2, b0 = l8 & 1;
-    float r4[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float keep = b2 ? v[i + 4] : v[i], send = b2 ? v[i] : v[i + 4];
-        r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    float r2[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float keep = b1 ? r4[i + 2] : r4[i], send = b1 ? r4[i] : r4[i + 2];
-        r2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    const float keep = b0 ? r2[1] : r2[0], send = b0 ? r2[0] : r2[1];
-    return keep + __shfl_xor_sync(0xffffffffu, send, 1);
-}
-
-__device__ __forceinline__ float quad_sum(float v) {          // over the 4 lanes that differ in bits 0, 1
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v + __shfl_xor_sync(0xffffffffu, v, 2);
-}
-__device__ __forceinline__ float octet_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v + __shfl_xor_sync(0xffffffffu, v, 4);
-}
-
-// LayerNorm over the 32 features of a node held as 4 values in each of the 8 lanes of an octet (biased variance)
-__device__ __forceinline__ void octet_layer_norm(float (&x)[4], float eps, const float4 g, const float4 b) {
-    const float mean = octet_sum((x[0] + x[1]) + (x[2] + x[3])) * (1.f / FC);
-    const float d0 = x[0] - mean, d1 = x[1] - mean, d2 = x[2] - mean, d3 = x[3] - mean;
-    const float var = octet_sum(fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)))) * (1.f / FC);
-    const float rstd = rsqrtf(var + eps);
-    x[0] = fmaf(d0 * rstd, g.x, b.x);
-    x[1] = fmaf(d1 * rstd, g.y, b.y);
-    x[2] = fmaf(d2 * rstd, g.z, b.z);
-    x[3] = fmaf(d3 * rstd, g.w, b.w);
-}
-
-__device__ __forceinline__ void cell_sync() { asm volatile("bar.sync 0, %0;" ::"n"(CELL_THREADS) : "memory"); }
-
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
 // per-thread state of the pipelined tile loop ------------------------------------------------------------------------
 struct CellOwn {                // this thread's share of the [h | x] row of its node (cg 0: h[0..15], 1: h[16..23], 2: h[24..31], 3: x)
@@ -308,7 +210,8 @@ __device__ __forceinline__ void cell_tile(const CellTiling& tl, int N, int r, in
 }
 
 __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const __grid_constant__ FusedFwdArgs a,
-                                                                         const uint8_t* __restrict__ img, const CellTiling tl) {
+                                                                         const uint8_t* __restrict__ img, const CellTiling tl,
+                                                                         float* __restrict__ usave) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[2];                 // 0: MMA groups (every commit is waited once by every thread), 1: image landed
     __shared__ uint32_t tmem_slot;
@@ -457,6 +360,10 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
             float4 u[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) u[c] = ld4(xrow + c * XPLANE + 4 * l8);
+            if (usave && valid) {               // logit projections u_c = W1_c h + b1_c of the four H convs: the backward kernel's
+#pragma unroll                                  // source-side term ds_e u_i needs them (fused_cell_bwd.cu)
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(usave + (size_t)i * 128 + 32 * c + 4 * l8) = u[c];
+            }
             float2 w01[2];
 #pragma unroll
             for (int r = 0; r < 2; ++r) w01[r] = *reinterpret_cast<const float2*>(xrow + (2 * r + cc) * XPLANE + 32);
@@ -796,11 +703,12 @@ QMP_API int qmp_fused_pack_cell(const float* packA, const float* packB, void* ou
 
 // One decoder-cell step (qmp_fused_fwd_tc with DA = 4, GA = 4, DB = 32, GB = 4, shared H input, gate mode, C = 32) from
 // the cell image built by qmp_fused_pack_cell.  Rows of xa (4 floats), xb (32 floats), head_in must be 16-byte aligned.
+// usave [N, 128] (may be NULL): receives the logit projections u of the four H convs, which qmp_fused_cell_bwd reads.
 QMP_API int qmp_fused_cell_fwd(int N, const int* in_ptr, const int* in_src, const float* ea, const float* xa, int lda,
                                const float* xb, int ldb, const void* image, const float* Cprev, const float* params,
                                int norm_h, int norm_c, int norm_o, float eps, float* gates, float* Craw, float* Oout,
                                float* Hout, float* Cout, float* head_in, int ldh, const float* concat, float* logit,
-                               float* mstat, float* linv, float drop_p, unsigned long long seed, void* stream) {
+                               float* mstat, float* linv, float* usave, float drop_p, unsigned long long seed, void* stream) {
     if (N <= 0) return 0;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     QMP_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ldb >= 32 && al16(xa) && al16(xb) && al16(image) && al16(params),
@@ -808,6 +716,7 @@ QMP_API int qmp_fused_cell_fwd(int N, const int* in_ptr, const int* in_src, cons
     QMP_REQUIRE(al16(gates) && al16(Craw) && al16(Hout) && al16(Cout) && (!Oout || al16(Oout)) && (!Cprev || al16(Cprev)) &&
                     (!head_in || (al16(head_in) && ldh % 4 == 0 && ldh > FC)),
                 "qmp_fused_cell_fwd: output rows must be 16-byte aligned");
+    QMP_REQUIRE(!usave || al16(usave), "qmp_fused_cell_fwd: usave must be 16-byte aligned");
     QMP_REQUIRE(!ea || (reinterpret_cast<uintptr_t>(ea) & 7) == 0, "qmp_fused_cell_fwd: edge attributes must be 8-byte aligned");
     FusedFwdArgs a{};
     a.N = N; a.ptr = in_ptr; a.nbr = in_src; a.ea = ea; a.xa = xa; a.lda = lda; a.DA = 4; a.GA = 4; a.xb = xb; a.ldb = ldb;
@@ -833,7 +742,8 @@ QMP_API int qmp_fused_cell_fwd(int N, const int* in_ptr, const int* in_src, cons
     tl.R = cdiv(tl.Q, 128);
     tl.T0 = (cdiv(tl.Q, tl.R) + 3) & ~3;
     tl.stagger = 128 - tl.T0 < g_cell_stagger ? (128 - tl.T0) & ~3 : g_cell_stagger;
-    fused_cell_fwd_kernel<<<cdiv(N, tl.Q), CELL_THREADS, CELL_SMEM, (cudaStream_t)stream>>>(a, reinterpret_cast<const uint8_t*>(image), tl);
+    fused_cell_fwd_kernel<<<cdiv(N, tl.Q), CELL_THREADS, CELL_SMEM, (cudaStream_t)stream>>>(a, reinterpret_cast<const uint8_t*>(image), tl,
+                                                                                          usave);
     QMP_LAUNCH_CHECK("fused_cell_fwd_kernel");
     return 0;
 }

@@ -18,6 +18,7 @@ TC_WGRAD = True     # weight gradients: one tcgen05 launch per group (False: ten
 TC_BWD = True       # backward (target / source side) on tcgen05 (csrc/fused_bwd_tc.inl); False: fp32-FFMA kernels
 TC_FWD = True       # forward on tcgen05 (csrc/fused_fwd_tc.inl); False: the fp32-FFMA kernel (csrc/fused_fwd.inl)
 SCALAR_HEAD = True  # decoder head's fc_out2 (hidden -> 1 channel): scalar query / key / value kernels (csrc/tconv1.cu)
+CELL_BWD = True     # ... and its backward: target + source side of every edge in one persistent launch (csrc/fused_cell_bwd.cu)
 CELL_FWD = True     # decoder cell (4 X convs + 4 H convs, gate mode): the persistent gates-batched kernel (csrc/fused_cell_fwd.cu)
 _f32 = torch.float32
 
@@ -155,6 +156,23 @@ def cell_image(wa, wb):
     return img
 
 
+_cellb_cache = {}
+
+
+def cell_bwd_image(wa, wb):
+    """uint8 image for qmp_fused_cell_bwd (qmp_fused_pack_cell_bwd), cached per pack pair."""
+    key = (wa.data_ptr(), wb.data_ptr(), wa._version, wb._version)
+    hit = _cellb_cache.get(key)
+    if hit is not None and hit[0] is wa and hit[1] is wb:
+        return hit[2]
+    img = torch.empty(int(_lib.lib().qmp_fused_cell_bwd_image_bytes()), dtype=torch.uint8, device=wb.device)
+    _lib.call("qmp_fused_pack_cell_bwd", wa.detach().contiguous(), wb.detach().contiguous(), img)
+    if len(_cellb_cache) > 64:
+        _cellb_cache.clear()
+    _cellb_cache[key] = (wa, wb, img)
+    return img
+
+
 def is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb):
     return (mode == 1 and GA == 4 and GB == 4 and sharedB and DA == 4 and DB == 32 and C == FC and xa is not None
             and xa.shape[1] % 4 == 0 and xb.shape[1] % 4 == 0)
@@ -191,10 +209,13 @@ class FusedGroupFn(torch.autograd.Function):
         cc = concat.contiguous().reshape(-1) if (want_head and concat is not None) else None
         prm = params.contiguous() if params is not None else None
         entry, wa_k, wb_k = "qmp_fused_fwd", wa, wb
+        usave = None
         if TC_FWD and CELL_FWD and is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb):
+            if CELL_BWD and TC_BWD and any(ctx.needs_input_grad):      # the backward kernel reads the logit projections
+                usave = torch.empty(N, 4 * FC, dtype=_f32, device=dev)
             _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, xa.shape[1], xb, xb.shape[1],
                       cell_image(wa, wb), Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps), gates, Craw, O, H, Cn, head,
-                      HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
+                      HEADW, cc, logit, mstat, linv, usave, float(drop_p), int(seed))
             entry = None
         elif TC_FWD:
             entry = "qmp_fused_fwd_tc"
@@ -206,7 +227,7 @@ class FusedGroupFn(torch.autograd.Function):
                       xb, xb.shape[1], DB, GB, int(sharedB), wb_k,
                       mode, int(relu_out), C, out, NC * C, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps),
                       gates, Craw, O, H, Cn, head, HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
-        ctx.save_for_backward(xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out if relu_out else None)
+        ctx.save_for_backward(xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out if relu_out else None, usave)
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero-filled tensors
         ctx.holders = tuple(getattr(t, "_qmp_acc", None) if t is not None else None for t in (wa, wb, prm))
         ctx.csr, ctx.cfg = csr, cfg

@@ -64,7 +64,7 @@ def fused_group_backward(ctx, *grads):
     from . import fused as _fz
     if all(g is None for g in grads):
         return (None,) * 9
-    xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out_relu = ctx.saved_tensors
+    xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out_relu, usave = ctx.saved_tensors
     ha, hb, hp = ctx.holders
     _fz.ACC_HITS += sum(h is not None for h in (ha, hb, hp))
     csr = ctx.csr
@@ -96,7 +96,9 @@ def fused_group_backward(ctx, *grads):
 
     need_dxa = GA > 0 and ctx.needs_input_grad[0]
     need_dxb = ctx.needs_input_grad[2]
-    ds = torch.empty(max(E, 1), NC, dtype=_f32, device=dev)
+    cell = (_fz.CELL_BWD and _fz.TC_BWD and usave is not None and need_dxa and need_dxb
+            and _fz.is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb))
+    ds = None if cell else torch.empty(max(E, 1), NC, dtype=_f32, device=dev)
     ZsA = dUsA = None
     if GA:
         ZsA = torch.empty(N, GA, DAC + 4, dtype=_f32, device=dev)
@@ -107,18 +109,22 @@ def fused_group_backward(ctx, *grads):
     dxb = torch.empty_like(xb) if need_dxb else None
     from . import fused as _f
     tcb = _f.TC_BWD
-    if tcb:
+    lda = xa.shape[1] if xa is not None else 0
+    ldb = xb.shape[1]
+    if cell:        # target and source side of every edge in one persistent launch (csrc/fused_cell_bwd.cu)
+        _lib.call("qmp_fused_cell_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda, xb, ldb, _f.cell_bwd_image(wa, wb),
+                  usave, dP, lddp, logit, mstat, linv, ZsA, dUsA, ZsB, dUsB, dxa, dxb, float(drop_p), int(seed))
+    elif tcb:
         pa = _f.tc_image(wa, DAC, 1) if GA else None
         pb = _f.tc_image(wb, DBC, 1)
     else:
         pa = bwd_pack(wa, DAC) if GA else None
         pb = bwd_pack(wb, DBC)
-    lda = xa.shape[1] if xa is not None else 0
-    ldb = xb.shape[1]
-    _lib.call("qmp_fused_bwd_target_tc" if tcb else "qmp_fused_bwd_target", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda, DA, GA, pa, xb, ldb, DB, GB,
-              int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, ZsA, dUsA, ZsB, dUsB, dxa, dxb, float(drop_p),
-              int(seed))
-    if need_dxa or need_dxb:
+    if not cell:
+        _lib.call("qmp_fused_bwd_target_tc" if tcb else "qmp_fused_bwd_target", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda,
+                  DA, GA, pa, xb, ldb, DB, GB, int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, ZsA, dUsA, ZsB, dUsB, dxa,
+                  dxb, float(drop_p), int(seed))
+    if (need_dxa or need_dxb) and not cell:
         if tcb:
             pa = _f.tc_image(wa, DAC, 2) if GA else None
             pb = _f.tc_image(wb, DBC, 2)

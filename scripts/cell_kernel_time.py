@@ -40,7 +40,7 @@ def old():
 
 def new():
     _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, ic, Cp, prm, 1, 1, 1, 1e-5, o["gates"],
-              o["Craw"], o["O"], o["H"], o["C"], o["head"], 36, concat, o["logit"], o["mstat"], o["linv"], 0.0, 1)
+              o["Craw"], o["O"], o["H"], o["C"], o["head"], 36, concat, o["logit"], o["mstat"], o["linv"], None, 0.0, 1)
 
 
 modes = sys.argv[1:] or ["write"]

@@ -33,7 +33,7 @@ buf = (ctypes.c_float * 4096)()
 for it in range(3):
     L.qmpx_cell_trace_dump(buf, 1)
     _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, ic, Cp, prm, 1, 1, 1, 1e-5, o["gates"],
-              o["Craw"], o["O"], o["H"], o["C"], o["head"], 36, concat, o["logit"], o["mstat"], o["linv"], 0.0, 1)
+              o["Craw"], o["O"], o["H"], o["C"], o["head"], 36, concat, o["logit"], o["mstat"], o["linv"], None, 0.0, 1)
     torch.cuda.synchronize()
 L.qmpx_cell_trace_dump(buf, 0)
 d = np.frombuffer(buf, dtype=np.float32).reshape(2, 2048)

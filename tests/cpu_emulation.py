@@ -621,12 +621,46 @@ def qmp_fused_pack_cell(packA, packB, out):
 
 
 def qmp_fused_cell_fwd(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, Cprev, params, norm_h, norm_c, norm_o, eps, gates, Craw,
-                       Oout, Hout, Cout, head_in, ldh, concat, logit, mstat, linv, drop_p, seed):
+                       Oout, Hout, Cout, head_in, ldh, concat, logit, mstat, linv, usave, drop_p, seed):
     na, nb = 4 * _total(4) * 4, 4 * _total(32) * 4
     wa = image[:na].contiguous().view(torch.float32).view(4, _total(4))
     wb = image[na:na + nb].contiguous().view(torch.float32).view(4, _total(32))
     qmp_fused_fwd(N, in_ptr, in_src, ea, xa, lda, 4, 4, wa, xb, ldb, 32, 4, 1, wb, 1, 0, _FC, None, 8 * _FC, Cprev, params, norm_h,
                   norm_c, norm_o, eps, gates, Craw, Oout, Hout, Cout, head_in, ldh, concat, logit, mstat, linv, drop_p, seed)
+    if usave is not None:
+        W1, b1 = _unpack_fwd(wb, 4, 32)[:2]
+        h = rows(xb, N, ldb, 32)
+        flat(usave, N * 128).view(N, 4, 32).copy_(torch.stack([h @ W1[g, :32].T + b1[g, :32] for g in range(4)], 1))
+
+
+def qmp_fused_pack_cell_bwd(packA, packB, out):
+    qmp_fused_pack_cell(packA, packB, out)
+
+
+def qmp_fused_cell_bwd(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, usave, dP, lddp, logit, mstat, linv, ZsA, dUsA, ZsB, dUsB,
+                       dxa, dxb, drop_p, seed):
+    """Target side by the emulated per-conv kernel; source side of every edge added from the same in-CSR edge list."""
+    na, nb = 4 * _total(4) * 4, 4 * _total(32) * 4
+    pa = _bwd_pack_from_image(image[:na].view(4, -1), 4, 4)
+    pb = _bwd_pack_from_image(image[na:na + nb].view(4, -1), 4, 32)
+    E, ti, sj = _edge_lists(N, in_ptr, in_src)
+    ds = torch.zeros(max(E, 1), 8)
+    qmp_fused_bwd_target(N, in_ptr, in_src, ea, xa, lda, 4, 4, pa, xb, ldb, 32, 4, 1, pb, 1, _FC, dP, lddp, logit, mstat, linv, ds, ZsA,
+                         dUsA, ZsB, dUsB, dxa, dxb, drop_p, seed)
+    lg, ms, li = flat(logit, max(E, 1) * 8).view(-1, 8), flat(mstat, N * 8).view(N, 8), flat(linv, N * 8).view(N, 8)
+    us = flat(usave, N * 128).view(N, 4, 32)
+    packs = {0: _unpack_bwd(pa, 4, 4), 1: _unpack_bwd(pb, 4, 32)}
+    for (c, seg, g, xp, ld, off, D, DC) in _fused_convs(xa, lda, 4, 4, xb, ldb, 32, 4, 1):
+        W1, b1, W2, W3 = (t[g] for t in packs[seg])
+        x = _rows_pad(xp, N, ld, off, D, DC)
+        g32 = _dP_of(dP, lddp, N, 1, _FC, c, 4)
+        al = (lg[:E, c] - ms[ti, c]).exp() * li[ti, c]
+        u = x @ W1[:DC].T + b1[:DC]
+        if seg == 1:
+            assert torch.allclose(us[:, g], u, rtol=1e-4, atol=1e-5), "usave must hold the logit projections of the H convs"
+        contrib = al[:, None] * (g32 @ W2[:, :DC])[ti] + ds[:E, c][:, None] * u[ti]
+        dst = win(flat(dxa if seg == 0 else dxb), (N, D), (ld, 1), off)
+        dst.add_(torch.zeros(N, DC).index_add(0, sj, contrib)[:, :D])
 
 
 def _tconv1_common(N, in_ptr, in_src, ea, x, ldx, P, drop_p):
@@ -741,6 +775,10 @@ class Emulated:
 
             @staticmethod
             def qmp_fused_cell_image_bytes():
+                return 4 * 4 * (_total(4) + _total(32))
+
+            @staticmethod
+            def qmp_fused_cell_bwd_image_bytes():
                 return 4 * 4 * (_total(4) + _total(32))
 
         _lib.call = call

@@ -293,7 +293,7 @@ def test_decoder_cell_kernel_matches_per_conv_kernel(N, drop_p, with_c):
               None, 256, Cp, prm, 1, 1, 1, 1e-5, a["gates"], a["Craw"], a["O"], a["H"], a["C"], a["head"], 36, concat, a["logit"],
               a["mstat"], a["linv"], drop_p, seed)
     _lib.call("qmp_fused_cell_fwd", N, ptr, nbr, ea, xa, 4, xb, 32, FZ.cell_image(wa, wb), Cp, prm, 1, 1, 1, 1e-5, b["gates"],
-              b["Craw"], b["O"], b["H"], b["C"], b["head"], 36, concat, b["logit"], b["mstat"], b["linv"], drop_p, seed)
+              b["Craw"], b["O"], b["H"], b["C"], b["head"], 36, concat, b["logit"], b["mstat"], b["linv"], None, drop_p, seed)
     torch.cuda.synchronize()
     for k in a:
         va, vb = a[k], b[k]
@@ -336,3 +336,59 @@ def test_scalar_transformer_conv_matches_oracle(be, quadtree):
         gb = pb.grad if pb.grad is not None else torch.zeros_like(pb)
         diff = float((ga - gb.cpu()).abs().max())
         assert diff / max(float(ga.abs().max()), 1e-3) < 2e-4 or diff < 2e-5, f"grad {k}: {diff}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,drop_p", [(1, 0.0), (130, 0.0), (5001, 0.1), (47200, 0.0)])
+def test_decoder_cell_backward_kernel_matches_per_conv_kernels(N, drop_p):
+    """qmp_fused_cell_bwd (one persistent launch: target side in octet layout, source side of every edge by vector
+    reductions) against qmp_fused_bwd_target_tc + qmp_fused_bwd_source_tc on the same inputs: the rows for the weight-gradient
+    kernel and both input gradients must agree.  Ragged in-degrees 0..9, isolated nodes, partial tiles, attention dropout."""
+    from quadtree_mpnnlstm_b200 import _lib, fused as FZ
+    from quadtree_mpnnlstm_b200.graph_csr import get_csr
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(N + 7)
+    deg = torch.randint(0, 10, (N,), generator=g)
+    if N > 20000:
+        deg = deg.clamp(max=4)
+    dst = torch.repeat_interleave(torch.arange(N), deg)
+    E = int(dst.numel())
+    src = torch.randint(0, N, (E,), generator=g)
+    ei = torch.stack([src, dst]).to(dev)
+    ea = torch.rand(E, 2, generator=g).to(dev)
+    csr = get_csr(ei, ea, N)
+    xa, xb, Cp = (torch.randn(N, w, generator=g).to(dev) for w in (4, 32, 32))
+    wa = (torch.randn(4, FZ.conv_total(4), generator=g) * 0.3).to(dev)
+    wb = (torch.randn(4, FZ.conv_total(32), generator=g) * 0.2).to(dev)
+    prm = (torch.randn(13, 32, generator=g) * 0.5).to(dev)
+    dP = torch.randn(N, 128, generator=g).to(dev)
+    z = lambda *s: torch.full(s, float("nan"), device=dev)
+    o = dict(gates=z(N, 128), Craw=z(N, 32), O=z(N, 32), H=z(N, 32), C=z(N, 32), head=z(N, 36), logit=z(max(E, 1), 8),
+             mstat=z(N, 8), linv=z(N, 8), usave=z(N, 128))
+    seed = 424242
+    _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, FZ.cell_image(wa, wb), Cp, prm, 1, 1, 1,
+              1e-5, o["gates"], o["Craw"], o["O"], o["H"], o["C"], o["head"], 36, None, o["logit"], o["mstat"], o["linv"], o["usave"],
+              drop_p, seed)
+
+    def outs():
+        return dict(ZsA=z(N, 4, 8), dUsA=z(N, 4, 8), ZsB=z(N, 4, 36), dUsB=z(N, 4, 36), dxa=z(N, 4), dxb=z(N, 32))
+
+    a, b = outs(), outs()
+    ds = z(max(E, 1), 8)
+    _lib.call("qmp_fused_bwd_target_tc", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, 4, 4, FZ.tc_image(wa, 4, 1), xb, 32, 32, 4,
+              1, FZ.tc_image(wb, 32, 1), 1, 32, dP, 128, o["logit"], o["mstat"], o["linv"], ds, a["ZsA"], a["dUsA"], a["ZsB"],
+              a["dUsB"], a["dxa"], a["dxb"], drop_p, seed)
+    _lib.call("qmp_fused_bwd_source_tc", N, csr.out_ptr, csr.out_dst, csr.out_kin, xa, 4, 4, 4, FZ.tc_image(wa, 4, 2), xb, 32, 32, 4, 1,
+              FZ.tc_image(wb, 32, 2), 1, 32, dP, 128, o["logit"], o["mstat"], o["linv"], ds, a["dxa"], a["dxb"], drop_p, seed)
+    _lib.call("qmp_fused_cell_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, FZ.cell_bwd_image(wa, wb), o["usave"],
+              dP, 128, o["logit"], o["mstat"], o["linv"], b["ZsA"], b["dUsA"], b["ZsB"], b["dUsB"], b["dxa"], b["dxb"], drop_p, seed)
+    torch.cuda.synchronize()
+    for k in a:
+        va, vb = a[k], b[k]
+        if k in ("ZsA", "dUsA"):          # column 7 / columns 6, 7 are padding
+            va, vb = va[..., :7 if k == "ZsA" else 6], vb[..., :7 if k == "ZsA" else 6]
+        if k in ("ZsB", "dUsB"):
+            va, vb = va[..., :35 if k == "ZsB" else 34], vb[..., :35 if k == "ZsB" else 34]
+        assert not torch.isnan(vb).any(), f"{k}: unwritten / NaN entries"
+        err = float((va - vb).abs().max()) / max(float(va.abs().max()), 1e-6)
+        assert err < 5e-5, f"{k}: {err}"
