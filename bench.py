@@ -179,6 +179,7 @@ def cell_roofline(model, csr, dev, iters=20):
     Craw, O, Hn, Cn = (torch.empty(N, C, **f32) for _ in range(4))
     head = torch.empty(N, fused.HEADW, **f32)
     logit, ms, li = torch.empty(E, 8, **f32), torch.empty(N, 8, **f32), torch.empty(N, 8, **f32)
+    usave = torch.empty(N, 4 * C, **f32)          # logit projections of the H convs, saved for qmp_fused_cell_bwd
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
     for k in range(iters + 3):
@@ -186,14 +187,14 @@ def cell_roofline(model, csr, dev, iters=20):
         if k >= 3:
             ev[k - 3][0].record()
         _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, X, F_in, Hs, C, img, Cs, prm, 1, 1, 1, 1e-5,
-                  gates, Craw, O, Hn, Cn, head, fused.HEADW, cc, logit, ms, li, None, 0.0, 0)
+                  gates, Craw, O, Hn, Cn, head, fused.HEADW, cc, logit, ms, li, usave, 0.0, 0)
         if k >= 3:
             ev[k - 3][1].record()
     torch.cuda.synchronize()
     ms_avg = sum(a.elapsed_time(b) for a, b in ev) / iters
     reads = 4 * (N * (F_in + 2 * C) + N) + 4 * (N + 1 + E) + 8 * E          # X, H, C, concat; CSR; edge attributes
     writes = 4 * (3 * N * C + N * fused.HEADW)                                # O, H', C', head input
-    saved = 4 * (4 * N * C + N * C + 8 * E + 16 * N)                          # gates, raw C', logits, softmax max / 1/sum
+    saved = 4 * (4 * N * C + N * C + 8 * E + 16 * N + 4 * N * C)              # gates, raw C', logits, softmax max / 1/sum, u
     return ms_avg, reads + writes + saved
 
 

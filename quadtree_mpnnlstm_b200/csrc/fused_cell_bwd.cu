@@ -56,8 +56,42 @@ __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
     acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
 }
 
+// everything the X conv of one (node, conv) thread reads from global memory for its first four in-edges: fetched while the
+// first MMA group is in flight, so that only arithmetic is left once dz arrives
+struct CellbXPre {
+    int k0, k1, jn[4];
+    float4 xi, xj[4];
+    float2 ev[4];
+    float lg[4], m, li;
+};
+__device__ __forceinline__ void cellb_xconv_load(CellbXPre& x, const CellBwdArgs& a, int i, bool valid, int c) {
+    x.k0 = valid ? __ldg(a.ptr + i) : 0;
+    x.k1 = valid ? __ldg(a.ptr + i + 1) : 0;
+    x.xi = make_float4(0.f, 0.f, 0.f, 0.f);
+    x.m = x.li = 0.f;
+    if (valid) {
+        x.xi = __ldg(reinterpret_cast<const float4*>(a.xa + (size_t)i * a.lda));
+        x.m = __ldg(a.mstat + (size_t)i * 8 + c);
+        x.li = __ldg(a.linv + (size_t)i * 8 + c);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x.jn[e] = (x.k0 + e < x.k1) ? __ldg(a.nbr + x.k0 + e) : -1;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        x.xj[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        x.ev[e] = make_float2(0.f, 0.f);
+        x.lg[e] = 0.f;
+        if (x.jn[e] >= 0) {
+            x.xj[e] = __ldg(reinterpret_cast<const float4*>(a.xa + (size_t)x.jn[e] * a.lda));
+            if (a.ea) x.ev[e] = __ldg(reinterpret_cast<const float2*>(a.ea) + x.k0 + e);
+            x.lg[e] = __ldg(a.logit + (size_t)(x.k0 + e) * 8 + c);
+        }
+    }
+}
+
 // X conv c of node i (row nrow of the tile): target side, self term of dX into the exchange row, source side by reductions
-__device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t* smem, float* exch, int i, bool valid, int nrow, int c) {
+__device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t* smem, float* exch, int i, bool valid, int nrow, int c,
+                                            const CellbXPre& x) {
     using L = CellBwdLayout;
     float* xr = exch + c * XPLANE + nrow * XS + 36;        // dz_x (4) | dze0 dze1 dzs 0 of this conv and node
     const float4 dz = ld4(xr), dze = ld4(xr + 4);
@@ -65,7 +99,7 @@ __device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t*
     if (valid) {
         const float* w1x = reinterpret_cast<const float*>(smem + L::W1X) + c * 24;
         const float* b1x = reinterpret_cast<const float*>(smem + L::B1X) + c * 8;
-        const float4 xi = __ldg(reinterpret_cast<const float4*>(a.xa + (size_t)i * a.lda));
+        const float4 xi = x.xi;
         float4 u;                                          // logit projection of this node (rows 0..3 of W1x)
         {
             const float4 w0 = ld4(w1x), w1 = ld4(w1x + 4), w2 = ld4(w1x + 8), w3 = ld4(w1x + 12);
@@ -74,35 +108,55 @@ __device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t*
             u.z = fmaf(w2.w, xi.w, fmaf(w2.z, xi.z, fmaf(w2.y, xi.y, fmaf(w2.x, xi.x, b1x[2]))));
             u.w = fmaf(w3.w, xi.w, fmaf(w3.z, xi.z, fmaf(w3.y, xi.y, fmaf(w3.x, xi.x, b1x[3]))));
         }
-        const float m = __ldg(a.mstat + (size_t)i * 8 + c), li = __ldg(a.linv + (size_t)i * 8 + c);
-        const int k0 = __ldg(a.ptr + i), k1 = __ldg(a.ptr + i + 1);
-        auto edge = [&](int kk, float4& xj, float2& ev, float& al, float& keep) {
-            xj = __ldg(reinterpret_cast<const float4*>(a.xa + (size_t)__ldg(a.nbr + kk) * a.lda));
-            ev = make_float2(0.f, 0.f);
-            if (a.ea) ev = __ldg(reinterpret_cast<const float2*>(a.ea) + kk);
-            al = fast_exp(__ldg(a.logit + (size_t)kk * 8 + c) - m) * li;
+        const float m = x.m, li = x.li;
+        const int k0 = x.k0, k1 = x.k1;
+        auto dalpha = [&](int kk, const float4& xj, const float2& ev, float lg, float& al, float& keep) {
+            al = fast_exp(lg - m) * li;
             keep = fdropout_scale(a.seed, (long long)kk * 8 + c, a.drop_p);
             return (fmaf(dz.w, xj.w, fmaf(dz.z, xj.z, fmaf(dz.y, xj.y, dz.x * xj.x))) + fmaf(dze.x, ev.x, fmaf(dze.y, ev.y, dze.z))) * keep;
         };
-        float tsum = 0.f;
-        for (int kk = k0; kk < k1; ++kk) {
-            float4 xj; float2 ev; float al, keep;
-            const float dal = edge(kk, xj, ev, al, keep);
+        auto fetch = [&](int kk, int& j, float4& xj, float2& ev, float& lg) {       // in-edges beyond the fourth (quadtree meshes)
+            j = __ldg(a.nbr + kk);
+            xj = __ldg(reinterpret_cast<const float4*>(a.xa + (size_t)j * a.lda));
+            ev = make_float2(0.f, 0.f);
+            if (a.ea) ev = __ldg(reinterpret_cast<const float2*>(a.ea) + kk);
+            lg = __ldg(a.logit + (size_t)kk * 8 + c);
+        };
+        float al4[4], keep4[4], dal4[4], tsum = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            al4[e] = keep4[e] = dal4[e] = 0.f;
+            if (x.jn[e] >= 0) {
+                dal4[e] = dalpha(k0 + e, x.xj[e], x.ev[e], x.lg[e], al4[e], keep4[e]);
+                tsum = fmaf(al4[e], dal4[e], tsum);
+            }
+        }
+        for (int kk = k0 + 4; kk < k1; ++kk) {
+            int j; float4 xj; float2 ev; float lg, al, keep;
+            fetch(kk, j, xj, ev, lg);
+            const float dal = dalpha(kk, xj, ev, lg, al, keep);
             tsum = fmaf(al, dal, tsum);
         }
         float4 du = make_float4(0.f, 0.f, 0.f, 0.f), z = du;
         float dw0 = 0.f, dw1 = 0.f, ze0 = 0.f, ze1 = 0.f, zs = 0.f;
-        for (int kk = k0; kk < k1; ++kk) {
-            float4 xj; float2 ev; float al, keep;
-            const float dal = edge(kk, xj, ev, al, keep);
+        auto accumulate = [&](int j, const float4& xj, const float2& ev, float al, float keep, float dal) {
             const float dsv = al * (dal - tsum), alk = al * keep;
             fma4(du, dsv, xj);
             fma4(z, alk, xj);
             dw0 = fmaf(dsv, ev.x, dw0); dw1 = fmaf(dsv, ev.y, dw1);
             ze0 = fmaf(alk, ev.x, ze0); ze1 = fmaf(alk, ev.y, ze1); zs += alk;
             // source side of this edge: dX_j += ds u_i + alpha dz_i
-            red4(a.dxa + (size_t)__ldg(a.nbr + kk) * a.lda, fmaf(dsv, u.x, alk * dz.x), fmaf(dsv, u.y, alk * dz.y),
-                 fmaf(dsv, u.z, alk * dz.z), fmaf(dsv, u.w, alk * dz.w));
+            red4(a.dxa + (size_t)j * a.lda, fmaf(dsv, u.x, alk * dz.x), fmaf(dsv, u.y, alk * dz.y), fmaf(dsv, u.z, alk * dz.z),
+                 fmaf(dsv, u.w, alk * dz.w));
+        };
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (x.jn[e] >= 0) accumulate(x.jn[e], x.xj[e], x.ev[e], al4[e], keep4[e], dal4[e]);
+        for (int kk = k0 + 4; kk < k1; ++kk) {
+            int j; float4 xj; float2 ev; float lg, al, keep;
+            fetch(kk, j, xj, ev, lg);
+            const float dal = dalpha(kk, xj, ev, lg, al, keep);
+            accumulate(j, xj, ev, al, keep, dal);
         }
         float* zr = a.ZsA + ((size_t)i * 4 + c) * 8;
         st4(zr, z.x, z.y, z.z, z.w);
@@ -116,6 +170,44 @@ __device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t*
         for (int r = 0; r < 6; ++r) fma4(self, dU[r], ld4(w1x + 4 * r));
     }
     st4(xr, self.x, self.y, self.z, self.w);
+}
+
+// what one warp pass of the H-conv edge phase reads from global memory before any arithmetic: first edge quad (sources,
+// attributes, rows, logits), the node's saved logit projections and softmax statistics
+struct CellbHPre {
+    int k0, deg, jj0, jx0[4];
+    float2 ev0;
+    float4 hr0[4], uu[4];
+    float m[2], li[2], lg[2];
+};
+__device__ __forceinline__ void cellb_h_load(CellbHPre& h, const CellBwdArgs& a, int tile0, int tcount, int ln, int l8, int obase) {
+    const int cc = l8 >> 2, e4 = l8 & 3;
+    const bool valid = ln < tcount;
+    const int i = tile0 + ln;
+    h.k0 = valid ? __ldg(a.ptr + i) : 0;
+    h.deg = valid ? __ldg(a.ptr + i + 1) - h.k0 : 0;
+    const bool on0 = e4 < h.deg;
+    h.jj0 = on0 ? __ldg(a.nbr + h.k0 + e4) : -1;
+    h.ev0 = make_float2(0.f, 0.f);
+    if (on0 && a.ea) h.ev0 = __ldg(reinterpret_cast<const float2*>(a.ea) + h.k0 + e4);
+#pragma unroll
+    for (int r2 = 0; r2 < 2; ++r2) {
+        const int crole = 4 + 2 * r2 + cc;
+        h.m[r2] = valid ? __ldg(a.mstat + (size_t)i * 8 + crole) : 0.f;
+        h.li[r2] = valid ? __ldg(a.linv + (size_t)i * 8 + crole) : 0.f;
+        h.lg[r2] = on0 ? __ldg(a.logit + (size_t)(h.k0 + e4) * 8 + crole) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        h.uu[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) h.uu[c] = __ldg(reinterpret_cast<const float4*>(a.usave + (size_t)i * 128 + 32 * c) + l8);
+    }
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+        h.jx0[x] = __shfl_sync(0xffffffffu, h.jj0, obase + x);
+        h.hr0[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h.jx0[x] >= 0) h.hr0[x] = __ldg(reinterpret_cast<const float4*>(a.xb + (size_t)h.jx0[x] * a.ldb) + l8);
+    }
 }
 
 __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const __grid_constant__ CellBwdArgs a,
@@ -192,7 +284,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
             if (tile0 >= end) break;
             const int tcount = (end - tile0 < T0) ? end - tile0 : T0;
 
-            // ---- gate gradient rows of gate cg, row nrow -> tensor memory
+            CELL_MARK(1);
             {
                 const int i = tile0 + nrow;
                 const bool valid = nrow < tcount;
@@ -212,11 +304,19 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                 tc::tmem_st_wait();
             }
             tc::fence_before_sync();
+            CELL_MARK(2);
             cell_sync();                                       // (the MMA warp issues G1)
+            CELL_MARK(3);
+            // while G1 runs: every global read of the X conv and of the first edge-phase pass
+            CellbXPre xp;
+            cellb_xconv_load(xp, a, tile0 + nrow, nrow < tcount, cg);
+            CellbHPre pre;
+            cellb_h_load(pre, a, tile0, tcount, 4 * warp + o8, l8, obase);
             tc::mbar_wait(&bars[0], par);
             par ^= 1;
             tc::fence_after_sync();
 
+            CELL_MARK(4);
             // ---- dz block of gate cg, row nrow: tensor memory -> exchange plane cg (columns 0..35 | 36..43 = the X conv's)
             {
                 uint32_t rr[6][8];
@@ -233,50 +333,41 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                 st4(row + 36, __uint_as_float(rr[5][0]), __uint_as_float(rr[5][1]), __uint_as_float(rr[5][2]), __uint_as_float(rr[5][3]));
                 st4(row + 40, __uint_as_float(rr[5][4]), __uint_as_float(rr[5][5]), __uint_as_float(rr[5][6]), 0.f);
             }
+            CELL_MARK(5);
             // ---- X conv cg of node nrow (reads / rewrites columns 36..43 of its own exchange row)
-            cellb_xconv(a, smem, exch, tile0 + nrow, nrow < tcount, nrow, cg);
+            cellb_xconv(a, smem, exch, tile0 + nrow, nrow < tcount, nrow, cg, xp);
+            CELL_MARK(6);
             cell_sync();
+            CELL_MARK(7);
 
-            // ---- edge phase of the four H convs, octet layout, two conv pairs per pass
+            // ---- edge phase of the four H convs, octet layout, two conv pairs per pass (pass 0's reads were issued under G1)
 #pragma unroll 1
             for (int p = 0; p < 2; ++p) {
                 if (4 * (warp + 16 * p) >= tcount) continue;   // warp-uniform
+                if (p == 1) cellb_h_load(pre, a, tile0, tcount, 4 * (warp + 16) + o8, l8, obase);
                 const int ln = 4 * (warp + 16 * p) + o8;
                 const bool valid = ln < tcount;
                 const int i = tile0 + ln;
-                const int k0 = valid ? __ldg(a.ptr + i) : 0;
-                const int deg = valid ? __ldg(a.ptr + i + 1) - k0 : 0;
+                const int k0 = pre.k0, deg = pre.deg;
                 const int nq = __reduce_max_sync(0xffffffffu, (deg + 3) >> 2);      // edge quads of the largest in-degree of the pass
                 float* xrow = exch + ln * XS;
-                // first quad: sources, attributes, rows (kept for both conv pairs)
                 const bool on0 = e4 < deg;
-                const int jj0 = on0 ? __ldg(a.nbr + k0 + e4) : -1;
-                float2 ev0 = make_float2(0.f, 0.f);
-                if (on0 && a.ea) ev0 = __ldg(reinterpret_cast<const float2*>(a.ea) + k0 + e4);
-                float4 hr0[4], con0[4];
-                int jx0[4];
+                float4 con0[4];
 #pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    jx0[x] = __shfl_sync(0xffffffffu, jj0, obase + x);
-                    hr0[x] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    con0[x] = hr0[x];
-                    if (jx0[x] >= 0) hr0[x] = __ldg(reinterpret_cast<const float4*>(a.xb + (size_t)jx0[x] * a.ldb) + l8);
-                }
-#pragma unroll 1
+                for (int x = 0; x < 4; ++x) con0[x] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
                 for (int r2 = 0; r2 < 2; ++r2) {               // conv pair: H convs 2 r2 and 2 r2 + 1; this lane's role conv = 2 r2 + cc
                     float4 dz[2], uu[2];
 #pragma unroll
                     for (int c2 = 0; c2 < 2; ++c2) {
                         dz[c2] = ld4(xrow + (2 * r2 + c2) * XPLANE + 4 * l8);
-                        uu[c2] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) uu[c2] = __ldg(reinterpret_cast<const float4*>(a.usave + (size_t)i * 128 + 32 * (2 * r2 + c2)) + l8);
+                        uu[c2] = pre.uu[2 * r2 + c2];
                     }
                     const int crole = 4 + 2 * r2 + cc;                                         // conv index in logit / mstat / linv
                     const float4 dzt = ld4(xrow + (2 * r2 + cc) * XPLANE + 32);                 // dze0 dze1 dzs of the role conv
-                    const float m = valid ? __ldg(a.mstat + (size_t)i * 8 + crole) : 0.f;
-                    const float li = valid ? __ldg(a.linv + (size_t)i * 8 + crole) : 0.f;
+                    const float m = pre.m[r2], li = pre.li[r2];
                     // (alpha, d alpha) of this lane's (conv, edge) for the quad held in hr
-                    auto coef = [&](const float4 (&hr)[4], bool on, int kk, const float2& ev, float& al, float& keep) {
+                    auto coef = [&](const float4 (&hr)[4], bool on, int kk, float lg, const float2& ev, float& al, float& keep) {
                         float v[8];
 #pragma unroll
                         for (int c2 = 0; c2 < 2; ++c2)
@@ -286,17 +377,18 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                         al = 0.f;
                         keep = 0.f;
                         if (on) {
-                            al = fast_exp(__ldg(a.logit + (size_t)kk * 8 + crole) - m) * li;
+                            al = fast_exp(lg - m) * li;
                             keep = fdropout_scale(a.seed, (long long)kk * 8 + crole, a.drop_p);
                         }
                         return (tot + fmaf(dzt.x, ev.x, fmaf(dzt.y, ev.y, dzt.z))) * keep;
                     };
-                    auto gather = [&](int qd, bool& on, int& kk, float2& ev, float4 (&hr)[4], int (&jx)[4]) {
+                    auto gather = [&](int qd, bool& on, int& kk, float& lg, float2& ev, float4 (&hr)[4], int (&jx)[4]) {
                         on = 4 * qd + e4 < deg;
                         kk = k0 + 4 * qd + e4;
                         const int jj = on ? __ldg(a.nbr + kk) : -1;
                         ev = make_float2(0.f, 0.f);
                         if (on && a.ea) ev = __ldg(reinterpret_cast<const float2*>(a.ea) + kk);
+                        lg = on ? __ldg(a.logit + (size_t)kk * 8 + crole) : 0.f;
 #pragma unroll
                         for (int x = 0; x < 4; ++x) {
                             jx[x] = __shfl_sync(0xffffffffu, jj, obase + x);
@@ -306,13 +398,13 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                     };
                     // pass 1 over the quads: t = sum_e alpha_e d alpha_e of the role conv
                     float al0, keep0;
-                    const float dal0 = coef(hr0, on0, k0 + e4, ev0, al0, keep0);
+                    const float dal0 = coef(pre.hr0, on0, k0 + e4, pre.lg[r2], pre.ev0, al0, keep0);
                     float tsum = quad_sum(al0 * dal0);
                     for (int qd = 1; qd < nq; ++qd) {
-                        bool on; int kk; float2 ev; float4 hr[4]; int jx[4];
-                        gather(qd, on, kk, ev, hr, jx);
+                        bool on; int kk; float lg; float2 ev; float4 hr[4]; int jx[4];
+                        gather(qd, on, kk, lg, ev, hr, jx);
                         float al, keep;
-                        const float dal = coef(hr, on, kk, ev, al, keep);
+                        const float dal = coef(hr, on, kk, lg, ev, al, keep);
                         tsum += quad_sum(al * dal);
                     }
                     // pass 2: ds, du, z and the source-side contributions
@@ -336,14 +428,14 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                                 fma4(con[x], alb, dz[c2]);
                             }
                     };
-                    accumulate(hr0, al0, keep0, dal0, ev0, con0);
+                    accumulate(pre.hr0, al0, keep0, dal0, pre.ev0, con0);
                     for (int qd = 1; qd < nq; ++qd) {
-                        bool on; int kk; float2 ev; float4 hr[4], con[4]; int jx[4];
-                        gather(qd, on, kk, ev, hr, jx);
+                        bool on; int kk; float lg; float2 ev; float4 hr[4], con[4]; int jx[4];
+                        gather(qd, on, kk, lg, ev, hr, jx);
 #pragma unroll
                         for (int x = 0; x < 4; ++x) con[x] = make_float4(0.f, 0.f, 0.f, 0.f);
                         float al, keep;
-                        const float dal = coef(hr, on, kk, ev, al, keep);
+                        const float dal = coef(hr, on, kk, lg, ev, al, keep);
                         accumulate(hr, al, keep, dal, ev, con);
 #pragma unroll
                         for (int x = 0; x < 4; ++x)
@@ -371,9 +463,11 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                 }
 #pragma unroll
                 for (int x = 0; x < 4; ++x)                    // first quad's source rows: both conv pairs summed
-                    if (jx0[x] >= 0) red4(a.dxb + (size_t)jx0[x] * a.ldb + 4 * l8, con0[x].x, con0[x].y, con0[x].z, con0[x].w);
+                    if (pre.jx0[x] >= 0) red4(a.dxb + (size_t)pre.jx0[x] * a.ldb + 4 * l8, con0[x].x, con0[x].y, con0[x].z, con0[x].w);
             }
+            CELL_MARK(8);
             cell_sync();
+            CELL_MARK(9);
 
             // ---- [du | dw] of H conv cg, row nrow -> tensor memory (K = 40), second contraction
             {
@@ -391,11 +485,13 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                 tc::tmem_st_wait();
             }
             tc::fence_before_sync();
+            CELL_MARK(10);
             cell_sync();                                       // (the MMA warp issues G2)
             tc::mbar_wait(&bars[0], par);
             par ^= 1;
             tc::fence_after_sync();
 
+            CELL_MARK(11);
             // ---- self terms: dH_i (8 columns per thread) and, for cg == 0, dX_i = W3x^T g + sum_c W1x_c^T [du | dw]
             {
                 const int i = tile0 + nrow;
@@ -420,7 +516,9 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                 }
             }
             tc::fence_before_sync();
+            CELL_MARK(12);
             cell_sync();                                       // exchange planes and tensor memory free for the next tile
+            CELL_MARK(13);
         }
     }
     tc::fence_before_sync();
@@ -470,6 +568,18 @@ __global__ void __launch_bounds__(256) fused_pack_cell_bwd_kernel(const float* _
 
 }  // namespace qmp
 using namespace qmp;
+
+#ifdef QMP_CELL_TRACE
+extern "C" __attribute__((visibility("default"))) int qmpx_cellb_trace_dump(float* host_out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_out, g_cell_trace, sizeof(float) * 2 * 2048);
+    if (reset) {
+        static float zeros[2 * 2048];
+        cudaMemcpyToSymbol(g_cell_trace, zeros, sizeof(zeros));
+    }
+    return 0;
+}
+#endif
 
 // Bytes of the decoder-cell backward weight image.
 QMP_API long long qmp_fused_cell_bwd_image_bytes(void) { return CellBwdLayout::BYTES; }
