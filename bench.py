@@ -257,11 +257,12 @@ def run_gpu(args):
     h2d = sum(t.numel() * 4 for t in hs[0])
     barrier()
     e0.record()
+    nxt = step.stage(*hs[0])                    # pinned host -> device on a copy stream; sample i + 1 travels under step i
     for i in range(args.steps):
-        if args.no_graph:
-            last = step(*[t.to(dev, non_blocking=True) for t in hs[i]]).item()
-        else:
-            last = step(*hs[i]).item()          # pinned host -> the graph's static inputs -> replay
+        cur = nxt
+        if i + 1 < args.steps:
+            nxt = step.stage(*hs[i + 1])
+        last = step(*cur).item()                # -> the graph's static inputs -> replay; the loss comes back every step
     e1.record()
     barrier()
     ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)

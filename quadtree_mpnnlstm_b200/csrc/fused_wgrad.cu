@@ -77,11 +77,19 @@ constexpr int WG_KH = WG_KT / 2;                // nodes per tile staged by one 
 __device__ __forceinline__ void wg_sync() { asm volatile("bar.sync 0, %0;" ::"n"(WG_THREADS) : "memory"); }
 __device__ __forceinline__ void wg_sync_workers() { asm volatile("bar.sync 1, %0;" ::"n"(WG_WORKERS) : "memory"); }
 
+#ifdef QMP_CELL_TRACE
+static __device__ long long g_wg_trace[64];
+#define WG_MARK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (k) < 64) g_wg_trace[k] = clock64(); } while (0)
+#else
+#define WG_MARK(k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(WG_THREADS, 2) fused_wgrad_kernel(const __grid_constant__ WgArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     const int t = threadIdx.x, warp = t >> 5;
+    WG_MARK(0);
     int ci = 0;
     while (ci + 1 < a.nconv && (int)blockIdx.x >= a.c[ci].cta0 + a.c[ci].nctas) ++ci;
     const WgConv& cv = a.c[ci];
@@ -208,23 +216,30 @@ __global__ void __launch_bounds__(WG_THREADS, 2) fused_wgrad_kernel(const __grid
             acc = 1;
         }
     } else {
+        WG_MARK(1);
         if (tile < ntiles) fetch(tile);
+        int wk = 2;
         for (; tile < ntiles; tile += cv.nctas) {
             if (acc) {                   // the previous tile's MMAs must have read the operands before they are overwritten
                 tc::mbar_wait(&bar, parity);
                 parity ^= 1;
                 tc::fence_after_sync();
             }
+            WG_MARK(wk); ++wk;
             stage();
             tc::fence_async_smem();
             tc::fence_before_sync();
+            WG_MARK(wk); ++wk;
             wg_sync();
             acc = 1;
             if (tile + cv.nctas < ntiles) fetch(tile + cv.nctas);     // next tile's rows fly while the tensor core works
+            WG_MARK(wk); ++wk;
         }
+        WG_MARK(60);
         if (acc) {
             tc::mbar_wait(&bar, parity);
             tc::fence_after_sync();
+            WG_MARK(61);
             // flush.  Accumulator row t (thread t's TMEM lane) -> shared memory, then warps walk the rows with their lanes
             // along the columns so that one reduction instruction touches 4 sectors instead of 32 (the L2 atomic units
             // see 8x fewer transactions).  Pack offsets (fused.cuh): W1 | b1 | W2 | W3 | b3
@@ -275,13 +290,23 @@ __global__ void __launch_bounds__(WG_THREADS, 2) fused_wgrad_kernel(const __grid
             }
         }
     }
+    WG_MARK(62);
     tc::fence_before_sync();
     wg_sync();
+    WG_MARK(63);
     if (warp == 0) tc::tmem_dealloc(tmem, WG_TMEM_COLS);
 }
 
 }  // namespace qmp
 using namespace qmp;
+
+#ifdef QMP_CELL_TRACE
+extern "C" __attribute__((visibility("default"))) int qmpx_wg_trace_dump(long long* host_out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(host_out, g_wg_trace, sizeof(long long) * 64);
+    return 0;
+}
+#endif
 
 // Weight gradients of one fused layer group (see the top of this file): accumulates into gwa [GA, TOTAL(cap DA)] /
 // gwb [GB, TOTAL(cap DB)] (forward pack layout, caller zero-initialises).  Arguments as qmp_fused_bwd_target, whose

@@ -91,9 +91,27 @@ class TrainStep:
         self.model.graph = None
 
     # -- public -------------------------------------------------------------------------------------
+    def stage(self, x, y, concat):
+        """Start the host -> device copy of the NEXT sample (pinned host tensors) on a copy stream and return device tensors
+        that ``__call__`` accepts: the copy of sample i + 1 overlaps the step of sample i instead of preceding its own."""
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(self._copy_stream):
+            out = [t.to(cur.device, non_blocking=True) for t in (x, y, concat)]
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        for t in out:
+            t.record_stream(cur)
+        out[0]._qmp_ready = ev
+        return out
+
     def __call__(self, x, y, concat, warmup_eager=3):
         """Run one optimizer step on device tensors x [T_in,H,W,c], y [T_out,H,W,1], concat [T_out,H,W,1].
         Returns the (device) loss tensor of this step."""
+        ev = getattr(x, "_qmp_ready", None)
+        if ev is not None:                               # staged by stage(): wait for its copy
+            torch.cuda.current_stream().wait_event(ev)
         if not self.use_cuda_graph:
             return self._step(x, y, concat)
         if self.graph is None:
