@@ -49,6 +49,11 @@ struct CellBwdArgs {
     float drop_p; unsigned long long seed;
 };
 
+// 16 warps, no dedicated MMA warp: both MMA groups of a tile are issued at points where every warp waits for their result
+// anyway, and 512 threads keep the 128-register budget (the 17-warp CTA of the forward kernel is capped at 96)
+constexpr int CELLB_THREADS = CELL_WORKERS;
+__device__ __forceinline__ void cellb_sync() { asm volatile("bar.sync 0, %0;" ::"n"(CELLB_THREADS) : "memory"); }
+
 __device__ __forceinline__ void red4(float* p, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -210,7 +215,7 @@ __device__ __forceinline__ void cellb_h_load(CellbHPre& h, const CellBwdArgs& a,
     }
 }
 
-__global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const __grid_constant__ CellBwdArgs a,
+__global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const __grid_constant__ CellBwdArgs a,
                                                                          const uint8_t* __restrict__ img, const int Q, const int R,
                                                                          const int T0) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
     tc::fence_before_sync();
-    cell_sync();
+    cellb_sync();
     tc::fence_after_sync();
     if (t == 0) {
         tc::mbar_expect_tx(&bars[1], (uint32_t)L::BYTES);
@@ -240,39 +245,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
     if (end > a.N) end = a.N;
     tc::mbar_wait(&bars[1], 0);                                // weights in shared memory
 
-    if (warp == CELL_WORKERS / 32) {
-        // ---- the MMA warp: issues both groups of every tile, in step with the workers' barriers
-        for (int r = 0; r < R; ++r) {
-            if (beg + r * T0 >= end) break;
-            cell_sync();                                       // g rows staged
-            if (lane == 0) {
-                tc::fence_after_sync();
-#pragma unroll 1
-                for (int g = 0; g < 4; ++g) {
-                    const uint32_t ah = tmem + TB_A + 64 * g, al = ah + 32;
-                    tc_mma3_at(0, tmem + TB_D1 + 48 * g, ah, al, tc::smem_u32(smem + L::B1H + g * L::B1G),
-                               tc::smem_u32(smem + L::B1H + g * L::B1G + L::B1G / 2), 48, 32, false);
-                    tc_mma3_at(0, tmem + TB_D2, ah, al, tc::smem_u32(smem + L::B3H + g * L::B3G),
-                               tc::smem_u32(smem + L::B3H + g * L::B3G + L::B3G / 2), 48, 32, g > 0);
-                }
-                tc::commit(&bars[0]);
-            }
-            __syncwarp();
-            cell_sync();                                       // dz dumped, X convs done
-            cell_sync();                                       // edge phase done
-            cell_sync();                                       // [du | dw] staged
-            if (lane == 0) {
-                tc::fence_after_sync();
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c)
-                    tc_mma3_at(0, tmem + TB_D2, tmem + TB_A + 80 * c, tmem + TB_A + 80 * c + 40, tc::smem_u32(smem + L::B2H + c * L::B2G),
-                               tc::smem_u32(smem + L::B2H + c * L::B2G + L::B2G / 2), 32, 40, true);
-                tc::commit(&bars[0]);
-            }
-            __syncwarp();
-            cell_sync();                                       // dx flushed
-        }
-    } else {
+    {
         const int q = warp & 3, cg = warp >> 2;
         const int nrow = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
@@ -305,7 +278,20 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
             }
             tc::fence_before_sync();
             CELL_MARK(2);
-            cell_sync();                                       // (the MMA warp issues G1)
+            cellb_sync();
+            if (t == 0) {                                      // G1: dz of the four gates, skip-path part of dx
+                tc::fence_after_sync();
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t ah = tmem + TB_A + 64 * g, al = ah + 32;
+                    tc_mma3_at(0, tmem + TB_D1 + 48 * g, ah, al, tc::smem_u32(smem + L::B1H + g * L::B1G),
+                               tc::smem_u32(smem + L::B1H + g * L::B1G + L::B1G / 2), 48, 32, false);
+                    tc_mma3_at(0, tmem + TB_D2, ah, al, tc::smem_u32(smem + L::B3H + g * L::B3G),
+                               tc::smem_u32(smem + L::B3H + g * L::B3G + L::B3G / 2), 48, 32, g > 0);
+                }
+                tc::commit(&bars[0]);
+            }
+            __syncwarp();
             CELL_MARK(3);
             // while G1 runs: every global read of the X conv and of the first edge-phase pass
             CellbXPre xp;
@@ -337,7 +323,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
             // ---- X conv cg of node nrow (reads / rewrites columns 36..43 of its own exchange row)
             cellb_xconv(a, smem, exch, tile0 + nrow, nrow < tcount, nrow, cg, xp);
             CELL_MARK(6);
-            cell_sync();
+            cellb_sync();
             CELL_MARK(7);
 
             // ---- edge phase of the four H convs, octet layout, two conv pairs per pass (pass 0's reads were issued under G1)
@@ -466,7 +452,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
                     if (pre.jx0[x] >= 0) red4(a.dxb + (size_t)pre.jx0[x] * a.ldb + 4 * l8, con0[x].x, con0[x].y, con0[x].z, con0[x].w);
             }
             CELL_MARK(8);
-            cell_sync();
+            cellb_sync();
             CELL_MARK(9);
 
             // ---- [du | dw] of H conv cg, row nrow -> tensor memory (K = 40), second contraction
@@ -486,7 +472,16 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
             }
             tc::fence_before_sync();
             CELL_MARK(10);
-            cell_sync();                                       // (the MMA warp issues G2)
+            cellb_sync();
+            if (t == 0) {                                      // G2: dH += [du | dw] W1 of the four H convs
+                tc::fence_after_sync();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c)
+                    tc_mma3_at(0, tmem + TB_D2, tmem + TB_A + 80 * c, tmem + TB_A + 80 * c + 40, tc::smem_u32(smem + L::B2H + c * L::B2G),
+                               tc::smem_u32(smem + L::B2H + c * L::B2G + L::B2G / 2), 32, 40, true);
+                tc::commit(&bars[0]);
+            }
+            __syncwarp();
             tc::mbar_wait(&bars[0], par);
             par ^= 1;
             tc::fence_after_sync();
@@ -517,12 +512,12 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_bwd_kernel(const _
             }
             tc::fence_before_sync();
             CELL_MARK(12);
-            cell_sync();                                       // exchange planes and tensor memory free for the next tile
+            cellb_sync();                                       // exchange planes and tensor memory free for the next tile
             CELL_MARK(13);
         }
     }
     tc::fence_before_sync();
-    cell_sync();
+    cellb_sync();
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -622,7 +617,7 @@ QMP_API int qmp_fused_cell_bwd(int N, const int* in_ptr, const int* in_src, cons
     const int Q = (cdiv(N, G) + 3) & ~3;
     const int R = cdiv(Q, 128);
     const int T0 = (cdiv(Q, R) + 3) & ~3;
-    fused_cell_bwd_kernel<<<cdiv(N, Q), CELL_THREADS, CELLB_SMEM, st>>>(a, reinterpret_cast<const uint8_t*>(image), Q, R, T0);
+    fused_cell_bwd_kernel<<<cdiv(N, Q), CELLB_THREADS, CELLB_SMEM, st>>>(a, reinterpret_cast<const uint8_t*>(image), Q, R, T0);
     QMP_LAUNCH_CHECK("fused_cell_bwd_kernel");
     return 0;
 }
