@@ -293,9 +293,7 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
             }
             __syncwarp();
             CELL_MARK(3);
-            // while G1 runs: every global read of the X conv and of the first edge-phase pass
-            CellbXPre xp;
-            cellb_xconv_load(xp, a, tile0 + nrow, nrow < tcount, cg);
+            // while G1 runs: every global read of the first edge-phase pass
             CellbHPre pre;
             cellb_h_load(pre, a, tile0, tcount, 4 * warp + o8, l8, obase);
             tc::mbar_wait(&bars[0], par);
@@ -320,9 +318,6 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
                 st4(row + 40, __uint_as_float(rr[5][4]), __uint_as_float(rr[5][5]), __uint_as_float(rr[5][6]), 0.f);
             }
             CELL_MARK(5);
-            // ---- X conv cg of node nrow (reads / rewrites columns 36..43 of its own exchange row)
-            cellb_xconv(a, smem, exch, tile0 + nrow, nrow < tcount, nrow, cg, xp);
-            CELL_MARK(6);
             cellb_sync();
             CELL_MARK(7);
 
@@ -454,6 +449,8 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
             CELL_MARK(8);
             cellb_sync();
             CELL_MARK(9);
+            CellbXPre xp;                                      // the X conv's global reads fly under the staging and the G2 issue
+            cellb_xconv_load(xp, a, tile0 + nrow, nrow < tcount, cg);
 
             // ---- [du | dw] of H conv cg, row nrow -> tensor memory (K = 40), second contraction
             {
@@ -482,10 +479,13 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
                 tc::commit(&bars[0]);
             }
             __syncwarp();
+            // ---- while G2 runs: X conv cg of node nrow (reads dz_x in columns 36..43 of its own exchange row, leaves its dX term there)
+            cellb_xconv(a, smem, exch, tile0 + nrow, nrow < tcount, nrow, cg, xp);
+            CELL_MARK(6);
             tc::mbar_wait(&bars[0], par);
             par ^= 1;
             tc::fence_after_sync();
-
+            cellb_sync();                                      // every X conv's dX term is in the exchange rows
             CELL_MARK(11);
             // ---- self terms: dH_i (8 columns per thread) and, for cg == 0, dX_i = W3x^T g + sum_c W1x_c^T [du | dw]
             {
