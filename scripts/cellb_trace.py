@@ -61,8 +61,9 @@ if hasattr(L, "qmpx_cellb_trace_dump"):
     torch.cuda.synchronize()
     L.qmpx_cellb_trace_dump(buf, 0)
     d = np.frombuffer(buf, dtype=np.float32).reshape(2, 2048)
-    names = {1: "tile start", 2: "g rows staged", 3: "sync (G1 issued by the MMA warp)", 4: "G1 complete", 5: "dz dumped", 6: "X convs done",
-             7: "sync", 8: "edge phase done", 9: "sync", 10: "[du|dw] staged", 11: "G2 complete", 12: "dx flushed", 13: "sync"}
+    names = {1: "tile start", 2: "g rows staged", 3: "sync, G1 issued (thread 0)", 4: "first-pass reads issued, G1 complete", 5: "dz dumped",
+             7: "sync", 8: "edge phase done", 9: "sync", 10: "X reads issued, [du|dw] staged", 6: "sync, G2 issued, X convs done",
+             11: "G2 complete, sync", 12: "dx flushed", 13: "sync"}
     n = int(d[0, 0])
     tags = d[0, 1:1 + 2 * n:2].astype(int)
     clk = d[0, 2:2 + 2 * n:2].astype(np.int64)
