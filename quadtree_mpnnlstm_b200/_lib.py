@@ -55,6 +55,7 @@ SIGNATURES = {
     "qmp_fused_pack_tc": "piiipp",
     "qmp_fused_bwd_target_tc": "ippppiiippiiiipiipippppppppppfup",
     "qmp_fused_bwd_source_tc": "ippppiiippiiiipiipippppppfup",
+    "qmp_fused_bwd_onepass_tc": "ippppiiippiiiipiipippppppppppfup",
     "qmp_fused_pack_cell": "pppp",
     "qmp_fused_pack_cell_bwd": "pppp",
     "qmp_fused_cell_bwd": "ipppp" "i" "p" "i" "ppp" "i" "ppp" "pppp" "pp" "fup",
@@ -72,7 +73,7 @@ KERNELS_PER_CALL = {
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
     "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
-    "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1, "qmp_fused_bwd_target_tc": 1, "qmp_fused_bwd_source_tc": 1,
+    "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1, "qmp_fused_bwd_target_tc": 1, "qmp_fused_bwd_source_tc": 1, "qmp_fused_bwd_onepass_tc": 1,
     "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1, "qmp_tconv1_fwd": 2, "qmp_tconv1_bwd": 2, "qmp_fused_pack_cell_bwd": 1, "qmp_fused_cell_bwd": 1,
 }
 CALL_COUNTS = {}

@@ -54,6 +54,7 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_fused_fwd_tc": "model/model.py:394-463 GConvLSTM.forward around PyG TransformerConv + model/seq2seq.py:59-66, 138-165 (one launch, dense contractions on tcgen05)",
     "qmp_fused_bwd_target_tc": "autograd of qmp_fused_fwd_tc, target side (dense contractions on tcgen05)",
     "qmp_fused_bwd_source_tc": "autograd of qmp_fused_fwd_tc, source side (dense contractions on tcgen05)",
+    "qmp_fused_bwd_onepass_tc": "autograd of qmp_fused_fwd_tc, target and source side of every edge in one launch (source rows by vector reductions)",
     "qmp_fused_pack_tc": "(weight images for the tcgen05 fused kernels: hi / lo TF32 split, canonical K-major layout)",
     "qmp_fused_tc_image_bytes": "(size of one conv's weight image)",
     "qmp_fused_wgrad": "autograd weight gradients of the above (tcgen05 3xTF32 reduction over the mesh nodes)",

@@ -34,6 +34,7 @@ struct FusedBwdArgs {
     float* ds;
     float* ZsA; float* dUsA; float* ZsB; float* dUsB;                    // [N, G, cap+4]
     float* dxa; float* dxb; int need_dxa, need_dxb;
+    int onepass;                                                         // tcgen05 target kernel only: source side by reductions (dx zero on entry)
     float drop_p; unsigned long long seed;
 };
 

@@ -14,6 +14,35 @@
 namespace qmp {
 
 constexpr uint32_t TCB_DXB = 0, TCB_DXA = 64;                           // target kernel: dx accumulators inside the P block
+constexpr uint32_t TCB_UST = 80;                                        // one-pass mode: u_i stash (<= 40 columns of the P block)
+
+// ONE-PASS mode (FusedBwdArgs::onepass, entry point qmp_fused_bwd_onepass_tc): the target kernel also does the source side
+// of every in-edge j -> i, as in fused_cell_bwd.cu: the contribution ds_e u_i + alpha_e dz_i to dx_j is formed from
+// target-side quantities only (u_i = W1[:DC] x_i + b1 recomputed with FFMAs from the plain copy in the image, dz_i read
+// back from tensor memory) and added to row j with 16-byte vector reductions; the self part of dx_i goes the same way.
+// dxa / dxb are zeroed by the entry point.  No out-CSR pass, no second launch, no second weight image.
+__device__ __forceinline__ void tc_red4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// lane's row x is ADDED to base + j * ld (j < 0: skipped) with coalesced reductions: 8 lanes per row, 4 rows per instruction
+__device__ __forceinline__ void warp_red_rows32(float* tile, float* __restrict__ base, int ld, int j, const float (&x)[32]) {
+    const int lane = threadIdx.x & 31, c = lane & 7;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<float4*>(tc_tile_chunk(tile, lane, k)) = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int r = 4 * q + (lane >> 3);
+        const int jr = __shfl_sync(0xffffffffu, j, r);
+        if (jr >= 0) {
+            const float4 v = *reinterpret_cast<const float4*>(tc_tile_chunk(tile, r, c));
+            tc_red4(base + (size_t)jr * ld + 4 * c, v.x, v.y, v.z, v.w);
+        }
+    }
+    __syncwarp();
+}
 constexpr uint32_t TCS_DXB = 0, TCS_DXA = 48, TCS_AH = 64, TCS_AL = 144;   // source kernel map (A up to 80 columns)
 
 struct TcBStep {
@@ -104,6 +133,35 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         tc_mma3(cx.tmem, TC_U, tc::smem_u32(wb + L.W2TH), tc::smem_u32(wb + L.W2TL), L.N2, FC, false);
         if (need_dx) tc_mma3(cx.tmem, st.pcol, tc::smem_u32(wb + L.W3TH), tc::smem_u32(wb + L.W3TL), L.N1P, FC, !st.first);
         tc::commit(cx.bar);
+    }
+    const bool onep = need_dx && a.onepass;
+    if (onep) {     // u_i = W1[:DC] x_i + b1 (what d logit_e / d x_j is for every in-edge e of this node) -> TMEM stash
+        tc::mbar_wait(cx.wfull + buf, (cx.wpar >> buf) & 1u);
+        float u[L.K1];
+        const float* b1p = reinterpret_cast<const float*>(wb + L.B1P);
+#pragma unroll
+        for (int k = 0; k < L.K1; ++k) u[k] = b1p[k];
+        const float4* w1p = reinterpret_cast<const float4*>(wb + L.W1P);
+        const float4* xrow = reinterpret_cast<const float4*>(xin + (size_t)(valid ? i : 0) * ld);
+#pragma unroll 1
+        for (int m4 = 0; m4 < DC / 4; ++m4) {
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && 4 * m4 < D) xv = __ldg(xrow + m4);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const float4* wr = w1p + (4 * m4 + s4) * (L.K1 / 4);
+#pragma unroll
+                for (int q = 0; q < L.K1 / 4; ++q) {
+                    const float4 w = wr[q];
+                    u[4 * q] = fmaf(xs[s4], w.x, u[4 * q]);
+                    u[4 * q + 1] = fmaf(xs[s4], w.y, u[4 * q + 1]);
+                    u[4 * q + 2] = fmaf(xs[s4], w.z, u[4 * q + 2]);
+                    u[4 * q + 3] = fmaf(xs[s4], w.w, u[4 * q + 3]);
+                }
+            }
+        }
+        tc_store_cols<L.K1 / 8>(cx.lane_base, TCB_UST, u);
     }
     const int k0 = te.k0, k1 = te.k1;
     const int j0 = k0 < k1 ? te.j[0] : -1, j1 = k0 + 1 < k1 ? te.j[1] : -1, j2 = k0 + 2 < k1 ? te.j[2] : -1,
@@ -204,7 +262,54 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
             tc::commit(cx.bar);
         }
         cx.pending = true;
-        if (st.last) {          // dx_i (self part) = accumulated over the convs sharing this input
+        if (onep) {             // source side of this node's in-edges, under the MMA: dx_j += ds_e u_i + alpha_e dz_i
+            float u[L.K1], dzr[L.K1];
+            tc_load_cols<L.K1 / 8>(cx.lane_base, TCB_UST, u);
+            tc_load_cols<L.K1 / 8>(cx.lane_base, TC_U, dzr);
+            auto push = [&](int j, float dsv, float alk) {
+                if constexpr (co) {
+                    float r[32];
+#pragma unroll
+                    for (int k = 0; k < 32; ++k) r[k] = fmaf(dsv, u[k], alk * dzr[k]);
+                    warp_red_rows32(cx.rtile, st.dx, st.lddx, j, r);
+                } else if (j >= 0) {
+                    float* dr = st.dx + (size_t)j * st.lddx;
+#pragma unroll
+                    for (int k = 0; k < DC; k += 4)
+                        if (k < D)
+                            tc_red4(dr + k, fmaf(dsv, u[k], alk * dzr[k]), fmaf(dsv, u[k + 1], alk * dzr[k + 1]),
+                                    fmaf(dsv, u[k + 2], alk * dzr[k + 2]), fmaf(dsv, u[k + 3], alk * dzr[k + 3]));
+                }
+            };
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = e == 0 ? j0 : e == 1 ? j1 : e == 2 ? j2 : j3;
+                if (more(j >= 0))
+                    push(j, al4[e] * (dal4[e] - tsum), al4[e] * fdropout_scale(a.seed, (long long)(k0 + e) * a.NC + c, a.drop_p));
+            }
+            for (int kk = k0 + 4; more(kk < k1); ++kk) {
+                const bool on = kk < k1;
+                float dsv = 0.f, alk = 0.f;
+                if (on) {
+                    dsv = a.ds[(size_t)kk * a.NC + c];
+                    alk = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li * fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
+                }
+                push(on ? a.nbr[kk] : -1, dsv, alk);
+            }
+        }
+        if (st.last && onep) {  // self part added like every other contribution (rows are zero on entry, any CTA order)
+            tc_wait(cx);
+            float dx[L.K1];
+            tc_load_cols<L.K1 / 8>(cx.lane_base, st.pcol, dx);
+            if constexpr (co) {
+                warp_red_rows32(cx.rtile, st.dx, st.lddx, valid ? i : -1, dx);
+            } else if (valid) {
+                float* row = st.dx + (size_t)i * st.lddx;
+#pragma unroll
+                for (int k = 0; k < L.K1; k += 4)
+                    if (k < D) tc_red4(row + k, dx[k], dx[k + 1], dx[k + 2], dx[k + 3]);
+            }
+        } else if (st.last) {   // dx_i (self part) = accumulated over the convs sharing this input
             tc_wait(cx);
             float dx[L.K1];
             tc_load_cols<L.K1 / 8>(cx.lane_base, st.pcol, dx);
@@ -347,7 +452,8 @@ __global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_const
     cx.tmem = tmem_slot;
     cx.lane_base = cx.tmem + ((uint32_t)(warp * 32) << 16);
     cx.lane_off = (uint32_t)(warp * 32) << 16;
-    cx.rtile = reinterpret_cast<float*>(smem + 2 * SLOT) + warp * 2 * TC_ROWTILE;
+    constexpr int RT = DBC == 32 ? 2 : 1;          // the paired row loads exist for the 32-wide rows only
+    cx.rtile = reinterpret_cast<float*>(smem + 2 * SLOT) + warp * RT * TC_ROWTILE;
     cx.rtile_g = cx.rtile;
 
     const int ntiles = (a.N + 127) / 128;
@@ -395,7 +501,7 @@ int launch_bwd_tc(const FusedBwdArgs& a, cudaStream_t st) {
     constexpr int BA = KIND == 1 ? TcBwdTLayout(DA_).BYTES : TcBwdSLayout(DA_).BYTES;
     constexpr int BB = KIND == 1 ? TcBwdTLayout(DBC).BYTES : TcBwdSLayout(DBC).BYTES;
     constexpr int SLOT = BA > BB ? BA : BB;
-    const size_t smem = 2 * (size_t)SLOT + 4 * 2 * TC_ROWTILE * sizeof(float);
+    const size_t smem = 2 * (size_t)SLOT + 4 * (DBC == 32 ? 2 : 1) * TC_ROWTILE * sizeof(float);
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;

@@ -57,6 +57,11 @@ __global__ void __launch_bounds__(256) fused_pack_tc_kernel(const float* __restr
             const int n = idx / L.K2, r = idx % L.K2;
             img_put(img, L.W1TH, L.W1TL, n, r, L.K2, (n < DC && r < DC + 2) ? W1[r * DC + n] : 0.f);
         }
+        for (int idx = threadIdx.x; idx < DC * L.K1; idx += 256) {            // plain fp32: row = x index m, column = u index k
+            const int m = idx / L.K1, k = idx % L.K1;
+            reinterpret_cast<float*>(img + L.W1P)[idx] = (k < DC) ? W1[k * DC + m] : 0.f;
+        }
+        for (int idx = threadIdx.x; idx < L.K1; idx += 256) reinterpret_cast<float*>(img + L.B1P)[idx] = (idx < DC) ? b1[idx] : 0.f;
     } else {
         const TcBwdSLayout L(DC);
         uint8_t* img = out + (size_t)g * L.BYTES;

@@ -37,12 +37,14 @@ struct TcFwdLayout {
 __host__ __device__ constexpr int tc_pad16(int v) { return (v + 15) / 16 * 16; }
 
 // BACKWARD, target side: g (32) -> dz = W2^T g (N2 rows), dx_self = W3^T g (+ W1^T du) (N1P rows)
+// W1P / B1P: the logit weights once more as plain fp32, [DC rows m][K1 columns k] = W1[k][m] and b1[k] (K1 entries): the
+// one-pass mode recomputes u_i = W1[:DC] x_i + b1 with FFMAs (the transposed MMA image cannot produce it)
 struct TcBwdTLayout {
-    int K1, K2, N2, N1P, W2TH, W2TL, W3TH, W3TL, W1TH, W1TL, BYTES;
+    int K1, K2, N2, N1P, W2TH, W2TL, W3TH, W3TL, W1TH, W1TL, W1P, B1P, BYTES;
     __host__ __device__ constexpr TcBwdTLayout(int DC)
         : K1(tc_pad8(DC)), K2(tc_pad8(DC + 4)), N2(tc_pad16(K2)), N1P(tc_pad16(K1)), W2TH(0), W2TL(W2TH + N2 * FC * 4),
           W3TH(W2TL + N2 * FC * 4), W3TL(W3TH + N1P * FC * 4), W1TH(W3TL + N1P * FC * 4), W1TL(W1TH + N1P * K2 * 4),
-          BYTES(W1TL + N1P * K2 * 4) {}
+          W1P(W1TL + N1P * K2 * 4), B1P(W1P + DC * K1 * 4), BYTES(B1P + K1 * 4) {}
 };
 
 // BACKWARD, source side: [av (32) | bv (K1) | sum ds, 0 ...] (KS columns) -> dx += W2[:, :D]^T av + W1[:D] bv + b1 sum ds

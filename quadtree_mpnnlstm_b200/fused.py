@@ -18,6 +18,7 @@ TC_WGRAD = True     # weight gradients: one tcgen05 launch per group (False: ten
 TC_BWD = True       # backward (target / source side) on tcgen05 (csrc/fused_bwd_tc.inl); False: fp32-FFMA kernels
 TC_FWD = True       # forward on tcgen05 (csrc/fused_fwd_tc.inl); False: the fp32-FFMA kernel (csrc/fused_fwd.inl)
 SCALAR_HEAD = True  # decoder head's fc_out2 (hidden -> 1 channel): scalar query / key / value kernels (csrc/tconv1.cu)
+ONEPASS_BWD = True  # tcgen05 backward of the other groups: source side of every edge by vector reductions inside the target kernel (one launch)
 CELL_BWD = True     # ... and its backward: target + source side of every edge in one persistent launch (csrc/fused_cell_bwd.cu)
 CELL_FWD = True     # decoder cell (4 X convs + 4 H convs, gate mode): the persistent gates-batched kernel (csrc/fused_cell_fwd.cu)
 _f32 = torch.float32
@@ -63,7 +64,7 @@ def tc_image_bytes(DC, kind=0):
         return 8 * (N1 * K1 + FC * K1 + FC * K2) + 4 * (48 + FC)
     if kind == 1:
         N2, N1P = _pad16(K2), _pad16(K1)
-        return 8 * (N2 * FC + N1P * FC + N1P * K2)
+        return 8 * (N2 * FC + N1P * FC + N1P * K2) + 4 * (DC * K1 + K1)
     assert kind == 2
     return 8 * _pad16(K1) * (FC + K1 + 8)
 

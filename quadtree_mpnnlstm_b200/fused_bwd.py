@@ -105,10 +105,11 @@ def fused_group_backward(ctx, *grads):
         dUsA = torch.empty(N, GA, DAC + 4, dtype=_f32, device=dev)
     ZsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
     dUsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
-    dxa = torch.empty_like(xa) if need_dxa else None
-    dxb = torch.empty_like(xb) if need_dxb else None
     from . import fused as _f
     tcb = _f.TC_BWD
+    onepass = tcb and _f.ONEPASS_BWD and not cell and (need_dxa or need_dxb)
+    dxa = torch.empty_like(xa) if need_dxa else None
+    dxb = torch.empty_like(xb) if need_dxb else None
     lda = xa.shape[1] if xa is not None else 0
     ldb = xb.shape[1]
     if cell:        # target and source side of every edge in one persistent launch (csrc/fused_cell_bwd.cu)
@@ -121,10 +122,10 @@ def fused_group_backward(ctx, *grads):
         pa = bwd_pack(wa, DAC) if GA else None
         pb = bwd_pack(wb, DBC)
     if not cell:
-        _lib.call("qmp_fused_bwd_target_tc" if tcb else "qmp_fused_bwd_target", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda,
+        _lib.call(("qmp_fused_bwd_onepass_tc" if onepass else "qmp_fused_bwd_target_tc") if tcb else "qmp_fused_bwd_target", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda,
                   DA, GA, pa, xb, ldb, DB, GB, int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, ZsA, dUsA, ZsB, dUsB, dxa,
                   dxb, float(drop_p), int(seed))
-    if (need_dxa or need_dxb) and not cell:
+    if (need_dxa or need_dxb) and not cell and not onepass:
         if tcb:
             pa = _f.tc_image(wa, DAC, 2) if GA else None
             pb = _f.tc_image(wb, DBC, 2)

@@ -727,6 +727,22 @@ def qmp_fused_bwd_target_tc(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb,
                          ldb, DB, GB, sharedB, _bwd_pack_from_image(wb, GB, _cap(DB, False)), *rest)
 
 
+def qmp_fused_bwd_onepass_tc(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, mode, C, dP, lddp, logit, mstat,
+                             linv, ds, ZsA, dUsA, ZsB, dUsB, dxa, dxb, drop_p, seed):
+    """Target side, then the source side over the out-CSR derived from the in-CSR (the kernel does both in one pass)."""
+    for dxp in (dxa, dxb):
+        if dxp is not None:
+            dxp.zero_()
+    qmp_fused_bwd_target_tc(N, in_ptr, in_src, ea, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, mode, C, dP, lddp, logit, mstat,
+                            linv, ds, ZsA, dUsA, ZsB, dUsB, dxa, dxb, drop_p, seed)
+    E, ti, sj = _edge_lists(N, in_ptr, in_src)
+    order = torch.sort(sj, stable=True).indices
+    out_ptr = torch.zeros(N + 1, dtype=torch.int32)
+    out_ptr[1:] = torch.cumsum(torch.bincount(sj, minlength=N), 0).int()
+    qmp_fused_bwd_source_tc(N, out_ptr, ti[order].int(), order.int(), xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, mode, C, dP,
+                            lddp, logit, mstat, linv, ds, dxa, dxb, drop_p, seed)
+
+
 def qmp_fused_bwd_source_tc(N, out_ptr, out_dst, out_kin, xa, lda, DA, GA, wa, xb, ldb, DB, GB, sharedB, wb, *rest):
     qmp_fused_bwd_source(N, out_ptr, out_dst, out_kin, xa, lda, DA, GA, _bwd_pack_from_image(wa, GA, _cap(DA, True)) if GA else None,
                          xb, ldb, DB, GB, sharedB, _bwd_pack_from_image(wb, GB, _cap(DB, False)), *rest)

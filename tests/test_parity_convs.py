@@ -382,7 +382,16 @@ def test_decoder_cell_backward_kernel_matches_per_conv_kernels(N, drop_p):
               FZ.tc_image(wb, 32, 2), 1, 32, dP, 128, o["logit"], o["mstat"], o["linv"], ds, a["dxa"], a["dxb"], drop_p, seed)
     _lib.call("qmp_fused_cell_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, FZ.cell_bwd_image(wa, wb), o["usave"],
               dP, 128, o["logit"], o["mstat"], o["linv"], b["ZsA"], b["dUsA"], b["ZsB"], b["dUsB"], b["dxa"], b["dxb"], drop_p, seed)
+    # ... and the one-pass mode of the per-conv target kernel (source side by vector reductions, no out-CSR launch)
+    c = outs()
+    _lib.call("qmp_fused_bwd_onepass_tc", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, 4, 4, FZ.tc_image(wa, 4, 1), xb, 32, 32, 4,
+              1, FZ.tc_image(wb, 32, 1), 1, 32, dP, 128, o["logit"], o["mstat"], o["linv"], z(max(E, 1), 8), c["ZsA"], c["dUsA"],
+              c["ZsB"], c["dUsB"], c["dxa"], c["dxb"], drop_p, seed)
     torch.cuda.synchronize()
+    for k in ("dxa", "dxb"):
+        assert not torch.isnan(c[k]).any(), f"one-pass {k}: NaN entries"
+        err = float((a[k] - c[k]).abs().max()) / max(float(a[k].abs().max()), 1e-6)
+        assert err < 5e-5, f"one-pass {k}: {err}"
     for k in a:
         va, vb = a[k], b[k]
         if k in ("ZsA", "dUsA"):          # column 7 / columns 6, 7 are padding
