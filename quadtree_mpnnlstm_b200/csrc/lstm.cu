@@ -457,11 +457,12 @@ __global__ void head_finish_fwd_kernel(const float* __restrict__ y, const float*
     }
 }
 
-// dy and dx0 from d_out (+ d_xnext[:, 0]); out is the forward result
+// dy and the whole gradient row dx [N, F] of the step's input x: column 0 from d_out (+ d_xnext[:, 0]), columns 1.. = d_xnext
+// (zeros without it); out is the forward result
 __global__ void head_finish_bwd_kernel(const float* __restrict__ y, const float* __restrict__ out, const float* __restrict__ x,
                                        const float* __restrict__ d_out, const float* __restrict__ d_xnext, int N, int F,
                                        int binary, float drop_p, unsigned long long seed, float* __restrict__ dy,
-                                       float* __restrict__ dx0) {
+                                       float* __restrict__ dx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float keep = 1.f;
@@ -476,7 +477,8 @@ __global__ void head_finish_bwd_kernel(const float* __restrict__ y, const float*
     if (binary) g *= out[i] * (1.f - out[i]);
     const float th = tanhf(y[i] * keep);
     dy[i] = g * (1.f - th * th) * keep;
-    dx0[i] = g;
+    dx[(size_t)i * F] = g;
+    for (int f = 1; f < F; ++f) dx[(size_t)i * F + f] = d_xnext ? d_xnext[(size_t)i * F + f] : 0.f;
 }
 
 __global__ void relu_mask_kernel(const float* __restrict__ y, float* __restrict__ dy, long long n) {
@@ -555,10 +557,10 @@ QMP_API int qmp_head_finish_fwd(const float* y, const float* x, int N, int F, in
 
 QMP_API int qmp_head_finish_bwd(const float* y, const float* out, const float* x, const float* d_out,
                                 const float* d_xnext, int N, int F, int binary, float drop_p, unsigned long long seed,
-                                float* dy, float* dx0, void* stream) {
+                                float* dy, float* dx, void* stream) {
     if (N <= 0) return 0;
     head_finish_bwd_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(y, out, x, d_out, d_xnext, N, F, binary,
-                                                                           drop_p, seed, dy, dx0);
+                                                                           drop_p, seed, dy, dx);
     QMP_LAUNCH_CHECK("qmp_head_finish_bwd");
     return 0;
 }

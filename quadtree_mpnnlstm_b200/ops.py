@@ -253,8 +253,6 @@ class HeadFinishFn(torch.autograd.Function):
         d_out = d_out.contiguous() if d_out is not None else None
         d_xnext = d_xnext.contiguous() if d_xnext is not None else None
         dy = torch.empty(N, 1, dtype=_f32, device=x.device)
-        dx = torch.zeros_like(x) if d_xnext is None else d_xnext.clone()
-        dx0 = torch.empty(N, dtype=_f32, device=x.device)
-        _lib.call("qmp_head_finish_bwd", y, out, x, d_out, d_xnext, N, F, binary, drop_p, seed, dy, dx0)
-        dx[:, 0] = dx0
+        dx = torch.empty_like(x)               # the kernel writes whole rows: column 0 and the pass-through columns
+        _lib.call("qmp_head_finish_bwd", y, out, x, d_out, d_xnext, N, F, binary, drop_p, seed, dy, dx)
         return dy, dx, None, None, None

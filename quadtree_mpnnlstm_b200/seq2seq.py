@@ -34,6 +34,19 @@ def _rnn_class(rnn_type):
     return GConvLSTM
 
 
+def _stack_layers(states):
+    """[L, N, C] from the per-layer states.  One layer (every ice configuration): a view -- torch.stack would copy the state
+    every timestep, and its backward plus the select below would add a zero fill and two more copies per timestep."""
+    return states[0].unsqueeze(0) if len(states) == 1 else torch.stack(states)
+
+
+def _layer_states(S, n_layers):
+    """Per-layer [N, C] states of a stacked [L, N, C] tensor (views; no select_backward zero fills for one layer)."""
+    if n_layers == 1 and S.dim() == 3 and S.shape[0] == 1:
+        return (S.view(S.shape[1], S.shape[2]),) if S.is_contiguous() else (S[0],)
+    return [S[i] for i in range(n_layers)]
+
+
 class Encoder(torch.nn.Module):
     def __init__(self, input_features, hidden_size, dropout, n_layers=1, convolution_type='GCNConv', rnn_type='LSTM',
                  n_conv_layers=3, dummy=False):
@@ -64,7 +77,7 @@ class Encoder(torch.nn.Module):
             hidden.append(h)
             cell.append(c)
             inp = h
-        return torch.stack(hidden), torch.stack(cell)
+        return _stack_layers(hidden), _stack_layers(cell)
 
 
 class Decoder(torch.nn.Module):
@@ -112,9 +125,10 @@ class Decoder(torch.nn.Module):
         csr = get_csr(edge_index, edge_weight, N)
         hidden, cell = [], []
         inp, head = X, None
+        Hs, Cs = _layer_states(H, self.n_layers), _layer_states(C, self.n_layers)
         for i in range(self.n_layers):
             top = i == self.n_layers - 1
-            _, h, c, head = self.rnns[i].fused(inp, csr, None, H=H[i], C=C[i], norm_h=self.norm_h, norm_c=self.norm_c,
+            _, h, c, head = self.rnns[i].fused(inp, csr, None, H=Hs[i], C=Cs[i], norm_h=self.norm_h, norm_c=self.norm_c,
                                                norm_o=self.norm_o if top else None,
                                                concat=concat_layers if top else None, want_head=top, epoch=epoch)
             hidden.append(h)
@@ -123,7 +137,7 @@ class Decoder(torch.nn.Module):
         y = self._gnn_out(head, csr, epoch)                 # fc_out1 -> relu -> fc_out2 (seq2seq.py:182-187)
         p = self.dropout.p if self.training else 0.0
         out, x_next = HeadFinishFn.apply(y, X, self.binary, p, next_seed() if p > 0 else 0)
-        hidden, cell = torch.stack(hidden), torch.stack(cell)
+        hidden, cell = _stack_layers(hidden), _stack_layers(cell)
         if _want_next:
             return out, hidden, cell, x_next
         return out, hidden, cell
@@ -252,8 +266,8 @@ class Seq2Seq(torch.nn.Module):
                 X=self.graph.pyg.x[t],
                 edge_index=self.graph.pyg.edge_index,
                 edge_weight=self.graph.pyg.edge_attr,
-                H=self.graph.hidden[-1] if self.graph.hidden is not None else None,
-                C=self.graph.cell[-1] if self.graph.cell is not None else None,
+                H=_layer_states(self.graph.hidden, self.encoder.n_layers)[-1] if self.graph.hidden is not None else None,
+                C=_layer_states(self.graph.cell, self.encoder.n_layers)[-1] if self.graph.cell is not None else None,
                 _epoch=self._epoch)
             self.graph.hidden = hidden
             self.graph.cell = cell

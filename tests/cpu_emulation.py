@@ -403,7 +403,7 @@ def qmp_head_finish_fwd(y, x, N, F, binary, drop_p, seed, out, x_next):
         xn[:, 0] = o
 
 
-def qmp_head_finish_bwd(y, out, x, d_out, d_xnext, N, F, binary, drop_p, seed, dy, dx0):
+def qmp_head_finish_bwd(y, out, x, d_out, d_xnext, N, F, binary, drop_p, seed, dy, dx):
     g = torch.zeros(N)
     if d_out is not None:
         g = g + flat(d_out, N)
@@ -414,7 +414,9 @@ def qmp_head_finish_bwd(y, out, x, d_out, d_xnext, N, F, binary, drop_p, seed, d
         g = g * o * (1 - o)
     th = torch.tanh(flat(y, N))
     flat(dy, N).copy_(g * (1 - th * th))
-    flat(dx0, N).copy_(g)
+    rows = flat(dx, N * F).view(N, F)
+    rows.copy_(flat(d_xnext, N * F).view(N, F) if d_xnext is not None else torch.zeros(N, F))
+    rows[:, 0] = g
 
 
 def qmp_relu_mask(y, dy, n):
