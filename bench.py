@@ -255,14 +255,21 @@ def run_gpu(args):
     # ---- host-buffer loop through the public API -> e2e (H2D of the step's inputs + D2H of the loss inside)
     hs = [host_sample(i) for i in range(args.steps)]
     h2d = sum(t.numel() * 4 for t in hs[0])
+
+    def host_loop(samples):
+        nxt = step.stage(*samples[0])           # pinned host -> device on a copy stream; sample i + 1 travels under step i
+        for i in range(len(samples)):
+            cur = nxt
+            loss_i = step(*cur)                 # -> the graph's static inputs -> replay (asynchronous)
+            if i + 1 < len(samples):
+                nxt = step.stage(*samples[i + 1])   # the next sample's copy is enqueued while this step runs
+            last = loss_i.item()                # the loss comes back to the host every step
+        return last
+
+    host_loop(hs[:2])                           # untimed: the copy stream's allocator pool and the staging path warm up
     barrier()
     e0.record()
-    nxt = step.stage(*hs[0])                    # pinned host -> device on a copy stream; sample i + 1 travels under step i
-    for i in range(args.steps):
-        cur = nxt
-        if i + 1 < args.steps:
-            nxt = step.stage(*hs[i + 1])
-        last = step(*cur).item()                # -> the graph's static inputs -> replay; the loss comes back every step
+    last = host_loop(hs)
     e1.record()
     barrier()
     ms2 = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)

@@ -79,6 +79,9 @@ __device__ __forceinline__ void tc_bwd_step(const FusedBwdArgs& a, int k, TcBSte
     }
 }
 
+// target kernel: (tile, conv) work items when no two convs share an input (encoder conv layers 1.., 8 blocks of 32)
+__host__ __device__ __forceinline__ bool tc_bwd_conv_items(const FusedBwdArgs& a) { return a.GA == 0 && !a.sharedB && a.GB > 1; }
+
 // ------------------------------------------------------------------------------------------------ target side
 template <int DC>
 __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs& a, int i, bool valid, const TcEdges& te,
@@ -461,6 +464,32 @@ __global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_const
     const int kfirst = (KIND == 2 && !a.need_dxa) ? a.GA : 0;
     const int kend = (KIND == 2 && !a.need_dxb) ? a.GA : a.NC;
     TcBStep st, nx;
+    if constexpr (KIND == 1 && DAC == 0) {
+        if (tc_bwd_conv_items(a)) {
+            // every conv reads its own input block and owns its own gradient block: the work items are (tile, conv) pairs,
+            // so 369 tiles x 8 convs spread over the 296 resident CTAs in 10 rounds of one conv instead of 2 rounds of 8
+            const int items = ntiles * a.NC;
+            if ((int)blockIdx.x < items) {
+                tc_bwd_step<DA_, DBC, KIND>(a, (int)blockIdx.x % a.NC, st);
+                if (t == 0) tc_prefetch_image(cx, 0, st.img, st.bytes);
+            }
+            for (int w = blockIdx.x; w < items; w += gridDim.x) {
+                const int i = (w / a.NC) * 128 + t;
+                const bool valid = i < a.N;
+                TcEdges te;
+                tc_load_edges(te, a.ptr, a.nbr, a.ea, i, valid);
+                const int wn = w + (int)gridDim.x;
+                tc_bwd_step<DA_, DBC, KIND>(a, w % a.NC, st);
+                tc_bwd_step<DA_, DBC, KIND>(a, (wn < items ? wn : w) % a.NC, nx);
+                conv_bwd_target_tc<DBC>(cx, a, i, valid, te, st, nx, wn < items);
+            }
+            if (cx.pending) tc_wait(cx);
+            tc::fence_before_sync();
+            __syncthreads();
+            if (warp == 0) tc::tmem_dealloc(cx.tmem, TC_COLS);
+            return;
+        }
+    }
     if ((int)blockIdx.x < ntiles && kfirst < kend) {
         tc_bwd_step<DA_, DBC, KIND>(a, kfirst, st);
         if (t == 0) tc_prefetch_image(cx, 0, st.img, st.bytes);
@@ -511,7 +540,8 @@ int launch_bwd_tc(const FusedBwdArgs& a, cudaStream_t st) {
     auto kern = fused_bwd_tc_kernel<DAC, DBC, KIND>;
     QMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = cdiv(a.N, 128);
-    const int grid = ntiles < 2 * n_sm ? ntiles : 2 * n_sm;
+    const int work = (KIND == 1 && DAC == 0 && tc_bwd_conv_items(a)) ? ntiles * a.NC : ntiles;
+    const int grid = work < 2 * n_sm ? work : 2 * n_sm;
     kern<<<grid, 128, smem, st>>>(a);
     QMP_LAUNCH_CHECK("fused_bwd_tc_kernel");
     return 0;
