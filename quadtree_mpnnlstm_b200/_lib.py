@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqmp_b200.so")
+LIB_PATH = os.environ.get("QMP_LIB_PATH") or os.path.join(_HERE, "libqmp_b200.so")   # override: kernel experiments (scripts/)
 
 _P, _I, _L, _F, _D, _U = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_uint64
 _CODES = {"p": _P, "i": _I, "l": _L, "f": _F, "d": _D, "u": _U}

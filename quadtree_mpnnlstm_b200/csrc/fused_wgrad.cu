@@ -84,6 +84,8 @@ static __device__ long long g_wg_trace[64];
 #define WG_MARK(k) do { } while (0)
 #endif
 
+// 96 registers: registers are handed out per warp PAIR, so two 9-warp CTAs per SM count as 20 warps (65536 / 20 / 32 = 102);
+// __maxnreg__(112) removed the spills of the hoisted per-item state but left ONE CTA per SM (measured: 94 -> 129 us)
 __global__ void __launch_bounds__(WG_THREADS, 2) fused_wgrad_kernel(const __grid_constant__ WgArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bar;
@@ -130,31 +132,68 @@ __global__ void __launch_bounds__(WG_THREADS, 2) fused_wgrad_kernel(const __grid
     const int ntiles = (a.N + WG_KT - 1) / WG_KT;
     const int items = (WG_KT / 4) * qb;
 
+    // Everything about this thread's loads that does not depend on the tile is resolved once, here: the loop body below is
+    // issue-bound (CTA timeline: 7 k of 8.9 k cycles per tile went into ISSUING the old fetch -- per-element bound checks,
+    // a five-way column-range dispatch and two integer divisions per item and tile), not latency- or bandwidth-bound.
     float va[WG_KH];
     float4 vb[WG_BIT][4];
+#pragma unroll
+    for (int k = 0; k < WG_KH; ++k) va[k] = 0.f;           // rows without a source stay zero
+    const float* b_ptr[WG_BIT];                            // fast items (whole 16-byte chunks of an aligned row): chunk of node 0
+    int b_ld[WG_BIT], b_kg[WG_BIT];
+    uint32_t b_off[WG_BIT];                                // byte offset of the item's 4 x 4 block in the B tile
+#pragma unroll
+    for (int it = 0; it < WG_BIT; ++it) {
+        const int idx = t + WG_WORKERS * it;
+        const bool on = idx < items;
+        const int kg = on ? idx / qb : 0, q = on ? idx - kg * qb : 0;
+        b_kg[it] = kg;
+        b_off[it] = (uint32_t)(((q * 4) >> 3) * WG_SBO + kg * 128 + ((q * 4) & 7) * 16);
+        b_ptr[it] = nullptr; b_ld[it] = 0;
+        if (on && q != q_one) {
+            if (q < q_one) { if (vx0 && cv.p[0].D - q * 4 >= 4) { b_ptr[it] = cv.p[0].x + q * 4; b_ld[it] = cv.p[0].ldx; } }
+            else if (q < q_x1) { b_ptr[it] = cv.p[0].zs + (q - q_z0) * 4; b_ld[it] = cv.p[0].ldz; }
+            else if (q < q_z1) { if (vx1 && cv.p[1].D - (q - q_x1) * 4 >= 4) { b_ptr[it] = cv.p[1].x + (q - q_x1) * 4; b_ld[it] = cv.p[1].ldx; } }
+            else { b_ptr[it] = cv.p[1].zs + (q - q_z1) * 4; b_ld[it] = cv.p[1].ldz; }
+        }
+    }
     auto fetch = [&](int tile) {
         const int n0 = tile * WG_KT;
+        const bool full = n0 + WG_KT <= a.N;               // all but the last tile: no bound checks
+        if (a_src != nullptr) {
+            const float* p = a_src + (size_t)(n0 + half * WG_KH) * a_ld;
+            if (full) {
 #pragma unroll
-        for (int k = 0; k < WG_KH; ++k) {
-            const int i = n0 + half * WG_KH + k;
-            va[k] = (a_src != nullptr && i < a.N) ? __ldg(a_src + (size_t)i * a_ld) : 0.f;
+                for (int k = 0; k < WG_KH; ++k) va[k] = __ldg(p + (size_t)k * a_ld);
+            } else {
+#pragma unroll
+                for (int k = 0; k < WG_KH; ++k) va[k] = (n0 + half * WG_KH + k < a.N) ? __ldg(p + (size_t)k * a_ld) : 0.f;
+            }
         }
 #pragma unroll
         for (int it = 0; it < WG_BIT; ++it) {
-            const int idx = t + WG_WORKERS * it;
+            if (b_ptr[it] != nullptr && full) {
+                const float* p = b_ptr[it] + (size_t)(n0 + b_kg[it] * 4) * b_ld[it];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) vb[it][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < items) {
-                const int kg = idx / qb, q = idx - kg * qb;
+                for (int j = 0; j < 4; ++j) vb[it][j] = __ldg(reinterpret_cast<const float4*>(p + (size_t)j * b_ld[it]));
+            } else {                                       // the ones column, ragged rows, the last tile, no item
+                const int idx = t + WG_WORKERS * it;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int i = n0 + kg * 4 + j;
-                    if (i < a.N) {
-                        if (q < q_one) vb[it][j] = wg_load4(cv.p[0].x + (size_t)i * cv.p[0].ldx + q * 4, cv.p[0].D - q * 4, vx0);
-                        else if (q == q_one) vb[it][j].x = 1.f;
-                        else if (q < q_x1) vb[it][j] = wg_load4(cv.p[0].zs + (size_t)i * cv.p[0].ldz + (q - q_z0) * 4, 4, true);
-                        else if (q < q_z1) vb[it][j] = wg_load4(cv.p[1].x + (size_t)i * cv.p[1].ldx + (q - q_x1) * 4, cv.p[1].D - (q - q_x1) * 4, vx1);
-                        else vb[it][j] = wg_load4(cv.p[1].zs + (size_t)i * cv.p[1].ldz + (q - q_z1) * 4, 4, true);
+                for (int j = 0; j < 4; ++j) vb[it][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (idx < items) {
+                    const int kg = b_kg[it], q = idx - kg * qb;
+#pragma unroll 1
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = n0 + kg * 4 + j;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (i < a.N) {
+                            if (q < q_one) v = wg_load4(cv.p[0].x + (size_t)i * cv.p[0].ldx + q * 4, cv.p[0].D - q * 4, vx0);
+                            else if (q == q_one) v.x = 1.f;
+                            else if (q < q_x1) v = wg_load4(cv.p[0].zs + (size_t)i * cv.p[0].ldz + (q - q_z0) * 4, 4, true);
+                            else if (q < q_z1) v = wg_load4(cv.p[1].x + (size_t)i * cv.p[1].ldx + (q - q_x1) * 4, cv.p[1].D - (q - q_x1) * 4, vx1);
+                            else v = wg_load4(cv.p[1].zs + (size_t)i * cv.p[1].ldz + (q - q_z1) * 4, 4, true);
+                        }
+                        if (j == 0) vb[it][0] = v; else if (j == 1) vb[it][1] = v; else if (j == 2) vb[it][2] = v; else vb[it][3] = v;
                     }
                 }
             }
@@ -178,11 +217,8 @@ __global__ void __launch_bounds__(WG_THREADS, 2) fused_wgrad_kernel(const __grid
         // B -> shared memory, K-major: element (n, node k) at (n/8)*SBO + (k/4)*128 + (n%8)*16 + (k%4)*4
 #pragma unroll
         for (int it = 0; it < WG_BIT; ++it) {
-            const int idx = t + WG_WORKERS * it;
-            if (idx < items) {
-                const int kg = idx / qb, q = idx - kg * qb;
-                const int n = q * 4;
-                const uint32_t base = (uint32_t)((n >> 3) * WG_SBO + kg * 128 + (n & 7) * 16);
+            if (t + WG_WORKERS * it < items) {
+                const uint32_t base = b_off[it];
                 wg_st_split(b_hi, b_lo, base, vb[it][0].x, vb[it][1].x, vb[it][2].x, vb[it][3].x);
                 wg_st_split(b_hi, b_lo, base + 16, vb[it][0].y, vb[it][1].y, vb[it][2].y, vb[it][3].y);
                 wg_st_split(b_hi, b_lo, base + 32, vb[it][0].z, vb[it][1].z, vb[it][2].z, vb[it][3].z);
