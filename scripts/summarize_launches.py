@@ -13,9 +13,13 @@ def main(path, top=30):
     hdr = next(r)
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     tot, cnt = collections.defaultdict(float), collections.Counter()
-    for row in r:
-        if len(row) <= vi:
-            continue
+    rows = [row for row in r if len(row) > vi]
+    # exactly one optimizer step: from one loss kernel (once per step) to the next
+    marks = [i for i, row in enumerate(rows) if "mse_kernel_cuda" in row[ki]]
+    if len(marks) >= 2:
+        rows = rows[marks[0]:marks[1]]
+        print(f"# one optimizer step: launches {marks[0]}..{marks[1]} of the capture (loss kernel to loss kernel)")
+    for row in rows:
         v = float(row[vi].replace(",", ""))
         v = v / 1e3 if row[ui] == "ns" else v * 1e3 if row[ui] == "ms" else v
         name = re.sub(r"\(.*", "", row[ki])[:80]
