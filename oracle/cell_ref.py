@@ -2,7 +2,7 @@
 
 ``GraphConv`` = model/model.py:59-97 (a chain of convs with no nonlinearity between; the third
 positional argument is the edge weight for GCN/Cheb and the edge attribute for Transformer).
-``GConvLSTM`` = model/model.py:263-463.  ``MPNNLSTM`` = model/model.py:613-684 (legacy, API only).
+``GConvLSTM`` = model/model.py:263-463.  ``GConvGRU`` = model/model.py:100-259.  ``MPNNLSTM`` = model/model.py:613-684 (legacy, API only).
 Module / parameter names follow the reference so state dicts are interchangeable; creation
 order follows model/model.py:294-373 so a shared seed gives identical initial weights.
 """
@@ -73,6 +73,36 @@ class GConvLSTM(nn.Module):
         C = Fg * C + I * T
         O = torch.sigmoid(self._pre("o", X, edge_index, edge_weight, H) + self.w_c_o * C + self.b_o)
         return O, O * torch.tanh(C), C
+
+
+class GConvGRU(nn.Module):
+    """Graph-convolutional GRU cell (model/model.py:100-259):
+
+        Z  = sigmoid(conv_x_z(X) + conv_h_z(H))                 update gate        (:215-219)
+        R  = sigmoid(conv_x_r(X) + conv_h_r(H))                 reset gate         (:221-225)
+        H~ = tanh   (conv_x_h(X) + conv_h_h(H * R))             candidate state    (:227-231)
+        H' = Z * H + (1 - Z) * H~                               returns (H', H', None)   (:233-259)
+
+    No biases or peepholes of its own; ``C`` is accepted and ignored (LSTM compatibility, :243).  The constructor takes no
+    ``name`` argument (:133-139), which is why ``Seq2Seq(rnn_type='GRU')`` fails in the reference (seq2seq.py:43 passes one).
+    Creation order z, r, h with x before h (:149-208)."""
+
+    def __init__(self, in_channels, out_channels, n_conv_layers=1, convolution_type="GCNConv"):
+        super().__init__()
+        assert convolution_type in CONVOLUTIONS
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.n_conv_layers, self.convolution_type = n_conv_layers, convolution_type
+        for g in ("z", "r", "h"):
+            setattr(self, f"conv_x_{g}", GraphConv(convolution_type, in_channels, out_channels, n_conv_layers))
+            setattr(self, f"conv_h_{g}", GraphConv(convolution_type, out_channels, out_channels, n_conv_layers))
+
+    def forward(self, X, edge_index, edge_weight=None, H=None, C=None):
+        H = torch.zeros(X.shape[0], self.out_channels) if H is None else H
+        Z = torch.sigmoid(self.conv_x_z(X, edge_index, edge_weight) + self.conv_h_z(H, edge_index, edge_weight))
+        R = torch.sigmoid(self.conv_x_r(X, edge_index, edge_weight) + self.conv_h_r(H, edge_index, edge_weight))
+        Ht = torch.tanh(self.conv_x_h(X, edge_index, edge_weight) + self.conv_h_h(H * R, edge_index, edge_weight))
+        H = Z * H + (1 - Z) * Ht
+        return H, H, None
 
 
 class MPNNLSTM(nn.Module):

@@ -6,7 +6,7 @@ module surface, on hand-written sm_100a CUDA reached through a C ABI (``include/
 """
 from .graph_functions import (Graph, Mesh, create_static_heterogeneous_graph, create_static_homogeneous_graph,  # noqa: F401
                               flatten, image_to_graph, image_to_graph_pixelwise, plot_contours, unflatten)
-from .model import CONVOLUTION_KWARGS, CONVOLUTIONS, GConvLSTM, GraphConv, MPNNLSTM, MPNNLSTMI  # noqa: F401
+from .model import CONVOLUTION_KWARGS, CONVOLUTIONS, GConvGRU, GConvLSTM, GraphConv, MPNNLSTM, MPNNLSTMI  # noqa: F401
 from .seq2seq import Decoder, Encoder, Seq2Seq  # noqa: F401
 from .mpnnlstm import DeviceWindowDataset, NextFramePredictor, NextFramePredictorS2S  # noqa: F401
 from .utils import add_positional_encoding, get_n_params, int_to_datetime, normalize  # noqa: F401

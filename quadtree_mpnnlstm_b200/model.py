@@ -240,6 +240,39 @@ class GConvLSTM(nn.Module):
         return O, Hn, Cn
 
 
+class GConvGRU(nn.Module):
+    r"""Graph-convolutional GRU cell, the reference's alternative to ``GConvLSTM`` (model/model.py:100-259): same constructor
+    (no ``name`` argument, :133-139), same six ``conv_{x,h}_{z,r,h}`` stacks and state-dict keys, ``forward`` returns
+    ``(H', H', None)`` and ignores ``C`` (:236-259).
+
+    The six conv stacks run on the qmp kernels (``GraphConv`` -> ``convs.py``: CSR message passing + node GEMMs, forward and
+    backward); the gate arithmetic is three element-wise expressions on their outputs.  ``conv_h_h`` reads ``H * R``, i.e. it
+    depends on the reset gate, so unlike the LSTM cell the six stacks cannot all be batched into one group per layer:
+    ``conv_x_*`` and ``conv_h_{z,r}`` first, ``conv_h_h`` after the reset gate."""
+
+    def __init__(self, in_channels, out_channels, n_conv_layers=1, convolution_type='GCNConv'):
+        super(GConvGRU, self).__init__()
+        assert convolution_type in CONVOLUTIONS
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.n_conv_layers = n_conv_layers
+        self.convolution_type = convolution_type
+        for g in ("z", "r", "h"):      # creation order follows model/model.py:149-208 (same RNG stream for a seed)
+            setattr(self, f"conv_x_{g}", GraphConv(convolution_type, in_channels, out_channels, n_conv_layers))
+            setattr(self, f"conv_h_{g}", GraphConv(convolution_type, out_channels, out_channels, n_conv_layers))
+
+    def forward(self, X, edge_index, edge_weight=None, H=None, C=None):
+        """Returns (H', H', None) like the reference (model/model.py:236-259)."""
+        X = X.float()
+        if H is None:
+            H = torch.zeros(X.shape[0], self.out_channels, device=X.device)
+        Z = torch.sigmoid(self.conv_x_z(X, edge_index, edge_weight) + self.conv_h_z(H, edge_index, edge_weight))
+        R = torch.sigmoid(self.conv_x_r(X, edge_index, edge_weight) + self.conv_h_r(H, edge_index, edge_weight))
+        Ht = torch.tanh(self.conv_x_h(X, edge_index, edge_weight) + self.conv_h_h(H * R, edge_index, edge_weight))
+        Hn = Z * H + (1 - Z) * Ht
+        return Hn, Hn, None
+
+
 class MPNNLSTM(nn.Module):
     """Legacy model kept for API compatibility (model/model.py:613-684): three GCNConv blocks per frame,
     ``nn.LSTM`` over time, skip connection, two linears.  The graph convolutions run on the qmp kernels;

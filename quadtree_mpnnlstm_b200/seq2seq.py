@@ -28,6 +28,12 @@ from .utils import add_positional_encoding
 
 def _rnn_class(rnn_type):
     assert rnn_type in ['GRU', 'LSTM', 'SplitLSTM']
+    if rnn_type == 'GRU':
+        # the reference cannot build this either: Encoder / Decoder pass name=... (seq2seq.py:43-44, 108-109) to
+        # GConvGRU.__init__, which has no such argument (model/model.py:133-139) -> TypeError.  The cell itself is
+        # available stand-alone as model.GConvGRU.
+        raise TypeError("GConvGRU.__init__() got an unexpected keyword argument 'name' (rnn_type='GRU' fails the same way "
+                        "in the reference driver; use model.GConvGRU directly)")
     if rnn_type != 'LSTM':
         raise NotImplementedError(f"rnn_type={rnn_type!r}: only the LSTM cell is on the hot path (every reference "
                                   "config uses rnn_type='LSTM'; SURVEY.md section 2)")

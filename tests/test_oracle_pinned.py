@@ -76,3 +76,34 @@ def test_seq2seq_sweep(ref, conv, thresh):
             assert pb.grad is None or float(pb.grad.abs().max()) < 1e-6, k
         else:
             assert float((pa.grad - pb.grad).abs().max()) <= 1e-4 * float(pa.grad.abs().max()) + 1e-7, k
+
+
+@pytest.mark.parametrize("conv,n_conv_layers", [("TransformerConv", 1), ("ChebConv", 2), ("GCNConv", 3)])
+def test_gru_cell(ref, conv, n_conv_layers):
+    """The oracle's GConvGRU against the unmodified reference cell (model/model.py:100-259): same parameter names and
+    creation order (same weights for a seed), outputs and gradients."""
+    from oracle import cell_ref as R
+    rng = np.random.default_rng(5)
+    img = rng.random((1, 16, 20, 1)).astype(np.float32) * (rng.random((1, 16, 20, 1)) > 0.8)
+    g = G.image_to_graph(G.add_positional_encoding(torch.from_numpy(img)), thresh=0.4, max_grid_size=8,
+                         use_edge_attrs=(conv == "TransformerConv"))
+    ei, ea, n = g["edge_index"], g["edge_attrs"], g["data"].shape[1]
+    torch.manual_seed(9)
+    a = ref.model.GConvGRU(4, 16, n_conv_layers, conv).eval()
+    torch.manual_seed(9)
+    b = R.GConvGRU(4, 16, n_conv_layers, conv).eval()
+    for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert ka == kb and torch.equal(pa, pb), (ka, kb)
+    X, H = torch.randn(n, 4), torch.randn(n, 16)
+    xa, ha = X.clone().requires_grad_(True), H.clone().requires_grad_(True)
+    xb, hb = X.clone().requires_grad_(True), H.clone().requires_grad_(True)
+    oa, ob = a(xa, ei, ea, ha), b(xb, ei, ea, hb)
+    assert oa[2] is None and ob[2] is None
+    assert rel_err(ob[0], oa[0]) < 1e-5
+    (oa[0] ** 2).sum().backward()
+    (ob[0] ** 2).sum().backward()
+    assert rel_err(xb.grad, xa.grad) < 1e-5 and rel_err(hb.grad, ha.grad) < 1e-5
+    for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        if pa.grad is not None:
+            assert float((pa.grad - pb.grad).abs().max()) <= 1e-4 * float(pa.grad.abs().max()) + 1e-7, k
+    assert rel_err(b(X, ei, ea)[0], a(X, ei, ea)[0]) < 1e-5

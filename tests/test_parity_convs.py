@@ -144,6 +144,40 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     assert rel_err(ob0[1], oa0[1]) < TOL
 
 
+@pytest.mark.parametrize("conv,n_conv_layers,f_in,hid", [("TransformerConv", 1, 4, 32), ("TransformerConv", 2, 8, 16),
+                                                         ("ChebConv", 2, 4, 16), ("GCNConv", 1, 5, 8)])
+def test_gconv_gru_cell(be, conv, n_conv_layers, f_in, hid):
+    """GConvGRU (model/model.py:100-259) on the qmp conv kernels against the oracle restatement (pinned against the
+    unmodified reference cell in test_oracle_pinned.py): forward, input gradients, every parameter gradient, H=None."""
+    import quadtree_mpnnlstm_b200.model as M
+    from oracle import cell_ref as R
+    ei, ea, n = _graph(5, use_edge_attrs=(conv == "TransformerConv"))
+    torch.manual_seed(13)
+    ref = R.GConvGRU(f_in, hid, n_conv_layers, conv).eval()
+    gpu = be.dev(M.GConvGRU(f_in, hid, n_conv_layers, conv)).eval()
+    assert [k for k, _ in ref.named_parameters()] == [k for k, _ in gpu.named_parameters()]
+    gpu.load_state_dict(ref.state_dict())
+    X, H = torch.randn(n, f_in), torch.randn(n, hid)
+    ins_a = [t.clone().requires_grad_(True) for t in (X, H)]
+    ins_b = [be.dev(t.clone()).requires_grad_(True) for t in (X, H)]
+    dev_ea = be.dev(ea) if ea is not None else None
+    oa = ref(ins_a[0], ei, ea, ins_a[1])
+    ob = gpu(ins_b[0], be.dev(ei), dev_ea, ins_b[1], C=None)
+    assert oa[2] is None and ob[2] is None and ob[0] is ob[1]
+    assert rel_err(ob[0], oa[0]) < TOL, rel_err(ob[0], oa[0])
+    w = torch.randn_like(oa[0])
+    (oa[0] * w).sum().backward()
+    (ob[0] * be.dev(w)).sum().backward()
+    for a, b, name in zip(ins_a, ins_b, ("dX", "dH")):
+        assert rel_err(b.grad, a.grad) < 1e-4, f"{name}: {rel_err(b.grad, a.grad)}"
+    for (k, pa), (_, pb) in zip(ref.named_parameters(), gpu.named_parameters()):
+        ga = pa.grad if pa.grad is not None else torch.zeros_like(pa)
+        gb = pb.grad if pb.grad is not None else torch.zeros_like(pb)
+        diff = float((ga - gb.cpu()).abs().max())
+        assert diff / max(float(ga.abs().max()), 1e-3) < 2e-4 or diff < 2e-5, f"grad {k}: abs {diff}"
+    assert rel_err(gpu(be.dev(X), be.dev(ei), dev_ea)[0], ref(X, ei, ea)[0]) < TOL      # H=None -> zeros
+
+
 @pytest.mark.parametrize("tensor_cores", [1, 0])
 def test_gemm_kernels(be, tensor_cores):
     """Dense contractions: tcgen05 3xTF32 path (default for n >= 256) and the FFMA fallback."""
