@@ -435,3 +435,75 @@ def test_decoder_cell_backward_kernel_matches_per_conv_kernels(N, drop_p):
         assert not torch.isnan(vb).any(), f"{k}: unwritten / NaN entries"
         err = float((va - vb).abs().max()) / max(float(va.abs().max()), 1e-6)
         assert err < 5e-5, f"{k}: {err}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 333, 47200])
+@pytest.mark.parametrize("DA,GA,DB,GB,shared,mode", [(0, 0, 36, 1, 1, 0),      # decoder head conv fc_out1 (36-wide rows)
+                                                      (0, 0, 32, 8, 0, 0),      # encoder conv layer 1: (tile, conv) work items
+                                                      (0, 0, 32, 8, 0, 1),      # encoder conv layer 2 (gate mode)
+                                                      (8, 4, 32, 4, 1, 0)])     # encoder conv layer 0: X convs need no dx
+def test_onepass_backward_matches_target_plus_source(N, DA, GA, DB, GB, shared, mode):
+    """qmp_fused_bwd_onepass_tc (source side of every in-edge by vector reductions inside the target kernel)
+    against qmp_fused_bwd_target_tc + qmp_fused_bwd_source_tc on the same inputs, at the bench size too: input gradients and
+    the rows for the weight-gradient kernel.  Ragged in-degrees 0..9 (0..4 at the full size), isolated nodes, partial tiles,
+    attention dropout; the softmax statistics are made consistent with random logits on the host."""
+    from quadtree_mpnnlstm_b200 import _lib, fused as FZ
+    from quadtree_mpnnlstm_b200.graph_csr import get_csr
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(N + 31 * DB + GB)
+    deg = torch.randint(0, 10, (N,), generator=g)
+    if N > 20000:
+        deg = deg.clamp(max=4)
+    dst = torch.repeat_interleave(torch.arange(N), deg)
+    E = int(dst.numel())
+    src = torch.randint(0, N, (E,), generator=g)
+    csr = get_csr(torch.stack([src, dst]).to(dev), torch.rand(E, 2, generator=g).to(dev), N)
+    NC, C = GA + GB, 32
+    dac, dbc = (4 if DA <= 4 else 8) if GA else 0, (32 if DB <= 32 else 36)
+    xa = torch.randn(N, DA, generator=g).to(dev) if GA else None
+    xb = torch.randn(N, DB if shared else GB * DB, generator=g).to(dev)
+    wa = (torch.randn(GA, FZ.conv_total(dac), generator=g) * 0.3).to(dev) if GA else None
+    wb = (torch.randn(GB, FZ.conv_total(dbc), generator=g) * 0.2).to(dev)
+    lddp = 128 if mode == 1 else NC * C
+    dP = torch.randn(N, lddp, generator=g).to(dev)
+    # logits in in-CSR order; m = segment max, linv = 1 / segment sum of exp(logit - m)
+    logit = torch.randn(max(E, 1), NC, generator=g).to(dev)
+    ptr = csr.in_ptr.long()
+    seg = torch.repeat_interleave(torch.arange(N, device=dev), ptr[1:] - ptr[:-1])
+    mstat = torch.full((N, NC), -1e30, device=dev).scatter_reduce(0, seg[:, None].expand(E, NC), logit[:E], "amax")
+    ssum = torch.zeros(N, NC, device=dev).index_add_(0, seg, (logit[:E] - mstat[seg]).exp())
+    linv = torch.where(ssum > 0, 1.0 / ssum.clamp(min=1e-30), torch.zeros_like(ssum))
+    z = lambda *s: torch.full(s, float("nan"), device=dev)
+    drop_p, seed = (0.1 if N == 333 else 0.0), 777
+
+    def outs():
+        o = dict(ZsB=z(N, GB, dbc + 4), dUsB=z(N, GB, dbc + 4), dxb=z(*xb.shape), ds=z(max(E, 1), NC))
+        o.update(ZsA=z(N, GA, dac + 4), dUsA=z(N, GA, dac + 4)) if GA else o.update(ZsA=None, dUsA=None)
+        return o
+
+    a, b = outs(), outs()
+    head = (N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, DA, DA, GA)
+    mid = (xb, xb.shape[1], DB, GB, shared)
+    tail = (mode, C, dP, lddp, logit, mstat, linv)
+    img = lambda w, dc, kind: FZ.tc_image(w, dc, kind) if w is not None else None
+    _lib.call("qmp_fused_bwd_target_tc", *head, img(wa, dac, 1), *mid, img(wb, dbc, 1), *tail, a["ds"], a["ZsA"], a["dUsA"], a["ZsB"],
+              a["dUsB"], None, a["dxb"], drop_p, seed)
+    _lib.call("qmp_fused_bwd_source_tc", N, csr.out_ptr, csr.out_dst, csr.out_kin, xa, DA, DA, GA, img(wa, dac, 2), *mid, img(wb, dbc, 2),
+              *tail, a["ds"], None, a["dxb"], drop_p, seed)
+    _lib.call("qmp_fused_bwd_onepass_tc", *head, img(wa, dac, 1), *mid, img(wb, dbc, 1), *tail, b["ds"], b["ZsA"], b["dUsA"], b["ZsB"],
+              b["dUsB"], None, b["dxb"], drop_p, seed)
+    torch.cuda.synchronize()
+    for k in ("dxb", "ZsB", "dUsB", "ZsA", "dUsA"):
+        va, vb = a[k], b[k]
+        if va is None:
+            continue
+        if k in ("ZsB", "dUsB"):
+            va, vb = va[..., :dbc + (3 if k == "ZsB" else 2)], vb[..., :dbc + (3 if k == "ZsB" else 2)]
+        if k in ("ZsA", "dUsA"):
+            va, vb = va[..., :dac + (3 if k == "ZsA" else 2)], vb[..., :dac + (3 if k == "ZsA" else 2)]
+        if k == "dxb" and DB == 36:
+            va, vb = va[:, :DB], vb[:, :DB]
+        assert not torch.isnan(vb).any(), f"{k}: unwritten / NaN entries"
+        err = float((va - vb).abs().max()) / max(float(va.abs().max()), 1e-6)
+        assert err < 5e-5, f"{k}: {err}"
