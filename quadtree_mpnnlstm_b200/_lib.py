@@ -44,6 +44,7 @@ SIGNATURES = {
     "qmp_head_finish_fwd": "ppiiifuppp",
     "qmp_head_finish_bwd": "pppppiiifuppp",
     "qmp_relu_mask": "pplp",
+    "qmp_relu_mask_to": "ppplp",
     "qmp_tc_gemm_probe": "pppiiiip",
     "qmp_fused_fwd": "ippppiiippiiiipiiipippiiifppppppippppfup",
     "qmp_fused_bwd_target": "ippppiiippiiiipiipippppppppppfup",
@@ -72,7 +73,7 @@ KERNELS_PER_CALL = {
     "qmp_adjacency_pixelwise": 5, "qmp_edge_attrs": 1, "qmp_add_positional_encoding": 1,
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
-    "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
+    "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_relu_mask_to": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
     "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1, "qmp_fused_bwd_target_tc": 1, "qmp_fused_bwd_source_tc": 1, "qmp_fused_bwd_onepass_tc": 1,
     "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1, "qmp_tconv1_fwd": 2, "qmp_tconv1_bwd": 2, "qmp_fused_pack_cell_bwd": 1, "qmp_fused_cell_bwd": 1,
 }

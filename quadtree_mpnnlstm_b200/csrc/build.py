@@ -48,6 +48,7 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_head_finish_fwd": "model/seq2seq.py:167-178 (dropout, tanh, residual, sigmoid) and :427-428 (next input)",
     "qmp_head_finish_bwd": "autograd of the above",
     "qmp_relu_mask": "model/seq2seq.py:184 F.relu backward",
+    "qmp_relu_mask_to": "model/seq2seq.py:184 F.relu backward (out of place)",
     "qmp_fused_fwd": "model/model.py:394-463 GConvLSTM.forward around PyG TransformerConv + model/seq2seq.py:59-66, 138-165 (one launch)",
     "qmp_fused_bwd_target": "autograd of the above, target side",
     "qmp_fused_bwd_source": "autograd of the above, source side",

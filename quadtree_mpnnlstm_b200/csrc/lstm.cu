@@ -486,6 +486,20 @@ __global__ void relu_mask_kernel(const float* __restrict__ y, float* __restrict_
     if (i < n && !(y[i] > 0.f)) dy[i] = 0.f;
 }
 
+// out-of-place form: out = g where y > 0, else 0 (16-byte vectors when n and the pointers allow it)
+__global__ void relu_mask_to_kernel(const float* __restrict__ y, const float* __restrict__ g, float* __restrict__ out, long long n,
+                                    int vec) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        if (i * 4 >= n) return;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(y) + i), b = __ldg(reinterpret_cast<const float4*>(g) + i);
+        reinterpret_cast<float4*>(out)[i] = make_float4(a.x > 0.f ? b.x : 0.f, a.y > 0.f ? b.y : 0.f, a.z > 0.f ? b.z : 0.f,
+                                                        a.w > 0.f ? b.w : 0.f);
+    } else if (i < n) {
+        out[i] = y[i] > 0.f ? g[i] : 0.f;
+    }
+}
+
 }  // namespace qmp
 using namespace qmp;
 
@@ -570,5 +584,15 @@ QMP_API int qmp_relu_mask(const float* y, float* dy, long long n, void* stream) 
     if (n <= 0) return 0;
     relu_mask_kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(y, dy, n);
     QMP_LAUNCH_CHECK("qmp_relu_mask");
+    return 0;
+}
+
+// out[i] = g[i] where y[i] > 0, else 0: the backward of relu without the clone an in-place mask needs (autograd owns g)
+QMP_API int qmp_relu_mask_to(const float* y, const float* g, float* out, long long n, void* stream) {
+    if (n <= 0) return 0;
+    const int vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const long long work = vec ? n / 4 : n;
+    relu_mask_to_kernel<<<(unsigned)cdiv(work, 256), 256, 0, (cudaStream_t)stream>>>(y, g, out, n, vec);
+    QMP_LAUNCH_CHECK("qmp_relu_mask_to");
     return 0;
 }

@@ -90,8 +90,8 @@ def fused_group_backward(ctx, *grads):
     else:
         dP = c_(grads[0])
         if relu_out:
-            dP = dP.clone()
-            _lib.call("qmp_relu_mask", out_relu, dP, dP.numel())
+            g0, dP = dP, torch.empty_like(dP)
+            _lib.call("qmp_relu_mask_to", out_relu, g0, dP, dP.numel())
         lddp = NC * C
 
     need_dxa = GA > 0 and ctx.needs_input_grad[0]

@@ -419,6 +419,10 @@ def qmp_head_finish_bwd(y, out, x, d_out, d_xnext, N, F, binary, drop_p, seed, d
     rows[:, 0] = g
 
 
+def qmp_relu_mask_to(y, g, out, n):
+    flat(out, n).copy_(torch.where(flat(y, n) > 0, flat(g, n), torch.zeros(n)))
+
+
 def qmp_relu_mask(y, dy, n):
     d = flat(dy, n)
     d[~(flat(y, n) > 0)] = 0.0
