@@ -209,6 +209,10 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
+        # stdout carries exactly one JSON line: with NCCL_DEBUG=VERSION (set on the GPU boxes) NCCL prints its version banner
+        # there (NCCL_DEBUG_FILE does not move it); WARN keeps real diagnostics and drops the banner
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()   # fail loudly if the CUDA library is missing
 
