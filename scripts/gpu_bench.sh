@@ -7,7 +7,7 @@ rc=$?
 echo "bench rc=$rc"; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
 if [ $rc -eq 0 ]; then
   python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/plain.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -s 4500 -c 6000 --csv --log-file gpurun_out/launches.csv \
+  ncu --metrics gpu__time_duration.sum --clock-control none -s 4500 -c 4400 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
   echo "ncu launches rc=$?"; tail -2 gpurun_out/ncu_launch.log
   python scripts/kernel_times.py 2 3 > gpurun_out/plain2.log 2>&1 &&
