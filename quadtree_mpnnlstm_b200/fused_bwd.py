@@ -1,4 +1,5 @@
-"""Backward of FusedGroupFn: gate backward (qmp_lstm_gates_bwd) -> fused target / source kernels ->
+"""Backward of FusedGroupFn: gate backward (qmp_lstm_gates_bwd) -> decoder-cell kernel, or the one-pass per-conv kernel
+(target + source side of every edge in one launch; fused.ONEPASS_BWD = False: separate target / source launches) ->
 weight-gradient reductions (qmp_gemm_tn_acc) written straight into the padded pack layout."""
 from __future__ import annotations
 
