@@ -9,6 +9,7 @@ in the reference trainer, model/mpnnlstm.py:219-257).  One "step" = one sample.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference ...                      # the CPU oracle port on the host cores
+    python bench.py --mode infer --gpus N                     # configs[4]: rollout inference, launch dates sharded
 
 Under torchrun every rank trains on its own launch dates and the gradients are all-reduced over NCCL
 (data parallel, weak scaling).  One JSON line on stdout (rank 0).
@@ -32,6 +33,8 @@ sys.path.insert(0, ROOT)
 H, W, N_VARS, T_IN, T_OUT, HIDDEN = 229, 361, 5, 10, 90, 32
 FRAMES = T_IN + T_OUT
 METRIC = "graph-frames/sec MPNNLSTM fwd+bwd"
+WORKLOAD = ("ice_exp default (configs[1]): 229x361 grid, pixel-wise static mesh N=%d E=%d, TransformerConv hidden 32, "
+            "10+90 frames, batch 1, fwd+bwd+clip+Adam")
 
 
 def dist_from_05(arr):
@@ -107,36 +110,59 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_rate(threads, seconds_target=20.0, t_in=2, t_out=4):
-    """The oracle port (reference driver + cell restated, oracle/seq2seq_ref.py) on the host cores, on a bounded
-    sample of the same workload: the full 229 x 361 mesh, t_in + t_out frames instead of 10 + 90."""
+def oracle_frames_for_memory():
+    """(t_in, t_out) of the CPU oracle's timed samples.  The oracle's autograd tape of one full 10 + 90 sample is ~140 GB of
+    host memory (E x 32 edge tensors of 24 convs per encoder frame, 10 per decoder frame); on a host that cannot hold it the
+    sample keeps the encoder : decoder frame mix of the workload (1 : 9, so the per-frame cost is the same) with fewer frames."""
+    mem = host_memory_gb()
+    if mem >= 220:
+        return T_IN, T_OUT, mem
+    if mem >= 48:
+        return 2, 18, mem
+    return 1, 9, mem
+
+
+def cpu_oracle_rate(threads, max_samples=1, seconds_cap=150.0, dropout=0.1, t_in=T_IN, t_out=T_OUT):
+    """The oracle port (reference driver + cell restated, oracle/seq2seq_ref.py) on the host cores, on the SAME workload as the
+    GPU arm: full 10 + 90-frame samples on the full 229 x 361 mesh, train() mode (attention dropout 0.1 active, decoder dropout
+    as given), fwd + bwd + clip + Adam.  Bounded sample: a 1 + 1-frame mini-sample warms up (allocator, thread pool), then
+    ``max_samples`` full samples are timed (stops early once ``seconds_cap`` is exceeded)."""
     from oracle.seq2seq_ref import Seq2Seq as OSeq
     torch.set_num_threads(threads)
     mask = ocean_mask()
-    cube = synthetic_cube(t_in + t_out + 4)
-    clim = cube[..., :1].mean(0, keepdims=True).repeat(8, 0)
-    torch.manual_seed(21)
-    model = OSeq(**model_kwargs(t_in, t_out)).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    cube = synthetic_cube(t_in + t_out + max_samples + 4)
+    clim = np.ascontiguousarray(cube[..., :1].mean(0, keepdims=True).repeat(366, 0))
     keep = torch.from_numpy(~mask)
-    done, t0 = 0, None
-    for it in range(64):
-        x, y, cl = sample(cube, clim, it % 3, t_in, t_out)
+
+    def one(model, opt, day, t_in, t_out):
+        x, y, cl = sample(cube, clim, day, t_in, t_out)
         opt.zero_grad()
         out, _ = model(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(cl), teacher_forcing_ratio=0, mask=mask)
-        y_nodes = torch.from_numpy(y)[:, keep]
-        loss = torch.nn.functional.mse_loss(torch.stack(out), y_nodes)
+        loss = torch.nn.functional.mse_loss(torch.stack(out), torch.from_numpy(y)[:, keep])
         loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=10)
         opt.step()
-        if it == 0:
-            t0 = time.perf_counter()       # first sample = warm-up
-            continue
+        return float(loss)
+
+    torch.manual_seed(21)
+    warm = OSeq(**model_kwargs(1, 1, dropout)).train()
+    one(warm, torch.optim.Adam(warm.parameters(), lr=1e-4), 0, 1, 1)
+    del warm
+    torch.manual_seed(21)
+    model = OSeq(**model_kwargs(t_in, t_out, dropout)).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    done, t0 = 0, time.perf_counter()
+    for it in range(max_samples):
+        one(model, opt, it, t_in, t_out)
         done += 1
-        if time.perf_counter() - t0 > seconds_target:
+        if time.perf_counter() - t0 > seconds_cap:
             break
     dt = time.perf_counter() - t0
-    return done * (t_in + t_out) / dt, dt, done, f"{done} samples of {t_in}+{t_out} frames on the full 229x361 pixel-wise mesh (47200 nodes)"
+    what = (f"{done} sample(s) of {t_in}+{t_out} frames on the full 229x361 pixel-wise mesh (47200 nodes, 187808 edges), "
+            f"train mode, fwd+bwd+clip+Adam, after a 1+1-frame warm-up"
+            + ("" if (t_in, t_out) == (T_IN, T_OUT) else f"; same 1:9 encoder:decoder frame mix as 10+90, fewer frames because the "
+               f"oracle's autograd tape of a full sample (~140 GB) does not fit this host ({host_memory_gb():.0f} GB)"))
+    return done * (t_in + t_out) / dt, dt, done, what
 
 
 def run_reference(args):
@@ -145,13 +171,16 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     steps = max(1, args.steps)
-    rate, dt, done, what = cpu_oracle_rate(threads, seconds_target=min(60.0, 6.0 * steps))
+    t_in, t_out, _ = oracle_frames_for_memory()
+    rate, dt, done, what = cpu_oracle_rate(threads, max_samples=steps, seconds_cap=150.0, dropout=args.dropout, t_in=t_in, t_out=t_out)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "graph-frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(done, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ice_exp default (configs[1]): 229x361 pixel-wise mesh, TransformerConv, hidden 32",
+            "config": {"workload": WORKLOAD % (47200, 187808), "dropout": args.dropout, "cuda_graph": False,
+                       "parallelism": "cpu",
                        "note": "reference CPU path = oracle port (the reference itself cannot travel to the GPU box; "
-                               "torch-geometric is not installable): reference driver/cell restated + restated PyG convs"},
+                               "torch-geometric is not installable): reference driver/cell restated + restated PyG convs; "
+                               f"{done} of the {steps} requested steps timed (each step = one {t_in}+{t_out}-frame sample, bounded at 150 s)"},
             "cpu_baseline": {"value": rate, "unit": "graph-frames/s", "cores": threads, "kind": "port", "sample": what},
             "e2e": {"value": rate, "unit": "graph-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -159,61 +188,264 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def cell_roofline(model, csr, dev, iters=20):
-    """Time the roofline kernel of the step -- the decoder-cell forward (qmp_fused_cell_fwd: 8 TransformerConvs'
-    message passing over the CSR + their gate contractions on tcgen05 + the LSTM gate epilogue, ONE launch per
-    forecast step) -- alone with CUDA events on the launching stream, flushing L2 between launches.
-    Algorithmic bytes per launch: DESIGN.md section 5 (inputs X, H, C + CSR + edge attributes; outputs O, H', C',
-    head input; activations saved for the backward pass: gates, raw cell state, edge logits, softmax statistics)."""
-    from quadtree_mpnnlstm_b200 import _lib, fused
-    N, E, C = csr.n_nodes, csr.n_edges, HIDDEN
-    cell = model.decoder.rnns[0]
-    F_in = cell.in_channels
-    with torch.no_grad():
-        pa, pb = fused.pack_fused(cell._convs("x", 0), fused.cap_of(F_in, True)), fused.pack_fused(cell._convs("h", 0), C)
-        img = fused.cell_image(pa, pb)
-        prm = cell._gate_params(-1, model.decoder.norm_h, model.decoder.norm_c, model.decoder.norm_o).contiguous()
-    f32 = dict(dtype=torch.float32, device=dev)
-    X, Hs, Cs, cc = torch.randn(N, F_in, **f32), torch.randn(N, C, **f32), torch.randn(N, C, **f32), torch.randn(N, **f32)
-    gates = torch.empty(N, 4 * C, **f32)
-    Craw, O, Hn, Cn = (torch.empty(N, C, **f32) for _ in range(4))
-    head = torch.empty(N, fused.HEADW, **f32)
-    logit, ms, li = torch.empty(E, 8, **f32), torch.empty(N, 8, **f32), torch.empty(N, 8, **f32)
-    usave = torch.empty(N, 4 * C, **f32)          # logit projections of the H convs, saved for qmp_fused_cell_bwd
+def host_memory_gb():
+    """Memory this process may use (cgroup limit when there is one, else what the host reports as available)."""
+    lim = None
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v.isdigit() and int(v) < (1 << 60):
+                lim = int(v)
+                break
+        except Exception:
+            pass
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = None
+    cands = [v for v in (lim, avail) if v]
+    return min(cands) / 2 ** 30 if cands else 0.0
+
+
+def algorithmic_bytes(N, E, C=HIDDEN, d_e=2):
+    """SURVEY.md section 8(d), verbatim: compulsory fp32 traffic per graph-frame of each part of the step."""
+    def b_f(F, S):
+        return 4 * (N * (F + 2 * C) + 3 * N * C) + 4 * (E + N + 1) + 4 * E * d_e + (S - 1) * 2 * 4 * 8 * N * C
+
+    def b_b(F, S):
+        return 4 * (3 * N * C + N * (F + 2 * C) + 6 * N * C) + 4 * (E + N + 1) + 4 * E * d_e + (S - 1) * 2 * 4 * 8 * N * C
+
+    saved = 4 * 6 * N * C
+    head = 4 * (N * (C + 1) + 2 * N * C + N)
+    return {"decoder_cell_fwd": b_f(4, 1) + saved,      # B_f + the gate activations a training forward must write
+            "decoder_cell_bwd": b_b(4, 1),              # gate backward + message-passing backward + weight gradients
+            "decoder_head_fwd": head,
+            "decoder_head_bwd": 2 * head,               # not in 8(d): inputs re-read + one gradient per forward tensor
+            "encoder_fwd": b_f(8, 3) + saved,
+            "encoder_bwd": b_b(8, 3)}
+
+
+def _classify(name, args):
+    """(group, short kernel key) of one C-ABI call of the training step."""
+    if name == "qmp_fused_cell_fwd":
+        return "decoder_cell_fwd", name
+    if name in ("qmp_fused_cell_bwd", "qmp_fused_cell_bwd_full"):
+        return "decoder_cell_bwd", name
+    if name == "qmp_lstm_gates_bwd":        # args: N C gates Craw Cp prm norm_h norm_c norm_o ...
+        return ("decoder_cell_bwd" if args[8] else "encoder_bwd"), name
+    if name.startswith("qmp_fused_fwd") or name.startswith("qmp_fused_bwd"):
+        DA, GA, DB, GB, mode = args[6], args[7], args[11], args[12], args[15]
+        key = f"{name}[DA={DA} GA={GA} DB={DB} GB={GB} mode={mode}]"
+        fwd = "_fwd" in name
+        if DB == 36:
+            return ("decoder_head_fwd" if fwd else "decoder_head_bwd"), key
+        if GA == 4 and DA == 4:
+            return ("decoder_cell_fwd" if fwd else "decoder_cell_bwd"), key
+        return ("encoder_fwd" if fwd else "encoder_bwd"), key
+    if name == "qmp_fused_wgrad":
+        DA, GA, DB, GB, mode = args[3], args[4], args[7], args[8], args[10]
+        key = f"{name}[DA={DA} GA={GA} DB={DB} GB={GB} mode={mode}]"
+        if DB == 36:
+            return "decoder_head_bwd", key
+        return ("decoder_cell_bwd" if (GA == 4 and DA == 4) else "encoder_bwd"), key
+    if name in ("qmp_tconv1_fwd", "qmp_head_finish_fwd"):
+        return "decoder_head_fwd", name
+    if name in ("qmp_tconv1_bwd", "qmp_head_finish_bwd", "qmp_relu_mask_to", "qmp_relu_mask"):
+        return "decoder_head_bwd", name
+    return "other", name
+
+
+def per_kernel_times(dev, mask, cube, clim, dropout, t_in=2, t_out=4, reps=2):
+    """Every C-ABI call of one eager training sample (full mesh, ``t_in + t_out`` frames) timed ALONE with CUDA events on the
+    launching stream, L2 flushed by a 256 MB write before each call.  Returns {key: (group, avg us, calls per frame)}."""
+    import quadtree_mpnnlstm_b200 as q
+    from quadtree_mpnnlstm_b200 import _lib
+    from quadtree_mpnnlstm_b200.train import TrainStep
+    torch.manual_seed(21)
+    model = q.Seq2Seq(**model_kwargs(t_in, t_out, dropout), device=dev).to(dev).train()
+    step = TrainStep(model, mask, lr=1e-4, use_cuda_graph=False)
+    smp = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in sample(cube, clim, 0, t_in, t_out)]
+    step(*smp)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
-    for k in range(iters + 3):
+    records, orig = [], _lib.call
+
+    def timed(name, *args):
         flush.zero_()
-        if k >= 3:
-            ev[k - 3][0].record()
-        _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, X, F_in, Hs, C, img, Cs, prm, 1, 1, 1, 1e-5,
-                  gates, Craw, O, Hn, Cn, head, fused.HEADW, cc, logit, ms, li, usave, 0.0, 0)
-        if k >= 3:
-            ev[k - 3][1].record()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(name, *args)
+        e1.record()
+        records.append((_classify(name, args), e0, e1))
+
+    _lib.call = timed
+    try:
+        for _ in range(reps):
+            step(*smp)
+    finally:
+        _lib.call = orig
     torch.cuda.synchronize()
-    ms_avg = sum(a.elapsed_time(b) for a, b in ev) / iters
-    reads = 4 * (N * (F_in + 2 * C) + N) + 4 * (N + 1 + E) + 8 * E          # X, H, C, concat; CSR; edge attributes
-    writes = 4 * (3 * N * C + N * fused.HEADW)                                # O, H', C', head input
-    saved = 4 * (4 * N * C + N * C + 8 * E + 16 * N + 4 * N * C)              # gates, raw C', logits, softmax max / 1/sum, u
-    return ms_avg, reads + writes + saved
+    tot, cnt = {}, {}
+    for (group, key), a, b in records:
+        tot[(group, key)] = tot.get((group, key), 0.0) + a.elapsed_time(b) * 1e3
+        cnt[(group, key)] = cnt.get((group, key), 0) + 1
+    out = {}
+    for (group, key), t in tot.items():
+        frames = t_in if group.startswith("encoder") else t_out
+        out[key] = (group, t / cnt[(group, key)], cnt[(group, key)] / (reps * frames))
+    N, E = int(model.graph.pyg.x.shape[0]), int(model.graph.pyg.edge_index.shape[1])
+    return out, N, E
+
+
+def roofline_report(times, N, E, hbm, peaks_known):
+    """Groups of section 8(d) with their live times; the roofline is reported on the group with the largest share of a
+    10 + 90-frame step (today: the decoder-cell backward)."""
+    bytes_of = algorithmic_bytes(N, E)
+    frames_of = lambda g: T_IN if g.startswith("encoder") else T_OUT
+    groups = {}
+    for key, (group, us, per_frame) in times.items():
+        g = groups.setdefault(group, {"us_per_frame": 0.0, "kernels": []})
+        g["us_per_frame"] += us * per_frame
+        g["kernels"].append({"kernel": key, "us": round(us, 2), "launches_per_frame": round(per_frame, 3)})
+    step_us = sum(g["us_per_frame"] * frames_of(name) for name, g in groups.items())
+    per_group = []
+    for name, g in sorted(groups.items(), key=lambda kv: -kv[1]["us_per_frame"] * frames_of(kv[0])):
+        row = {"group": name, "us_per_frame": round(g["us_per_frame"], 2), "frames_per_step": frames_of(name),
+               "share_of_step": round(g["us_per_frame"] * frames_of(name) / step_us, 4),
+               "kernels": sorted(g["kernels"], key=lambda k: -k["us"] * k["launches_per_frame"])}
+        if name in bytes_of:
+            gbs = bytes_of[name] / (g["us_per_frame"] * 1e-6) / 1e9
+            row.update({"algorithmic_bytes": bytes_of[name], "achieved_gbs": round(gbs, 1), "frac": round(gbs / hbm, 4)})
+        per_group.append(row)
+    top = next(r for r in per_group if "frac" in r)
+    traffic = None
+    try:      # dram bytes of the same kernels from the committed ncu --set full capture (profiles/), per frame
+        t = json.load(open(os.path.join(ROOT, "profiles", "roofline_kernel_traffic.json")))
+        traffic = t.get(top["group"], {}).get("dram_bytes_per_frame")
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": top["group"] + ": " + " + ".join(k["kernel"] for k in top["kernels"]),
+            "achieved": top["achieved_gbs"], "peak": hbm, "unit": "GB/s", "frac": top["frac"], "traffic": traffic,
+            "ms_per_launch": top["us_per_frame"] / 1e3, "algorithmic_bytes": top["algorithmic_bytes"],
+            "bytes_formula": "SURVEY.md 8(d): fwd B_f + 4*6NC, bwd B_b (F=4, C=32, S=1, d_e=2 for the decoder cell)",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks_known else "fallback 6650",
+            "whole_step_frac": None, "per_kernel": per_group}
+    return roof
+
+
+def extra_dynamic_quadtree(dev, mask, cube, clim, dropout, hbm):
+    """configs[2]: the ice grid with the quadtree rebuilt every forecast step (thresh 0.15, dist_from_05, 91 mesh builds per
+    sample, data-dependent N / E: eager), and the graph build alone against the HBM roofline (section 8(d) bytes)."""
+    import quadtree_mpnnlstm_b200 as q
+    from quadtree_mpnnlstm_b200.train import TrainStep
+    kw = model_kwargs(dropout=dropout)
+    kw["thresh"] = 0.15
+    torch.manual_seed(21)
+    model = q.Seq2Seq(**kw, device=dev).to(dev).train()
+    step = TrainStep(model, mask, lr=1e-4, use_cuda_graph=False)
+    smp = [[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in sample(cube, clim, d)] for d in range(3)]
+    step(*smp[0])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s_ in smp[1:]:
+        step(*s_)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / len(smp[1:])
+    # the graph build alone
+    img = q.add_positional_encoding(smp[0][0])
+    build = lambda: q.image_to_graph(img, thresh=0.15, mask=mask, transform_func=dist_from_05, use_edge_attrs=True)
+    g = build()
+    N, E = int(g["data"].shape[1]), int(g["edge_index"].shape[1])
+    torch.cuda.synchronize()
+    iters = 20
+    e0.record()
+    for _ in range(iters):
+        build()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / iters
+    P, c, T = H * W, int(img.shape[-1]), int(img.shape[0])
+    # 8(d): read image 4P per frame of the criterion channel (+ mask P), write labels 4P, edges 16E, attrs 4E*d_e; pool 4P*c in, 4N*c out
+    nbytes = 4 * P * T + P + 4 * P + 16 * E + 4 * E * 2 + T * (4 * P * c + 4 * N * c)
+    return {"workload": "configs[2]: 229x361, quadtree thresh 0.15 + dist_from_05 + mask, remesh every forecast step, 10+90 frames, "
+                        "fwd+bwd+clip+Adam, eager (data-dependent mesh)",
+            "graph_frames_per_s": FRAMES / (ms / 1e3), "ms_per_sample": ms,
+            "graph_build": {"us": us, "N": N, "E": E, "algorithmic_bytes": nbytes, "achieved_gbs": nbytes / (us * 1e-6) / 1e9,
+                            "frac_of_hbm_peak": nbytes / (us * 1e-6) / 1e9 / hbm,
+                            "what": "image_to_graph of the 10 input frames (quadtree + pixel lists + pooling + adjacency + edge attributes), wall per call incl. its one host read-back"}}
+
+
+def inference_setup(dev, mask, static_mesh=True):
+    import quadtree_mpnnlstm_b200 as q
+    torch.manual_seed(21)
+    model = q.Seq2Seq(**model_kwargs(), device=dev).to(dev).eval()
+    gs = (q.create_static_heterogeneous_graph((H, W), 4, mask, use_edge_attrs=True, resolution=1 / 12, device=dev)
+          if static_mesh else None)
+    return model, gs
+
+
+def extra_inference(dev, mask, cube, clim, n_dates=12):
+    """configs[4] (ice_inf.py:60): rollout inference on the static heterogeneous mesh (max cell 4), 10 + 90 frames per launch
+    date, no_grad, the whole rollout one CUDA-graph replay per launch date (infer.Rollout)."""
+    from quadtree_mpnnlstm_b200.infer import Rollout
+    model, gs = inference_setup(dev, mask)
+    ro = Rollout(model, mask, graph_structure=gs, use_cuda_graph=True)
+    xs = [[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in sample(cube, clim, d % 4)] for d in range(4)]
+    for d in range(4):                  # 2 eager warm-ups, the capture, one replay
+        ro(xs[d][0], xs[d][2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for d in range(n_dates):
+        out = ro(xs[d % 4][0], xs[d % 4][2])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_dates
+    return {"workload": "configs[4]: static heterogeneous mesh max cell 4 (N=%d, E=%d), 10+90 frames per launch date, no_grad, "
+                        "one CUDA-graph replay per date" % (int(gs["mapping"].n_nodes), int(gs["edge_index"].shape[1])),
+            "launch_dates_per_s": 1e3 / ms, "graph_frames_per_s": FRAMES * 1e3 / ms, "ms_per_launch_date": ms,
+            "qmp_launches_per_date": ro.launches_per_replay}
+
+
+def _init_dist(dev):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    return world
+
+
+def _finish(world):
+    """NCCL teardown with a captured graph still holding the communicator hung for the full time limit on a 2-GPU box (the JSON
+    line had already been printed): synchronise, meet once more, and leave without it."""
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
 
 
 def run_gpu(args):
     import torch.distributed as dist
     import quadtree_mpnnlstm_b200 as q
     from quadtree_mpnnlstm_b200 import _lib
-    from quadtree_mpnnlstm_b200.graph_csr import get_csr
 
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    if world > 1:
-        # stdout carries exactly one JSON line: with NCCL_DEBUG=VERSION (set on the GPU boxes) NCCL prints its version banner
-        # there (NCCL_DEBUG_FILE does not move it); WARN keeps real diagnostics and drops the banner
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+    world = _init_dist(dev)
     _lib.lib()   # fail loudly if the CUDA library is missing
 
     mask = ocean_mask()
@@ -284,54 +516,111 @@ def run_gpu(args):
     if rank == 0:
         value = args.steps * FRAMES * world / (ms_total / 1e3)
         e2e = args.steps * FRAMES * world / (ms_e2e / 1e3)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
+        peaks = _peaks()
         hbm = float(peaks.get("hbm_gbs", 6650.0))
-        if model.graph is not None:
-            topo = (model.graph.pyg.edge_index, model.graph.pyg.edge_attr, int(model.graph.pyg.x.shape[0]))
-        else:
-            topo = step.topology
-        csr = get_csr(*topo)
-        k_ms, k_bytes = cell_roofline(model, csr, dev)
-        traffic = None
-        try:      # dram bytes of the same kernel from the committed ncu --set full capture (profiles/), per launch
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_kernel_traffic.json")))["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        achieved = k_bytes / (k_ms * 1e-3) / 1e9
+        del step, model
+        torch.cuda.empty_cache()
+        times, N, E = per_kernel_times(dev, mask, cube, clim, args.dropout)
+        roof = roofline_report(times, N, E, hbm, bool(peaks))
+        # whole step against the 8(d) speed of light: every group's compulsory bytes x its frames, over the measured step
+        ab = algorithmic_bytes(N, E)
+        step_bytes = T_OUT * (ab["decoder_cell_fwd"] + ab["decoder_cell_bwd"] + ab["decoder_head_fwd"] + ab["decoder_head_bwd"]) \
+            + T_IN * (ab["encoder_fwd"] + ab["encoder_bwd"])
+        roof["whole_step_frac"] = round(step_bytes / (ms_total / args.steps * 1e-3) / 1e9 / hbm, 4)
+        roof["whole_step_algorithmic_bytes"] = step_bytes
         line = {"metric": METRIC, "value": value, "unit": "graph-frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "ice_exp default (configs[1]): 229x361 grid, pixel-wise static mesh N=%d E=%d, "
-                                       "TransformerConv hidden 32, 10+90 frames, batch 1, fwd+bwd+clip+Adam" % (csr.n_nodes, csr.n_edges),
-                           "dropout": args.dropout, "cuda_graph": not args.no_graph, "parallelism": f"dp{world}" if world > 1 else "single",
-                           "l2": "inputs + saved activations per step (~10 GB) exceed the 126 MB L2; roofline kernel "
-                                 "timed with a 256 MB flush write between launches",
+                "config": {"workload": WORKLOAD % (N, E),
+                           "dropout": args.dropout, "attention_dropout": 0.1, "cuda_graph": not args.no_graph,
+                           "parallelism": f"dp{world}" if world > 1 else "single",
+                           "l2": "inputs + saved activations per step (~10 GB) exceed the 126 MB L2; per-kernel times taken "
+                                 "with a 256 MB flush write before every launch",
                            "final_loss": last},
                 "e2e": {"value": e2e, "unit": "graph-frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches,
                 "clocks": clocks.summary(),
-                "roofline": {"bound": "hbm", "kernel": "fused_cell_fwd_kernel (decoder cell forward: 8 convs' message "
-                                                         "passing + tcgen05 gate contractions + LSTM epilogue, one launch)",
-                             "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                             "traffic": traffic, "ms_per_launch": k_ms, "algorithmic_bytes": k_bytes,
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650"}}
+                "roofline": roof}
+        if world == 1 and not args.no_extras:
+            extra = {}
+            for name, fn in (("dynamic_quadtree", lambda: extra_dynamic_quadtree(dev, mask, cube, clim, args.dropout, hbm)),
+                             ("inference", lambda: extra_inference(dev, mask, cube, clim))):
+                try:
+                    extra[name] = fn()
+                except Exception as exc:        # an extra must never take the headline line down with it
+                    extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                torch.cuda.empty_cache()
+            line["extra"] = extra
         if world == 1 and not args.no_cpu:
-            rate, dt, done, what = cpu_oracle_rate(os.cpu_count() or 1, seconds_target=15.0)
+            t_in, t_out, _ = oracle_frames_for_memory()
+            rate, dt, done, what = cpu_oracle_rate(os.cpu_count() or 1, max_samples=1, dropout=args.dropout, t_in=t_in, t_out=t_out)
             line["cpu_baseline"] = {"value": rate, "unit": "graph-frames/s", "cores": os.cpu_count() or 1,
-                                    "kind": "port", "sample": what}
+                                    "kind": "port", "sample": what, "same_config": (t_in, t_out) == (T_IN, T_OUT),
+                                    "same_frame_mix": True}
         print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def run_infer(args):
+    """configs[4] at N GPUs: launch dates sharded round-robin over the ranks (infer.predict_sharded: no data-path
+    collective, one all_gather of the forecasts at the end), every rank replaying its captured rollout per date."""
+    import torch.distributed as dist
+    from quadtree_mpnnlstm_b200 import _lib
+    from quadtree_mpnnlstm_b200.infer import Rollout, predict_sharded
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    world = _init_dist(dev)
+    _lib.lib()
+    mask = ocean_mask()
+    per_rank = max(args.steps, 1)
+    n_dates = per_rank * world
+    cube = synthetic_cube(FRAMES + 8)
+    clim = np.ascontiguousarray(cube[..., :1].mean(0, keepdims=True).repeat(366, 0))
+    model, gs = inference_setup(dev, mask, static_mesh=not args.pixel_mesh)
+    ro = Rollout(model, mask, graph_structure=gs, use_cuda_graph=not args.no_graph)
+    pinned = [[torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in sample(cube, clim, d)] for d in range(4)]
+
+    def load(d):                # host -> device inside the timed region (e2e: inputs start in pinned host memory)
+        x, _, cl = pinned[d % 4]
+        return x.to(dev, non_blocking=True), cl.to(dev, non_blocking=True)
+
+    for _ in range(max(args.warmup, 4)):        # eager warm-ups, the capture, a replay
+        ro(*load(0))
     if world > 1:
-        # NCCL teardown with a captured graph still holding the communicator hung for the full time limit on a 2-GPU
-        # box (the JSON line had already been printed): synchronise, meet once more, and leave without it.
-        torch.cuda.synchronize()
         dist.barrier()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    torch.cuda.synchronize()
+    launches0 = _lib.kernel_launches()
+    with ClockSampler(local) as clocks:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        full = predict_sharded(model, load, n_dates, mask, rank=rank, world=world, rollout=ro)
+        host = full[rank::world].cpu() if world > 1 else full.cpu()      # the forecasts come back to the host
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sec = float(ms) / 1e3
+        launches = ro.launches_per_replay * per_rank if ro.graph is not None else _lib.kernel_launches() - launches0
+        mesh = "static heterogeneous mesh max cell 4" if gs is not None else "pixel-wise mesh"
+        N = int(gs["mapping"].n_nodes) if gs is not None else 47200
+        line = {"metric": "launch-dates/sec rollout inference (10+90 frames per date)", "value": n_dates / sec, "unit": "launch-dates/s",
+                "graph_frames_per_s": n_dates * FRAMES / sec, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * sec / per_rank, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "mode": "infer",
+                "config": {"workload": f"ice_inf (configs[4]): 229x361, {mesh} N={N}, TransformerConv hidden 32, 10+90 frames per "
+                                       f"launch date, no_grad, {per_rank} launch dates per GPU, forecasts gathered + copied to the host",
+                           "cuda_graph": ro.graph is not None, "parallelism": f"dates/{world}"},
+                "e2e": {"value": n_dates / sec, "unit": "launch-dates/s",
+                        "h2d_bytes_per_step": sum(t.numel() * 4 for t in (pinned[0][0], pinned[0][2])),
+                        "d2h_bytes_per_step": int(host[0].numel() * 4)},
+                "gpu_launches": launches, "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    _finish(world)
 
 
 def main():
@@ -340,12 +629,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--dropout", type=float, default=0.0)
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--dropout", type=float, default=0.1, help="decoder dropout (ice_exp.py:155 trains with 0.1); the "
+                    "TransformerConv attention dropout is 0.1 in train mode regardless, as in the reference")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip extra.dynamic_quadtree / extra.inference")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
+    ap.add_argument("--pixel-mesh", action="store_true", help="--mode infer on the pixel-wise mesh (N = 47 200) instead of configs[4]'s")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "infer":
+        run_infer(args)
     else:
         run_gpu(args)
 

@@ -115,6 +115,8 @@ def lib():
         L.qmp_fused_cell_image_bytes.argtypes = []
         L.qmp_fused_cell_bwd_image_bytes.restype = _L
         L.qmp_fused_cell_bwd_image_bytes.argtypes = []
+        L.qmp_set_dropout_salt.restype = _I
+        L.qmp_set_dropout_salt.argtypes = [_P]
         for name, sig in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = _I
@@ -158,5 +160,14 @@ def call(name, *args):
         raise QmpError(f"{name} failed (code {rc}): {L.qmp_last_error().decode(errors='replace')}")
 
 
+def set_dropout_salt(t):
+    """Point the seeded kernels at a device uint64 salt (``t``: int64 CUDA tensor with one element) or clear it (None);
+    see qmp_set_dropout_salt (csrc/core.cu)."""
+    L = lib()
+    fn = getattr(L, "qmp_set_dropout_salt", None)
+    if fn is not None:
+        fn(_ptr(t))
+
+
 def exported_symbols():
-    return ["qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes"] + list(SIGNATURES)
+    return ["qmp_set_dropout_salt", "qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes"] + list(SIGNATURES)

@@ -32,7 +32,7 @@ struct AttnArgs {
     float* mstat;         // [N, G] running max
     float* linv;          // [N, G] 1 / sum exp
     float drop_p;         // attention dropout probability (0 = off)
-    unsigned long long seed;
+    unsigned long long seed; const unsigned long long* salt;
     // backward
     const float* dZ;      // [N, G*(D+3)]
     float* dU;            // [N, G*(D+2)]
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
         const float mn = fmaxf(m, s);
         const float sc = expf(m - mn);   // first edge: exp(-inf) = 0
         const float p = expf(s - mn);
-        const float pk = p * dropout_scale(a.seed, (long long)kk * a.G + g, a.drop_p);
+        const float pk = p * dropout_scale(QMP_SEED(a), (long long)kk * a.G + g, a.drop_p);
         l = l * sc + p;
         asum = asum * sc + pk;
         e0 = e0 * sc + pk * a0;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) attn_bwd_target_kernel(AttnArgs a) {
         }
         const float a0 = a.ea ? a.ea[(size_t)kk * 2] : 0.f, a1 = a.ea ? a.ea[(size_t)kk * 2 + 1] : 0.f;
         // gradient w.r.t. the (dropped-out) weight, chained through the keep mask
-        const float keep = dropout_scale(a.seed, (long long)kk * a.G + g, a.drop_p);
+        const float keep = dropout_scale(QMP_SEED(a), (long long)kk * a.G + g, a.drop_p);
         const float dal = keep * (group8_sum(part, gmask) + de0 * a0 + de1 * a1 + dsig);
         const float al = expf(a.logit[(size_t)kk * a.G + g] - m) * li;
         tsum = fmaf(al, dal, tsum);
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) attn_bwd_source_kernel(AttnArgs a, int sh
             const int i = a.odst[kk], kin = a.okin[kk];
             const long long pi = (long long)i * a.G + g;
             const float al = expf(a.logit[(size_t)kin * a.G + g] - a.mstat[pi]) * a.linv[pi] *
-                             dropout_scale(a.seed, (long long)kin * a.G + g, a.drop_p);
+                             dropout_scale(QMP_SEED(a), (long long)kin * a.G + g, a.drop_p);
             const float dsv = a.ds[(size_t)kin * a.G + g];
             const float* dz = a.dZ + (size_t)i * a.G * (D + 3) + (size_t)g * (D + 3);
             const float* ur = a.U + (size_t)i * a.G * (D + 2) + (size_t)g * (D + 2);
@@ -263,7 +263,7 @@ QMP_API int qmp_attn_fwd(int N, int G, int D, const int* in_ptr, const int* in_s
     if (N <= 0 || G <= 0) return 0;
     AttnArgs a{};
     a.N = N; a.G = G; a.D = D; a.ptr = in_ptr; a.nbr = in_src; a.ea = ea; a.x = x; a.ldx = ldx; a.xoff = xoff;
-    a.U = U; a.Z = Z; a.logit = logit; a.mstat = mstat; a.linv = linv; a.drop_p = drop_p; a.seed = seed;
+    a.U = U; a.Z = Z; a.logit = logit; a.mstat = mstat; a.linv = linv; a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     const int blocks = cdiv((long long)N * G * 8, 256);
 #define CALL(QQ) attn_fwd_kernel<QQ><<<blocks, 256, 0, (cudaStream_t)stream>>>(a)
     QMP_DISPATCH_Q(D, CALL);
@@ -281,7 +281,7 @@ QMP_API int qmp_attn_bwd_target(int N, int G, int D, const int* in_ptr, const in
     AttnArgs a{};
     a.N = N; a.G = G; a.D = D; a.ptr = in_ptr; a.nbr = in_src; a.ea = ea; a.x = x; a.ldx = ldx; a.xoff = xoff;
     a.logit = const_cast<float*>(logit); a.mstat = const_cast<float*>(mstat); a.linv = const_cast<float*>(linv);
-    a.dZ = dZ; a.ds = ds; a.dU = dU; a.drop_p = drop_p; a.seed = seed;
+    a.dZ = dZ; a.ds = ds; a.dU = dU; a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     const int blocks = cdiv((long long)N * G * 8, 256);
 #define CALL(QQ) attn_bwd_target_kernel<QQ><<<blocks, 256, 0, (cudaStream_t)stream>>>(a)
     QMP_DISPATCH_Q(D, CALL);
@@ -301,7 +301,7 @@ QMP_API int qmp_attn_bwd_source(int N, int G, int D, const int* out_ptr, const i
     a.N = N; a.G = G; a.D = D; a.optr = out_ptr; a.odst = out_dst; a.okin = out_kin;
     a.logit = const_cast<float*>(logit); a.mstat = const_cast<float*>(mstat); a.linv = const_cast<float*>(linv);
     a.ds = const_cast<float*>(ds); a.dZ = dZ; a.U = U; a.dx = dx; a.lddx = lddx; a.dxoff = dxoff;
-    a.dx_accumulate = accumulate; a.drop_p = drop_p; a.seed = seed;
+    a.dx_accumulate = accumulate; a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     const int blocks = cdiv((long long)N * (shared ? 1 : G) * 8, 256);
 #define CALL(QQ) attn_bwd_source_kernel<QQ><<<blocks, 256, 0, (cudaStream_t)stream>>>(a, shared)
     QMP_DISPATCH_Q(D, CALL);

@@ -40,6 +40,16 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
         }                                                                           \
     } while (0)
 
+// Dropout salt (qmp_set_dropout_salt): a DEVICE uint64 the seeded kernels mix into their by-value seed at run time, so that
+// a captured CUDA graph draws a new mask every replay (the host bumps the device value; kernel arguments stay frozen).
+const unsigned long long* dropout_salt();
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned long long salted_seed(unsigned long long seed, const unsigned long long* salt) {
+    return salt ? seed + 0x9E3779B97F4A7C15ull * __ldg(salt) : seed;
+}
+#define QMP_SEED(a) qmp::salted_seed((a).seed, (a).salt)
+#endif
+
 // Exclusive scan of n int32 (n <= 4M).  `blocksums` is caller scratch of >= cdiv(n,1024)+1 ints.
 // Writes the grand total to *total (device) when total != nullptr.
 int exclusive_scan_i32(const int* in, int* out, int n, int* total, int* blocksums, cudaStream_t st);

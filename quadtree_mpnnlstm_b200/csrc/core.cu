@@ -13,6 +13,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static const unsigned long long* g_salt = nullptr;
+const unsigned long long* dropout_salt() { return g_salt; }
+
 // ---- scan: 1024 items per block (256 threads x 4), then a single block scans the block sums.
 __global__ void __launch_bounds__(256) scan_block_kernel(const int* __restrict__ in, int* __restrict__ out, int n,
                                                          int* __restrict__ blocksums) {
@@ -99,4 +102,15 @@ QMP_API int qmp_version(void) { return 100; }
 // Exposed for tests: out[i] = sum_{k<i} in[k]; *total = sum.  scratch >= n/1024 + 2 ints.
 QMP_API int qmp_exclusive_scan_i32(const int* in, int* out, int n, int* total, int* scratch, void* stream) {
     return qmp::exclusive_scan_i32(in, out, n, total, scratch, (cudaStream_t)stream);
+}
+
+// Dropout salt: a device uint64 (or NULL = none, the default) that every seeded kernel launched AFTER this call mixes into its
+// by-value seed: effective seed = seed + 0x9E3779B97F4A7C15 * (*salt), read on the device when the kernel runs.  Forward and
+// backward kernels of one step see the same value as long as the caller changes *salt only between steps.  This is what lets
+// a captured CUDA graph (whose kernel arguments are frozen) resample its dropout masks every replay (the reference resamples
+// per call: torch.nn.functional.dropout in PyG TransformerConv.message, nn.Dropout in model/seq2seq.py:169).  Process-wide
+// host state, read at launch time; returns 0.
+QMP_API int qmp_set_dropout_salt(const unsigned long long* salt) {
+    qmp::g_salt = salt;
+    return 0;
 }

@@ -35,7 +35,7 @@ QMP_API int qmp_fused_bwd_target(int N, const int* in_ptr, const int* in_src, co
     a.xb = xb; a.ldb = ldb; a.DB = DB; a.GB = GB; a.sharedB = sharedB; a.wb = wb; a.NC = GA + GB; a.mode = mode; a.C = C;
     a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ds = ds; a.ZsA = ZsA; a.dUsA = dUsA;
     a.ZsB = ZsB; a.dUsB = dUsB; a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr;
-    a.drop_p = drop_p; a.seed = seed;
+    a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     return dispatch_bwd(a, 0, (cudaStream_t)stream);
 }
 
@@ -50,6 +50,6 @@ QMP_API int qmp_fused_bwd_source(int N, const int* out_ptr, const int* out_dst, 
     a.N = N; a.ptr = out_ptr; a.nbr = out_dst; a.kin = out_kin; a.xa = xa; a.lda = lda; a.DA = DA; a.GA = GA; a.wa = wa;
     a.xb = xb; a.ldb = ldb; a.DB = DB; a.GB = GB; a.sharedB = sharedB; a.wb = wb; a.NC = GA + GB; a.mode = mode; a.C = C;
     a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ds = const_cast<float*>(ds);
-    a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr; a.drop_p = drop_p; a.seed = seed;
+    a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr; a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     return dispatch_bwd(a, 1, (cudaStream_t)stream);
 }

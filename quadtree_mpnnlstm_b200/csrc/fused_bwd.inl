@@ -35,7 +35,7 @@ struct FusedBwdArgs {
     float* ZsA; float* dUsA; float* ZsB; float* dUsB;                    // [N, G, cap+4]
     float* dxa; float* dxb; int need_dxa, need_dxb;
     int onepass;                                                         // tcgen05 target kernel only: source side by reductions (dx zero on entry)
-    float drop_p; unsigned long long seed;
+    float drop_p; unsigned long long seed; const unsigned long long* salt;
 };
 
 // y[k] = sum_o WT[k][o] g[o] for k < R (WT row-major [R][FC])
@@ -93,7 +93,7 @@ __device__ __forceinline__ void conv_bwd_target(const FusedBwdArgs& a, int i, in
         float dal = fmaf(dz[DC], a0, fmaf(dz[DC + 1], a1, dz[DC + 2]));
 #pragma unroll
         for (int k = 0; k < DC; ++k) dal = fmaf(dz[k], xj[k], dal);
-        dal *= fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
+        dal *= fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
         const float al = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li;
         tsum = fmaf(al, dal, tsum);
         a.ds[(size_t)kk * a.NC + c] = dal;       // stash, finalised in pass 2
@@ -109,7 +109,7 @@ __device__ __forceinline__ void conv_bwd_target(const FusedBwdArgs& a, int i, in
         const float al = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li;
         const float dsv = al * (a.ds[(size_t)kk * a.NC + c] - tsum);
         a.ds[(size_t)kk * a.NC + c] = dsv;
-        const float alk = al * fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
+        const float alk = al * fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
 #pragma unroll
         for (int k = 0; k < DC; ++k) {
             du[k] = fmaf(dsv, xj[k], du[k]);
@@ -196,7 +196,7 @@ __device__ __forceinline__ void conv_bwd_source(const FusedBwdArgs& a, int j, in
     for (int kk = a.ptr[j]; kk < k1; ++kk) {
         const int i = a.nbr[kk], kin = a.kin[kk];
         const float al = __expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
-                         fdropout_scale(a.seed, (long long)kin * a.NC + c, a.drop_p);
+                         fdropout_scale(QMP_SEED(a), (long long)kin * a.NC + c, a.drop_p);
         const float dsv = a.ds[(size_t)kin * a.NC + c];
         float g[FC];
         load_dP(g, a, i, c);

@@ -44,7 +44,7 @@ QMP_API int qmp_fused_bwd_target_tc(int N, const int* in_ptr, const int* in_src,
     a.NC = GA + GB; a.mode = mode; a.C = C;
     a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ds = ds; a.ZsA = ZsA; a.dUsA = dUsA;
     a.ZsB = ZsB; a.dUsB = dUsB; a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr;
-    a.drop_p = drop_p; a.seed = seed;
+    a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     return dispatch_bwd_tc<1>(a, (cudaStream_t)stream);
 }
 
@@ -72,7 +72,7 @@ QMP_API int qmp_fused_bwd_onepass_tc(int N, const int* in_ptr, const int* in_src
     a.NC = GA + GB; a.mode = mode; a.C = C;
     a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ds = ds; a.ZsA = ZsA; a.dUsA = dUsA;
     a.ZsB = ZsB; a.dUsB = dUsB; a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr;
-    a.drop_p = drop_p; a.seed = seed; a.onepass = 1;
+    a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt(); a.onepass = 1;
     if (dxa) QMP_CUDA(cudaMemsetAsync(dxa, 0, (size_t)N * lda * sizeof(float), (cudaStream_t)stream));
     if (dxb) QMP_CUDA(cudaMemsetAsync(dxb, 0, (size_t)N * ldb * sizeof(float), (cudaStream_t)stream));
     return dispatch_bwd_tc<1>(a, (cudaStream_t)stream);
@@ -95,6 +95,6 @@ QMP_API int qmp_fused_bwd_source_tc(int N, const int* out_ptr, const int* out_ds
     a.xb = xb; a.ldb = ldb; a.DB = DB; a.GB = GB; a.sharedB = sharedB; a.wb = reinterpret_cast<const float*>(wb);
     a.NC = GA + GB; a.mode = mode; a.C = C;
     a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ds = const_cast<float*>(ds);
-    a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr; a.drop_p = drop_p; a.seed = seed;
+    a.dxa = dxa; a.dxb = dxb; a.need_dxa = dxa != nullptr; a.need_dxb = dxb != nullptr; a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     return dispatch_bwd_tc<2>(a, (cudaStream_t)stream);
 }

@@ -46,7 +46,7 @@ struct CellBwdArgs {
     const float* logit; const float* mstat; const float* linv;     // [E, 8], [N, 8], [N, 8]
     float* ZsA; float* dUsA; float* ZsB; float* dUsB;      // [N, 4, 8] and [N, 4, 36]
     float* dxa; float* dxb;                                // [N, lda], [N, ldb]: zero on entry
-    float drop_p; unsigned long long seed;
+    float drop_p; unsigned long long seed; const unsigned long long* salt;
 };
 
 // 16 warps, no dedicated MMA warp: both MMA groups of a tile are issued at points where every warp waits for their result
@@ -117,7 +117,7 @@ __device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t*
         const int k0 = x.k0, k1 = x.k1;
         auto dalpha = [&](int kk, const float4& xj, const float2& ev, float lg, float& al, float& keep) {
             al = fast_exp(lg - m) * li;
-            keep = fdropout_scale(a.seed, (long long)kk * 8 + c, a.drop_p);
+            keep = fdropout_scale(QMP_SEED(a), (long long)kk * 8 + c, a.drop_p);
             return (fmaf(dz.w, xj.w, fmaf(dz.z, xj.z, fmaf(dz.y, xj.y, dz.x * xj.x))) + fmaf(dze.x, ev.x, fmaf(dze.y, ev.y, dze.z))) * keep;
         };
         auto fetch = [&](int kk, int& j, float4& xj, float2& ev, float& lg) {       // in-edges beyond the fourth (quadtree meshes)
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
                         keep = 0.f;
                         if (on) {
                             al = fast_exp(lg - m) * li;
-                            keep = fdropout_scale(a.seed, (long long)kk * 8 + crole, a.drop_p);
+                            keep = fdropout_scale(QMP_SEED(a), (long long)kk * 8 + crole, a.drop_p);
                         }
                         return (tot + fmaf(dzt.x, ev.x, fmaf(dzt.y, ev.y, dzt.z))) * keep;
                     };
@@ -602,7 +602,7 @@ QMP_API int qmp_fused_cell_bwd(int N, const int* in_ptr, const int* in_src, cons
     CellBwdArgs a{};
     a.N = N; a.ptr = in_ptr; a.nbr = in_src; a.ea = ea; a.xa = xa; a.lda = lda; a.xb = xb; a.ldb = ldb; a.usave = usave;
     a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ZsA = ZsA; a.dUsA = dUsA; a.ZsB = ZsB;
-    a.dUsB = dUsB; a.dxa = dxa; a.dxb = dxb; a.drop_p = drop_p; a.seed = seed;
+    a.dUsB = dUsB; a.dxa = dxa; a.dxb = dxb; a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;

@@ -118,7 +118,7 @@ __device__ __forceinline__ void cell_xconv(const FusedFwdArgs& a, const uint8_t*
         a.logit[(size_t)kk * 8 + cg] = s;
         const float mn = fmaxf(m, s);
         const float sc = fast_exp(m - mn), pe = fast_exp(s - mn);
-        const float pk = pe * fdropout_scale(a.seed, (long long)kk * 8 + cg, a.drop_p);
+        const float pk = pe * fdropout_scale(QMP_SEED(a), (long long)kk * 8 + cg, a.drop_p);
         l = fmaf(l, sc, pe);
         zs = fmaf(zs, sc, pk);
         ze0 = fmaf(ze0, sc, pk * ev.x);
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
                     const float mn = fmaxf(m[r], gm);
                     sc[r] = (mn == -INFINITY) ? 1.f : fast_exp(m[r] - mn);
                     const float pe = on ? fast_exp(s - mn) : 0.f;
-                    pk[r] = pe * fdropout_scale(a.seed, (long long)kk * 8 + c, a.drop_p);
+                    pk[r] = pe * fdropout_scale(QMP_SEED(a), (long long)kk * 8 + c, a.drop_p);
                     l[r] = fmaf(l[r], sc[r], quad_sum(pe));
                     zs[r] = fmaf(zs[r], sc[r], quad_sum(pk[r]));
                     ze0[r] = fmaf(ze0[r], sc[r], quad_sum(pk[r] * ev.x));
@@ -723,7 +723,7 @@ QMP_API int qmp_fused_cell_fwd(int N, const int* in_ptr, const int* in_src, cons
     a.DB = 32; a.GB = 4; a.sharedB = 1; a.NC = 8; a.mode = 1; a.C = FC; a.Cprev = Cprev; a.params = params; a.norm_h = norm_h;
     a.norm_c = norm_c; a.norm_o = norm_o; a.eps = eps; a.gates = gates; a.Craw = Craw; a.Oout = Oout; a.Hout = Hout;
     a.Cout = Cout; a.head_in = head_in; a.ldh = ldh; a.concat = concat; a.logit = logit; a.mstat = mstat; a.linv = linv;
-    a.drop_p = drop_p; a.seed = seed;
+    a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;

@@ -26,7 +26,7 @@ struct FusedFwdArgs {
     const float* Cprev; const float* params; int norm_h, norm_c, norm_o; float eps;
     float* gates; float* Craw; float* Oout; float* Hout; float* Cout; float* head_in; int ldh; const float* concat;
     float* logit; float* mstat; float* linv;
-    float drop_p; unsigned long long seed;
+    float drop_p; unsigned long long seed; const unsigned long long* salt;
 };
 
 template <int DC>
@@ -63,7 +63,7 @@ __device__ __forceinline__ void conv_accumulate(const FusedFwdArgs& a, int i, in
         a.logit[(size_t)kk * a.NC + c] = s;
         const float mn = fmaxf(m, s);
         const float sc = __expf(m - mn), p = __expf(s - mn);
-        const float pk = p * fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
+        const float pk = p * fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
         l = fmaf(l, sc, p);
         zs = fmaf(zs, sc, pk);
         ze0 = fmaf(ze0, sc, pk * a0);

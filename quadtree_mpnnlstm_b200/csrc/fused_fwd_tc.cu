@@ -46,7 +46,7 @@ QMP_API int qmp_fused_fwd_tc(int N, const int* in_ptr, const int* in_src, const 
     a.relu_out = relu_out; a.C = C; a.out = out; a.ldo = ldo; a.Cprev = Cprev; a.params = params; a.norm_h = norm_h;
     a.norm_c = norm_c; a.norm_o = norm_o; a.eps = eps; a.gates = gates; a.Craw = Craw; a.Oout = Oout; a.Hout = Hout;
     a.Cout = Cout; a.head_in = head_in; a.ldh = ldh; a.concat = concat; a.logit = logit; a.mstat = mstat; a.linv = linv;
-    a.drop_p = drop_p; a.seed = seed;
+    a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     cudaStream_t st = (cudaStream_t)stream;
     const int dac = (GA == 0) ? 0 : (DA <= 4 ? 4 : 8);
     const int dbc = (DB <= 32) ? 32 : 36;

@@ -37,7 +37,7 @@ __device__ __forceinline__ void tc_edge(const FusedFwdArgs& a, int kk, int c, co
     a.logit[(size_t)kk * a.NC + c] = s;
     const float mn = fmaxf(m, s);
     const float sc = __expf(m - mn), p = __expf(s - mn);
-    const float pk = p * fdropout_scale(a.seed, (long long)kk * a.NC + c, a.drop_p);
+    const float pk = p * fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
     l = fmaf(l, sc, p);
     zs = fmaf(zs, sc, pk);
     ze0 = fmaf(ze0, sc, pk * e0);

@@ -436,12 +436,13 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_oct_kernel(LstmArgs a) {
 // decoder head tail (model/seq2seq.py:167-178, 427-428): out = tanh(drop(y)) + x0 [-> sigmoid];
 // x_next = [out, x[:, 1:]]
 __global__ void head_finish_fwd_kernel(const float* __restrict__ y, const float* __restrict__ x, int N, int F, int binary,
-                                       float drop_p, unsigned long long seed, float* __restrict__ out,
-                                       float* __restrict__ x_next) {
+                                       float drop_p, unsigned long long seed, const unsigned long long* __restrict__ salt,
+                                       float* __restrict__ out, float* __restrict__ x_next) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float keep = 1.f;
     if (drop_p > 0.f) {
+        seed = salted_seed(seed, salt);
         unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
@@ -461,12 +462,14 @@ __global__ void head_finish_fwd_kernel(const float* __restrict__ y, const float*
 // (zeros without it); out is the forward result
 __global__ void head_finish_bwd_kernel(const float* __restrict__ y, const float* __restrict__ out, const float* __restrict__ x,
                                        const float* __restrict__ d_out, const float* __restrict__ d_xnext, int N, int F,
-                                       int binary, float drop_p, unsigned long long seed, float* __restrict__ dy,
+                                       int binary, float drop_p, unsigned long long seed,
+                                       const unsigned long long* __restrict__ salt, float* __restrict__ dy,
                                        float* __restrict__ dx) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     float keep = 1.f;
     if (drop_p > 0.f) {
+        seed = salted_seed(seed, salt);
         unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
@@ -564,7 +567,7 @@ QMP_API int qmp_lstm_gates_bwd(int N, int C, const float* gates, const float* Cr
 QMP_API int qmp_head_finish_fwd(const float* y, const float* x, int N, int F, int binary, float drop_p,
                                 unsigned long long seed, float* out, float* x_next, void* stream) {
     if (N <= 0) return 0;
-    head_finish_fwd_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(y, x, N, F, binary, drop_p, seed, out, x_next);
+    head_finish_fwd_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(y, x, N, F, binary, drop_p, seed, qmp::dropout_salt(), out, x_next);
     QMP_LAUNCH_CHECK("qmp_head_finish_fwd");
     return 0;
 }
@@ -574,7 +577,7 @@ QMP_API int qmp_head_finish_bwd(const float* y, const float* out, const float* x
                                 float* dy, float* dx, void* stream) {
     if (N <= 0) return 0;
     head_finish_bwd_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(y, out, x, d_out, d_xnext, N, F, binary,
-                                                                           drop_p, seed, dy, dx);
+                                                                           drop_p, seed, qmp::dropout_salt(), dy, dx);
     QMP_LAUNCH_CHECK("qmp_head_finish_bwd");
     return 0;
 }

@@ -135,9 +135,15 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// split for 3xTF32
+// split for 3xTF32: x = hi + lo with hi ROUNDED to the nearest tf32.  The tensor core reads the upper 19 bits of an fp32
+// operand, i.e. it TRUNCATES: with hi = x & 0xFFFFE000 the remainder lo is always of x's sign and keeps up to 13 significant
+// bits, the hardware chops it to 11, and every operand carries a ONE-SIDED error of up to 2^-20 |x| -- measured at the full
+// configs[1] size as forecasts drifting from 1.5e-6 (step 0) to 2.2e-4 (step 84) against the oracle.  With hi rounded
+// (add half an ulp to the bit pattern, then truncate: two full-rate integer instructions; cvt.rna.tf32.f32 does the same on
+// the slower conversion pipe) |lo| <= 2^-11 |x| has either sign, lo = x - hi is exact in fp32, and the hardware's truncation
+// of lo is an error of at most 2^-21 |x| whose sign follows lo's, i.e. unbiased.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    hi = __uint_as_float((__float_as_uint(x) + 0x00001000u) & 0xFFFFE000u);
     lo = x - hi;
 }
 

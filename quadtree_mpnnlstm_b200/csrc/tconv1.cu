@@ -49,9 +49,10 @@ __global__ void __launch_bounds__(256) tconv1_node_fwd_kernel(int N, const float
 __global__ void __launch_bounds__(256) tconv1_edge_fwd_kernel(int N, const int* __restrict__ ptr, const int* __restrict__ nbr,
                                                               const float* __restrict__ ea, const float4* __restrict__ s4,
                                                               const float* __restrict__ P, float* __restrict__ out, float drop_p,
-                                                              unsigned long long seed) {
+                                                              unsigned long long seed, const unsigned long long* __restrict__ salt) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
+    if (drop_p > 0.f) seed = salted_seed(seed, salt);
     const float we0 = __ldg(P + 132), we1 = __ldg(P + 133);
     const float4 si = __ldg(s4 + i);
     float m = -INFINITY, l = 0.f, acc = 0.f;
@@ -79,7 +80,8 @@ __global__ void __launch_bounds__(256) tconv1_edge_bwd_kernel(int N, const int* 
                                                               const float* __restrict__ ea, const float4* __restrict__ s4,
                                                               const float* __restrict__ P, const float* __restrict__ g,
                                                               float* __restrict__ ds4, float* __restrict__ gP, float drop_p,
-                                                              unsigned long long seed) {
+                                                              unsigned long long seed, const unsigned long long* __restrict__ salt) {
+    if (drop_p > 0.f) seed = salted_seed(seed, salt);
     __shared__ float s_we[2];
     if (threadIdx.x < 2) s_we[threadIdx.x] = 0.f;
     __syncthreads();
@@ -215,7 +217,7 @@ QMP_API int qmp_tconv1_fwd(int N, const int* in_ptr, const int* in_src, const fl
     cudaStream_t st = (cudaStream_t)stream;
     tconv1_node_fwd_kernel<<<t1_grid(N), 256, 0, st>>>(N, x, ldx, P, reinterpret_cast<float4*>(s4));
     QMP_LAUNCH_CHECK("tconv1_node_fwd_kernel");
-    tconv1_edge_fwd_kernel<<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, out, drop_p, seed);
+    tconv1_edge_fwd_kernel<<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, out, drop_p, seed, qmp::dropout_salt());
     QMP_LAUNCH_CHECK("tconv1_edge_fwd_kernel");
     return 0;
 }
@@ -232,7 +234,7 @@ QMP_API int qmp_tconv1_bwd(int N, const int* in_ptr, const int* in_src, const fl
     cudaStream_t st = (cudaStream_t)stream;
     QMP_CUDA(cudaMemsetAsync(ds4, 0, (size_t)N * 4 * sizeof(float), st));
     tconv1_edge_bwd_kernel<<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, g, ds4, gP,
-                                                         drop_p, seed);
+                                                         drop_p, seed, qmp::dropout_salt());
     QMP_LAUNCH_CHECK("tconv1_edge_bwd_kernel");
     tconv1_node_bwd_kernel<<<t1_grid(N) < 296 ? t1_grid(N) : 296, 256, 0, st>>>(N, x, ldx, P, reinterpret_cast<const float4*>(ds4), dx,
                                                                                lddx, gP);

@@ -14,8 +14,11 @@ What is different is where the work happens:
   * ``DeviceWindowDataset`` keeps ONE [T, H, W, c] cube on the device and serves (x, y, launch_date) sliding windows as
     views, instead of materialising every window on the host (ice_dataset.py:20-68).
 
-Truncated back-propagation (``truncated_backprop > 0``, model/mpnnlstm.py:281-313) is not implemented: ice_exp.py's
-default is 0.
+Truncated back-propagation (``truncated_backprop > 0``, the reference's default of 45; model/mpnnlstm.py:281-313) runs the
+reference's chunked loop as it is written there, quirks included: every chunk re-encodes the inputs and unrolls
+``range(t - truncated_backprop, t)`` from the encoder state, ``zero_grad`` runs at the start of EVERY chunk (so the optimizer
+step after the last chunk sees the last chunk's gradients only), no gradient clipping, and a chunk that runs past
+``output_timesteps`` raises ``IndexError`` (``output_timesteps`` must be a multiple of ``truncated_backprop``).
 """
 from __future__ import annotations
 
@@ -193,9 +196,6 @@ class NextFramePredictorS2S(NextFramePredictor):
             self.initiate_training(lr, lr_decay)
         if mask is not None:
             assert tuple(mask.shape) == image_shape, f'Mask and image shapes do not match. Got {mask.shape} and {image_shape}'
-        if truncated_backprop != 0:
-            raise NotImplementedError("truncated back-propagation (model/mpnnlstm.py:281-313) is not implemented on this "
-                                      "path; pass truncated_backprop=0 (the ice_exp.py default)")
         dev = self.device
         params = list(self.model.parameters())
         st = time.time()
@@ -206,9 +206,13 @@ class NextFramePredictorS2S(NextFramePredictor):
             for x, y, launch_date in loader_train:
                 x, y = x.squeeze(0).to(dev), y.squeeze(0).to(dev)
                 concat_layers = self.get_climatology_array(climatology, launch_date) if climatology is not None else None
-                loss = self._train_step(x, y, concat_layers, mask, high_interest_region, graph_structure, image_shape, params)
-                if self.debug:
-                    self.writer.add_scalar("Loss/train", loss.item(), batch_step)
+                if truncated_backprop == 0:
+                    loss = self._train_step(x, y, concat_layers, mask, high_interest_region, graph_structure, image_shape, params,
+                                            batch_step)
+                else:
+                    loss = self._train_step_truncated(x, y, concat_layers, mask, high_interest_region, graph_structure,
+                                                      image_shape, truncated_backprop)
+                self.writer.add_scalar("Loss/train", loss, batch_step)      # unconditional, per batch (model/mpnnlstm.py:315)
                 running = running + loss
                 step += 1
                 batch_step += 1
@@ -240,7 +244,24 @@ class NextFramePredictorS2S(NextFramePredictor):
         self.writer.flush()
         self.loss = pd.DataFrame({'train_loss': self.train_loss, 'test_loss': self.test_loss})
 
-    def _train_step(self, x, y, concat_layers, mask, hir, graph_structure, image_shape, params):
+    def _train_step_truncated(self, x, y, concat_layers, mask, hir, graph_structure, image_shape, truncated_backprop):
+        """The reference's chunked loop (model/mpnnlstm.py:281-313), statement for statement."""
+        output_timestep = 0
+        loss = None
+        while output_timestep < self.output_timesteps:
+            output_timestep = min(output_timestep + truncated_backprop, self.output_timesteps + 1)
+            unroll_steps = range(output_timestep - truncated_backprop, output_timestep)
+            self.optimizer.zero_grad()
+            self.model.process_inputs(x, mask=mask, high_interest_region=hir, graph_structure=graph_structure)
+            y_hat, maps = self.model.unroll_output(unroll_steps, y, concat_layers=concat_layers, teacher_forcing_ratio=0, mask=mask,
+                                                   high_interest_region=hir, remesh_every=1)
+            loss = self._loss(y_hat, maps, y[list(unroll_steps)], image_shape, mask)
+            loss.backward(retain_graph=True)
+            del y_hat, maps
+        self.optimizer.step()
+        return loss.detach()
+
+    def _train_step(self, x, y, concat_layers, mask, hir, graph_structure, image_shape, params, batch_step=0):
         # node-space loss == pixel-space loss only on the pixel-wise mesh (one pixel per node), which is what TrainStep captures
         if (self.use_cuda_graph and self.model.thresh == -float("inf") and graph_structure is None and not self.binary
                 and concat_layers is not None and x.is_cuda and hir is None):
@@ -256,7 +277,7 @@ class NextFramePredictorS2S(NextFramePredictor):
             for name, mod in (("encoder", self.model.encoder), ("decoder", self.model.decoder)):
                 g = [torch.norm(p.grad.detach()) for p in mod.parameters() if p.grad is not None]
                 if g:
-                    self.writer.add_scalar(f"Grad/{name}/grad_norms", torch.norm(torch.stack(g)), len(self.train_loss))
+                    self.writer.add_scalar(f"Grad/{name}/grad_norms", torch.norm(torch.stack(g)), batch_step)
         return loss.detach()
 
     def _graph_train_step(self, x, y, concat_layers, mask, graph_structure):

@@ -29,6 +29,26 @@ def next_seed():
     return (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + _seed_counter[0] * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
 
 
+class dropout_salt:
+    """``with dropout_salt(t):`` -- every seeded kernel launched inside mixes the DEVICE value ``t[0]`` (int64 CUDA tensor) into
+    its by-value seed when it runs.  A captured CUDA graph freezes kernel arguments, so without this every replay would
+    drop the same attention edges / head outputs; the step bumps ``t`` (a device op inside the graph) and the masks are
+    resampled per replay like the reference resamples per call (train.TrainStep, infer.Rollout)."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def __enter__(self):
+        if self.t is not None:
+            _lib.set_dropout_salt(self.t)
+        return self.t
+
+    def __exit__(self, *exc):
+        if self.t is not None:
+            _lib.set_dropout_salt(None)
+        return False
+
+
 # =============================================================================== TransformerConv group
 class TConvFn(torch.autograd.Function):
     """G TransformerConvs over one graph in one pass.

@@ -17,11 +17,17 @@ import torch
 from .graph_functions import flatten, unflatten
 
 
-def shard_launch_dates(n_dates, rank, world, seed=0):
-    """Launch dates (sample indices) of one rank: a seed-fixed permutation dealt round-robin, the same count on every
-    rank (the remainder is dropped) so that every optimizer step has exactly one gradient all-reduce on all ranks."""
+def shard_launch_dates(n_dates, rank, world, seed=0, pad=False):
+    """Launch dates (sample indices) of one rank: a seed-fixed permutation dealt round-robin, the same count on every rank so
+    that every optimizer step / the final gather has exactly one collective on all ranks.  Training (``pad=False``) drops the
+    remainder; inference (``pad=True``) must forecast EVERY date, so short ranks repeat the last date and the caller trims
+    the padding after the gather (infer.predict_sharded)."""
     import numpy as np
     perm = np.random.default_rng(seed).permutation(n_dates) if seed else np.arange(n_dates)
+    if pad:
+        per = -(-n_dates // world)
+        mine = [int(d) for d in perm[rank::world]]
+        return mine + [int(perm[-1])] * (per - len(mine)) if n_dates else []
     per = n_dates // world
     return [int(d) for d in perm[rank:per * world:world]]
 
@@ -44,9 +50,21 @@ class TrainStep:
         self._bucket = None
         self.stream = None
         self.topology = None
+        # dropout under replay: kernel arguments (the per-call seeds) are frozen by the capture, so the seeded kernels also
+        # mix in this device counter, bumped by one device op at the start of every (captured) step
+        self.salt = None
+        if use_cuda_graph and self.params and self.params[0].is_cuda:
+            self.salt = torch.zeros(1, dtype=torch.int64, device=self.params[0].device)
 
     # -- one eager step -----------------------------------------------------------------------------
     def _step(self, x, y, concat):
+        from .ops import dropout_salt
+        if self.salt is not None:
+            self.salt.add_(1)
+        with dropout_salt(self.salt):
+            return self._step_body(x, y, concat)
+
+    def _step_body(self, x, y, concat):
         for p in self.params:
             p.grad = None
         out, maps = self.model(x, y, concat, teacher_forcing_ratio=0, mask=self.mask, graph_structure=self.graph_structure)

@@ -103,6 +103,11 @@ def test_shard_launch_dates_partitions_evenly():
         seen = [d for s in shards for d in s]
         assert len(seen) == len(set(seen)) and all(0 <= d < n for d in seen)
         assert len(seen) == (n // world) * world
+        # inference: every date is forecast; short ranks are padded to the same count (trimmed after the gather)
+        padded = [shard_launch_dates(n, r, world, pad=True) for r in range(world)]
+        assert len({len(s) for s in padded}) == 1 and len(padded[0]) == -(-n // world)
+        inter = [padded[r][i] for i in range(len(padded[0])) for r in range(world)]
+        assert inter[:n] == list(range(n)), "round-robin interleave restores launch-date order"
 
 
 def _infer_worker(rank, world, init_file, out_dir):
@@ -112,7 +117,7 @@ def _infer_worker(rank, world, init_file, out_dir):
     from quadtree_mpnnlstm_b200.infer import predict_sharded
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
     kw, mask, samples = _problem()
-    samples = samples * 2                                  # 4 launch dates over 2 ranks
+    samples = (samples * 2)[:3]                            # 3 launch dates over 2 ranks: rank 1 pads, the gather trims
     with Emulated():
         torch.manual_seed(3)
         model = q.Seq2Seq(**kw).eval()
@@ -133,11 +138,11 @@ def test_rollout_inference_sharded_over_two_ranks():
         a, b = (torch.load(os.path.join(tmp, f"inf{r}.pt")) for r in range(2))
     assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
     kw, mask, samples = _problem()
-    samples = samples * 2
+    samples = (samples * 2)[:3]
     with Emulated():
         torch.manual_seed(3)
         model = q.Seq2Seq(**kw).eval()
         ref = predict_sharded(model, lambda d: (samples[d][0], samples[d][2]), len(samples), mask)
-    assert a.shape == ref.shape == (4, 3, 12, 16, 1)
+    assert a.shape == ref.shape == (3, 3, 12, 16, 1), 'no launch date may be dropped'
     assert torch.equal(torch.isnan(a), torch.isnan(ref))
     assert torch.allclose(torch.nan_to_num(a), torch.nan_to_num(ref), atol=1e-6)
