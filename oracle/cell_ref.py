@@ -18,6 +18,7 @@ CONVOLUTION_KWARGS = {                                  # model/model.py:49-57
     "GCNConv": dict(add_self_loops=False),
     "TransformerConv": dict(heads=1, edge_dim=2, dropout=0.1, concat=False),
     "ChebConv": dict(K=3, normalization="sym", bias=True),
+    "MHTransformerConv": dict(heads=3, edge_dim=2, dropout=0.1),
 }
 
 GATES = ("i", "f", "c", "o")

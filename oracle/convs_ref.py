@@ -171,14 +171,15 @@ def segment_softmax(score, index, n):
 
 
 class TransformerConv(nn.Module):
-    """heads=1, concat=False, beta=False, root_weight=True (CONVOLUTION_KWARGS, model/model.py:51):
-    q_i = Wq x_i + bq; k_ij = Wk x_j + bk + We e_ij; v_ij = Wv x_j + bv + We e_ij;
-    alpha = softmax_j(q_i . k_ij / sqrt(C)); dropout(alpha); out_i = sum_j alpha v_ij + Ws x_i + bs."""
+    """PyG 2.2.0 ``TransformerConv`` with beta=False, root_weight=True (CONVOLUTION_KWARGS, model/model.py:51-52), H heads:
+    q_i = Wq x_i + bq; k_ij = Wk x_j + bk + We e_ij; v_ij = Wv x_j + bv + We e_ij, each viewed as [H, C];
+    alpha^h = softmax_j(q_i^h . k_ij^h / sqrt(C)); dropout(alpha); out_i^h = sum_j alpha^h v_ij^h;
+    concat=True: heads side by side [H*C] + lin_skip (in -> H*C); concat=False: mean over heads + lin_skip (in -> C)."""
 
     def __init__(self, in_channels, out_channels, heads=1, concat=True, beta=False, dropout=0.0,
                  edge_dim=None, bias=True, root_weight=True, **_):
         super().__init__()
-        assert heads == 1 and not beta and root_weight, "only the configuration the reference selects"
+        assert not beta and root_weight, "only the configurations the reference selects"
         self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
         self.concat, self.dropout, self.edge_dim = concat, dropout, edge_dim
         self.lin_key = Linear(in_channels, heads * out_channels)
@@ -187,20 +188,38 @@ class TransformerConv(nn.Module):
         self.lin_edge = Linear(edge_dim, heads * out_channels, bias=False) if edge_dim is not None else None
         self.lin_skip = Linear(in_channels, heads * out_channels if concat else out_channels, bias=bias)
 
-    def forward(self, x, edge_index, edge_attr=None):
-        n, c = x.shape[0], self.out_channels
+    def forward(self, x, edge_index, edge_attr=None, return_attention_weights=None):
+        assert not return_attention_weights, "attention weights are never requested on the hot path"
+        n, c, h = x.shape[0], self.out_channels, self.heads
         src, dst = edge_index[0], edge_index[1]
-        q, k, v = self.lin_query(x)[dst], self.lin_key(x)[src], self.lin_value(x)[src]
+        q = self.lin_query(x)[dst].view(-1, h, c)
+        k = self.lin_key(x)[src].view(-1, h, c)
+        v = self.lin_value(x)[src].view(-1, h, c)
         if self.lin_edge is not None:
             assert edge_attr is not None
-            e = self.lin_edge(edge_attr)
+            e = self.lin_edge(edge_attr).view(-1, h, c)
             k = k + e
-        alpha = (q * k).sum(-1) / math.sqrt(c)
-        alpha = segment_softmax(alpha, dst, n)
+        alpha = (q * k).sum(-1) / math.sqrt(c)                                   # [E, H]
+        alpha = torch.stack([segment_softmax(alpha[:, i], dst, n) for i in range(h)], dim=1)
         alpha = F.dropout(alpha, p=self.dropout, training=self.training)
         msg = v + e if self.lin_edge is not None else v
-        out = scatter_add_rows(msg * alpha[:, None], dst, n)
+        out = scatter_add_rows(msg * alpha[:, :, None], dst, n)                  # [N, H, C]
+        out = out.reshape(n, h * c) if self.concat else out.mean(dim=1)
         return out + self.lin_skip(x)
 
 
-CONVOLUTIONS = {"GCNConv": GCNConv, "TransformerConv": TransformerConv, "ChebConv": ChebConv}
+class MHTransformerConv(TransformerConv):
+    """The reference's own subclass (model/model.py:26-37): the multi-head TransformerConv followed by
+    ``lin`` (heads * out -> out)."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, beta=False, dropout=0.0, edge_dim=None,
+                 bias=True, root_weight=True, **kw):
+        super().__init__(in_channels, out_channels, heads, concat, beta, dropout, edge_dim, bias, root_weight, **kw)
+        self.lin = Linear(out_channels * heads, out_channels)
+
+    def forward(self, x, edge_index, edge_attr=None, return_attention_weights=None):
+        return self.lin(super().forward(x, edge_index, edge_attr))
+
+
+CONVOLUTIONS = {"GCNConv": GCNConv, "TransformerConv": TransformerConv, "ChebConv": ChebConv,
+                "MHTransformerConv": MHTransformerConv}

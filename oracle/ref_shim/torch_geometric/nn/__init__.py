@@ -1,5 +1,6 @@
 import torch.nn as nn
-from oracle.convs_ref import GCNConv, ChebConv, TransformerConv  # noqa: F401
+from oracle.convs_ref import GCNConv, ChebConv, TransformerConv  # noqa: F401  (TransformerConv: any number of heads, so the
+# reference's own MHTransformerConv subclass, model/model.py:26-37, runs on it unmodified)
 from .conv import MessagePassing  # noqa: F401
 
 

@@ -188,15 +188,64 @@ class ChebConv(nn.Module):
         return NodeLinearFn.apply(tx, W, b, True)
 
 
+class _HeadView:
+    """One attention head of a multi-head TransformerConv seen as a single-head conv (the slices of the PyG parameters that
+    belong to it), in the shape ``pack_tconv`` consumes."""
+
+    class _Lin:
+        def __init__(self, weight, bias):
+            self.weight, self.bias = weight, bias
+
+    def __init__(self, conv, h):
+        C = conv.out_channels
+        rows = slice(h * C, (h + 1) * C)
+        self.out_channels = C
+        self.lin_query = self._Lin(conv.lin_query.weight[rows], conv.lin_query.bias[rows])
+        self.lin_key = self._Lin(conv.lin_key.weight[rows], conv.lin_key.bias[rows])
+        self.lin_value = self._Lin(conv.lin_value.weight[rows], conv.lin_value.bias[rows])
+        self.lin_edge = self._Lin(conv.lin_edge.weight[rows], None)
+        self.lin_skip = self._Lin(conv.lin_skip.weight[rows], conv.lin_skip.bias[rows])
+
+
+class MHTransformerConv(nn.Module):
+    """The reference's multi-head variant (model/model.py:26-37, CONVOLUTION_KWARGS :52: heads=3, edge_dim=2, dropout=0.1):
+    PyG ``TransformerConv(in, out, heads, concat=True)`` -- every head attends with its own query / key / value / edge
+    slices, the head outputs are concatenated and the root weight ``lin_skip`` (in -> heads * out) is added -- followed by
+    ``lin`` (heads * out -> out).
+
+    A head is exactly a single-head TransformerConv of width ``out`` (the 1 / sqrt(out) logit scale is per head), and the
+    rows h * out .. (h + 1) * out of ``lin_skip`` are that head's skip path, so the ``heads`` heads run as ONE grouped launch
+    of the TransformerConv kernels over a shared input (attn.cu: G = heads convs), and ``lin`` is one node GEMM."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, beta=False, dropout=0.0, edge_dim=None, bias=True,
+                 root_weight=True, **kwargs):
+        super().__init__()
+        if not concat or beta or not root_weight or edge_dim != 2 or not bias:
+            raise NotImplementedError("MHTransformerConv: concat=True, beta=False, root_weight=True, edge_dim=2, bias=True "
+                                      "(the reference's CONVOLUTION_KWARGS) is implemented")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.dropout, self.edge_dim = concat, dropout, edge_dim
+        self.lin_key = Linear(in_channels, heads * out_channels)
+        self.lin_query = Linear(in_channels, heads * out_channels)
+        self.lin_value = Linear(in_channels, heads * out_channels)
+        self.lin_edge = Linear(edge_dim, heads * out_channels, bias=False)
+        self.lin_skip = Linear(in_channels, heads * out_channels, bias=bias)
+        self.lin = Linear(out_channels * heads, out_channels)
+
+    def forward(self, x, edge_index, edge_attr=None, return_attention_weights=None):
+        assert edge_attr is not None, "MHTransformerConv(edge_dim=2) needs edge attributes"
+        csr = get_csr(edge_index, edge_attr, _n_nodes(x))
+        p = self.dropout if self.training else 0.0
+        heads = [_HeadView(self, h) for h in range(self.heads)]
+        out = TConvFn.apply(x.float(), *pack_tconv(heads), csr, True, p, next_seed() if p > 0 else 0, False, None)   # [N, heads*out]
+        return NodeLinearFn.apply(out, self.lin.weight.unsqueeze(0), self.lin.bias.unsqueeze(0), True)
+
+
 class _Unsupported(nn.Module):
     def __init__(self, *a, **k):
         super().__init__()
         raise NotImplementedError(f"{type(self).__name__} is not selected by any configuration of the hot path "
                                   "(SURVEY.md section 2); not implemented")
-
-
-class MHTransformerConv(_Unsupported):
-    pass
 
 
 class GATConv(_Unsupported):

@@ -47,7 +47,11 @@ const unsigned long long* dropout_salt();
 __device__ __forceinline__ unsigned long long salted_seed(unsigned long long seed, const unsigned long long* salt) {
     return salt ? seed + 0x9E3779B97F4A7C15ull * __ldg(salt) : seed;
 }
+#ifdef QMP_NO_SALT      // timing experiment only: what the run-time salt costs
+#define QMP_SEED(a) ((a).seed)
+#else
 #define QMP_SEED(a) qmp::salted_seed((a).seed, (a).salt)
+#endif
 #endif
 
 // Exclusive scan of n int32 (n <= 4M).  `blocksums` is caller scratch of >= cdiv(n,1024)+1 ints.

@@ -6,6 +6,8 @@ cache keyed by the tensors' storage, so the per-call cost is a dictionary probe.
 """
 from __future__ import annotations
 
+import collections
+
 import torch
 
 from . import _lib
@@ -58,22 +60,22 @@ class GraphCSR:
         return val
 
 
-_cache = {}
-_ORDER = []
+_cache = collections.OrderedDict()       # least recently used first
 _MAX = 32
 
 
 def get_csr(edge_index, edge_attr, n_nodes, validate=True):
     if isinstance(edge_index, GraphCSR):
         return edge_index
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), int(n_nodes),
-           None if edge_attr is None else (edge_attr.data_ptr(), tuple(edge_attr.shape)))
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), int(n_nodes), edge_index._version,
+           None if edge_attr is None else (edge_attr.data_ptr(), tuple(edge_attr.shape), edge_attr._version))
     hit = _cache.get(key)
     if hit is not None and hit._keepalive[0] is edge_index and hit._keepalive[1] is edge_attr:
+        _cache.move_to_end(key)
         return hit
     csr = GraphCSR(edge_index, edge_attr, n_nodes, validate=validate)
-    _cache[key] = csr
-    _ORDER.append(key)
-    while len(_ORDER) > _MAX:
-        _cache.pop(_ORDER.pop(0), None)
+    _cache[key] = csr                    # a stale entry under the same key (same storage, new tensor object) is replaced
+    _cache.move_to_end(key)
+    while len(_cache) > _MAX:
+        _cache.popitem(last=False)
     return csr

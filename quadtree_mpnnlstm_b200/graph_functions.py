@@ -395,7 +395,7 @@ def image_to_graph(img, thresh=0.05, max_grid_size=64, mask=None, high_interest_
         data = data_cap[:, :N] if n == 1 else data_cap[:, :N].contiguous()
     cell_sizes = (mesh.npix / ((max_grid_size / 2) ** 2)).reshape(1, N, 1).expand(n, N, 1)   # :665-666
     data = torch.cat([data, cell_sizes], -1)
-    return dict(edge_index=ei[:, :E].contiguous(), edge_attrs=edge_attrs[:E], data=data,
+    return dict(edge_index=ei[:, :E].contiguous(), edge_attrs=edge_attrs[:E].contiguous(), data=data,
                 graph_nodes=np.arange(N), mapping=mesh, n_pixels_per_node=mesh.npix, labels=labels.view(h, w))
 
 

@@ -180,7 +180,13 @@ class GConvLSTM(nn.Module):
                     inp = ts[0]
                 cur = NodeLinearFn.apply(inp, W, b, False)
             return cur[:, :4 * C] + cur[:, 4 * C:]
-        raise NotImplementedError(f"GConvLSTM: convolution_type={kind!r} is not implemented on this path")
+        # any other conv type (MHTransformerConv, the GAT family): the eight stacks one module call at a time -- each call runs
+        # on its own qmp kernels (convs.py); only the batching of the eight stacks into grouped launches is missing
+        ei, ea = csr._keepalive              # the tensors the CSR was built from: the module calls hit the CSR cache by identity
+        outs = []
+        for g in GATES:
+            outs.append(getattr(self, f"conv_x_{g}")(X, ei, ea) + getattr(self, f"conv_h_{g}")(H, ei, ea))
+        return torch.cat(outs, dim=1)
 
     # ---- single-launch path (TransformerConv, hidden 32) ---------------------------------------
     def _fusable(self):

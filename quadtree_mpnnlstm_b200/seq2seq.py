@@ -181,7 +181,9 @@ class Decoder(torch.nn.Module):
                 o = NodeLinearFn.apply(t, W, conv.bias.unsqueeze(0), True)
                 return torch.relu(o) if relu else o
             return lin(self.fc_out2, lin(self.fc_out1, head, True), False)
-        raise NotImplementedError(kind)
+        # any other conv type: two module calls (seq2seq.py:182-187)
+        ei, ea = csr._keepalive
+        return self.fc_out2(torch.relu(self.fc_out1(head, ei, ea)), ei, ea)
 
     def gnn_out(self, x, edge_index, edge_weight):
         """Reference-shaped helper (seq2seq.py:182-187)."""

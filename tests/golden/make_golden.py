@@ -153,12 +153,82 @@ def make_seq_cases(ref):
         print(f"seq2seq_{name}: nodes per step {blob['n_nodes'].tolist()}")
 
 
+class RefWindows(torch.utils.data.Dataset):
+    """What ice_dataset.py:20-68 serves: materialised (x, y, launch_date) windows + image_shape."""
+
+    def __init__(self, cube, t_in, t_out, times, idx):
+        self.x = [cube[a:a + t_in] for a in idx]
+        self.y = [cube[a + t_in:a + t_in + t_out][..., :1] for a in idx]
+        self.d = [times[a + t_in] for a in idx]
+        self.image_shape = cube.shape[1:3]
+
+    def __len__(self):
+        return len(self.x)
+
+    def __getitem__(self, i):
+        return self.x[i], self.y[i], self.d[i]
+
+
+TRAINER_CASES = {
+    # name: (thresh, conv kwargs, T_in, T_out, truncated_backprop, epochs)
+    "quadtree_cheb": (0.1, dict(hidden_size=8, dropout=0.0, n_layers=1, n_conv_layers=1), 3, 3, 0, 2),
+    "pixelwise_transformer": (-np.inf, dict(hidden_size=32, dropout=0.0, n_layers=1, n_conv_layers=2, convolution_type="TransformerConv"),
+                              3, 4, 0, 2),
+    "quadtree_cheb_truncated": (0.1, dict(hidden_size=8, dropout=0.0, n_layers=1, n_conv_layers=1), 3, 4, 2, 2),
+}
+
+
+def make_trainer_cases(ref):
+    """The UNMODIFIED reference trainer (model/mpnnlstm.py: NextFramePredictorS2S.train / predict) on a small cube: epoch
+    losses, the forecasts of predict(), initial weights (the climatology is random((1, 366, H, W)) of seed ``clim_seed``).  eval() mode keeps the TransformerConv attention dropout
+    off (the product cannot reproduce torch's dropout stream)."""
+    import importlib
+    import tempfile
+    R = importlib.import_module("model.mpnnlstm")
+    H, W, c, T = 16, 20, 2, 16
+    for name, (thresh, kw, T_in, T_out, tb, epochs) in TRAINER_CASES.items():
+        rng = np.random.default_rng(3)
+        cube = moving_blob(rng, T, H, W)
+        cube = np.concatenate([cube, rng.random((T, H, W, c - 1)).astype(np.float32) * 0.5], -1).astype(np.float32)
+        times = (np.datetime64("2015-03-01").astype("datetime64[ns]").astype("int64") + np.arange(T, dtype=np.int64) * 86_400_000_000_000)
+        mask = np.zeros((H, W), bool)
+        mask[:3, :5] = True
+        mask[10:, 15:] = True
+        clim = np.random.default_rng(5).random((1, 366, H, W)).astype(np.float32)
+        tr_idx, te_idx = [0, 2, 4], [6, 7]
+        torch.manual_seed(4)
+        tr = R.NextFramePredictorS2S(thresh, experiment_name="g", input_features=c, input_timesteps=T_in, output_timesteps=T_out,
+                                     device=torch.device("cpu"), model_kwargs=kw,
+                                     transform_func=dist_from_05 if "Transformer" in kw.get("convolution_type", "") else None)
+        init = {k: _np(v).copy() for k, v in tr.model.state_dict().items()}
+        mk = lambda idx: torch.utils.data.DataLoader(RefWindows(cube, T_in, T_out, times, idx), batch_size=1, shuffle=False)
+        tr.model.eval()
+        cwd = os.getcwd()
+        with tempfile.TemporaryDirectory() as tmp:
+            os.chdir(tmp)                            # the reference writes TensorBoard runs/ into the working directory
+            try:
+                tr.train(mk(tr_idx), mk(te_idx), torch.from_numpy(clim), n_epochs=epochs, lr=0.01, lr_decay=0.5, mask=mask,
+                         truncated_backprop=tb)
+                pred = tr.predict(mk(te_idx), torch.from_numpy(clim), mask=mask)
+            finally:
+                os.chdir(cwd)
+        blob = dict(cube=cube, times=times, mask=mask, clim_seed=np.array(5), tr_idx=np.array(tr_idx), te_idx=np.array(te_idx),
+                    train_loss=np.array(tr.train_loss, np.float64), test_loss=np.array(tr.test_loss, np.float64),
+                    predict=pred.astype(np.float32), last_lr=np.array(tr.scheduler.get_last_lr(), np.float64))
+        for k, v in init.items():
+            blob["init::" + k] = v
+        np.savez_compressed(os.path.join(HERE, f"trainer_{name}.npz"), **blob)
+        print(f"trainer_{name}: train {tr.train_loss} test {tr.test_loss}")
+
+
 def main():
     ref = load_reference()
     if ref is None:
         raise SystemExit("/root/reference is not available: golden vectors can only be generated in the build container")
-    make_graph_cases(ref)
-    make_seq_cases(ref)
+    if "--trainer-only" not in sys.argv:
+        make_graph_cases(ref)
+        make_seq_cases(ref)
+    make_trainer_cases(ref)
 
 
 if __name__ == "__main__":

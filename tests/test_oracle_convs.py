@@ -76,6 +76,35 @@ def test_transformer_dense():
     assert torch.allclose(conv(x, ei, ea), out, atol=1e-9)
 
 
+def test_multi_head_transformer_dense():
+    """heads = 3, concat = True (+ the reference's MHTransformerConv output projection, model/model.py:26-37): every head is
+    a softmax over the in-edges with its own C-wide slices and the 1 / sqrt(C) scale."""
+    ei, _, n = _graph(seed=5)
+    torch.manual_seed(1)
+    H, C = 3, 4
+    conv = R.MHTransformerConv(5, C, heads=H, edge_dim=2, dropout=0.1).double().eval()
+    x = torch.randn(n, 5, dtype=torch.float64)
+    ea = torch.randn(ei.shape[1], 2, dtype=torch.float64)
+    q, k, v = conv.lin_query(x), conv.lin_key(x), conv.lin_value(x)
+    cat = conv.lin_skip(x).clone()
+    for i in range(n):
+        idx = torch.nonzero(ei[1] == i).squeeze(1)
+        if idx.numel() == 0:
+            continue
+        e = conv.lin_edge(ea[idx])
+        for h in range(H):
+            sl = slice(h * C, (h + 1) * C)
+            logits = ((k[ei[0, idx]][:, sl] + e[:, sl]) @ q[i, sl]) / math.sqrt(C)
+            alpha = torch.softmax(logits, 0)
+            cat[i, sl] += (alpha[:, None] * (v[ei[0, idx]][:, sl] + e[:, sl])).sum(0)
+    ref = cat @ conv.lin.weight.T + conv.lin.bias
+    assert torch.allclose(conv(x, ei, ea), ref, atol=1e-10)
+    assert conv(x, ei, ea).shape == (n, C)
+    keys = set(conv.state_dict())
+    assert {"lin.weight", "lin.bias", "lin_skip.weight", "lin_edge.weight", "lin_query.bias"} <= keys
+    assert conv.lin_skip.weight.shape == (H * C, 5) and conv.lin.weight.shape == (C, H * C)
+
+
 def test_init_matches_torch_linear_stream():
     """PyG Linear's default init consumes the RNG like nn.Linear: the product's parameter holders follow it."""
     torch.manual_seed(4)

@@ -49,7 +49,8 @@ def test_graph_sweep(ref, seed):
         assert np.array_equal(lab, b["labels"])
 
 
-@pytest.mark.parametrize("conv,thresh", [("TransformerConv", -np.inf), ("ChebConv", 0.1), ("GCNConv", 0.1), ("TransformerConv", 0.15)])
+@pytest.mark.parametrize("conv,thresh", [("TransformerConv", -np.inf), ("ChebConv", 0.1), ("GCNConv", 0.1), ("TransformerConv", 0.15),
+                                         ("MHTransformerConv", -np.inf), ("MHTransformerConv", 0.15)])
 def test_seq2seq_sweep(ref, conv, thresh):
     from oracle.seq2seq_ref import Seq2Seq as OSeq
     rng = np.random.default_rng(7)

@@ -60,6 +60,18 @@ def test_transformer_conv(be, d_in, d_out, quadtree):
     _check_module(be, lambda: R.TransformerConv(d_in, d_out, **kw), lambda: C.TransformerConv(d_in, d_out, **kw), ei, ea, n, d_in)
 
 
+@pytest.mark.parametrize("d_in,d_out,heads", [(4, 32, 3), (8, 16, 3), (32, 32, 3), (33, 8, 2), (32, 1, 3)])
+@pytest.mark.parametrize("quadtree", [True, False])
+def test_mh_transformer_conv(be, d_in, d_out, heads, quadtree):
+    """the reference's MHTransformerConv (model/model.py:26-37; 3 heads + output projection): forward, input
+    gradient and every parameter gradient against the oracle restatement."""
+    import quadtree_mpnnlstm_b200.convs as C
+    from oracle import convs_ref as R
+    ei, ea, n = _graph(4, quadtree=quadtree)
+    kw = dict(heads=heads, edge_dim=2, dropout=0.1)
+    _check_module(be, lambda: R.MHTransformerConv(d_in, d_out, **kw), lambda: C.MHTransformerConv(d_in, d_out, **kw), ei, ea, n, d_in)
+
+
 @pytest.mark.parametrize("d_in,d_out", [(4, 16), (16, 16), (17, 16), (16, 1), (32, 32)])
 @pytest.mark.parametrize("weighted", [True, False])
 def test_cheb_conv(be, d_in, d_out, weighted):
@@ -82,7 +94,8 @@ def test_gcn_conv(be, d_in, d_out, self_loops):
 
 @pytest.mark.parametrize("conv,n_conv_layers,f_in,hid", [("TransformerConv", 1, 4, 32), ("TransformerConv", 3, 8, 32),
                                                          ("ChebConv", 1, 4, 16), ("ChebConv", 2, 4, 16),
-                                                         ("GCNConv", 2, 4, 16), ("TransformerConv", 2, 5, 8)])
+                                                         ("GCNConv", 2, 4, 16), ("TransformerConv", 2, 5, 8),
+                                                         ("MHTransformerConv", 2, 5, 8)])
 @pytest.mark.parametrize("path", ["tc", "tc_pw", "tc_1t", "tc_2pass", "ffma", "modular"])
 def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     import quadtree_mpnnlstm_b200.model as M
@@ -109,7 +122,7 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     monkeypatch.setattr(FZ, "TC_BWD", path.startswith("tc"))
     n_fused = lambda: sum(_lib.CALL_COUNTS.get(k, 0) for k in ("qmp_fused_fwd", "qmp_fused_fwd_tc", "qmp_fused_cell_fwd"))
     calls_before = n_fused()
-    ei, ea, n = _graph(4, use_edge_attrs=(conv == "TransformerConv"))
+    ei, ea, n = _graph(4, use_edge_attrs=(conv in ("TransformerConv", "MHTransformerConv")))
     torch.manual_seed(11)
     ref = R.GConvLSTM(f_in, hid, n_conv_layers, conv)
     gpu = be.dev(M.GConvLSTM(f_in, hid, n_conv_layers, conv))

@@ -133,6 +133,18 @@ def test_gcn_quadtree_remesh_every_2(be):
     _run_pair(be, kw, x, y, cl, mask, remesh_every=2)
 
 
+def test_multi_head_transformer_seq2seq(be):
+    """the driver with convolution_type='MHTransformerConv' (model/model.py:26-37, 52; edge attributes on,
+    seq2seq.py:244) on a dynamic quadtree mesh."""
+    H, W = 24, 32
+    x, y, cl = _data(6, 3, 3, H, W, c=2)
+    rng = np.random.default_rng(2)
+    mask = rng.random((H, W)) > 0.85
+    kw = dict(hidden_size=8, dropout=0.0, thresh=0.15, input_timesteps=3, input_features=5, output_timesteps=3,
+              n_layers=1, n_conv_layers=2, convolution_type="MHTransformerConv", transform_func=dist_from_05)
+    _run_pair(be, kw, x, y, cl, mask)
+
+
 def test_state_dict_keys_match_reference_layout(be):
     import quadtree_mpnnlstm_b200 as q
     m = q.Seq2Seq(hidden_size=8, dropout=0.1, thresh=-np.inf, input_features=8, n_layers=1, n_conv_layers=2,

@@ -77,8 +77,44 @@ def test_trainer_matches_reference_trainer(be, tmp_path, monkeypatch):
     again = q.NextFramePredictorS2S(device=be.device, model_kwargs=kw, **args)
     again.load(str(tmp_path))
     assert all(torch.equal(a, b) for a, b in zip(again.model.state_dict().values(), mine.model.state_dict().values()))
-    with pytest.raises(NotImplementedError):
+    # truncated back-propagation (the reference's default of 45): a chunk that runs past the last forecast step raises in the
+    # reference (output_timesteps = 3 is not a multiple of 2: unroll step 3 indexes y[3]) -- and here
+    with pytest.raises(IndexError):
         mine.train(ds(tr_idx), ds(te_idx), be.dev(clim), n_epochs=1, mask=mask, truncated_backprop=2)
+
+
+@pytest.mark.parametrize("case", ["quadtree_cheb", "pixelwise_transformer", "quadtree_cheb_truncated"])
+def test_trainer_matches_reference_golden(be, case, tmp_path, monkeypatch):
+    """SURVEY 8(f).1-2 pinned ON THE GPU: NextFramePredictorS2S.train / predict and DeviceWindowDataset against epoch losses and
+    forecasts that the UNMODIFIED reference trainer produced (tests/golden/make_golden.py: make_trainer_cases) -- dynamic
+    quadtree + ChebConv, pixel-wise mesh + TransformerConv (the ice_exp default), and the truncated-BPTT loop
+    (model/mpnnlstm.py:281-313)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import TRAINER_CASES
+    from helpers import dist_from_05
+    import quadtree_mpnnlstm_b200 as q
+    monkeypatch.chdir(tmp_path)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"trainer_{case}.npz"))
+    thresh, kw, T_in, T_out, tb, epochs = TRAINER_CASES[case]
+    cube, times, mask = g["cube"], g["times"], g["mask"]
+    H, W, c = cube.shape[1:]
+    clim = torch.from_numpy(np.random.default_rng(int(g["clim_seed"])).random((1, 366, H, W)).astype(np.float32))
+    tf = dist_from_05 if "Transformer" in kw.get("convolution_type", "") else None
+    mine = q.NextFramePredictorS2S(thresh, experiment_name="g", input_features=c, input_timesteps=T_in, output_timesteps=T_out,
+                                   device=be.device, model_kwargs=kw, transform_func=tf)
+    mine.model.load_state_dict({k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("init::")})
+    dcube = be.dev(torch.from_numpy(cube))
+    ds = lambda idx: q.DeviceWindowDataset(dcube, T_in, T_out, times=times, indices=[int(i) for i in idx])
+    mine.model.eval()
+    mine.train(ds(g["tr_idx"]), ds(g["te_idx"]), be.dev(clim), n_epochs=epochs, lr=0.01, lr_decay=0.5, mask=mask, truncated_backprop=tb)
+    assert np.allclose(mine.train_loss, g["train_loss"], rtol=2e-3), (mine.train_loss, g["train_loss"])
+    assert np.allclose(mine.test_loss, g["test_loss"], rtol=2e-3), (mine.test_loss, g["test_loss"])
+    assert np.allclose(mine.scheduler.get_last_lr(), g["last_lr"])
+    pred = mine.predict(ds(g["te_idx"]), be.dev(clim), mask=mask)
+    assert pred.shape == g["predict"].shape
+    assert np.array_equal(np.isnan(pred), np.isnan(g["predict"]))
+    assert np.nanmax(np.abs(pred - g["predict"])) < 2e-3
 
 
 def test_device_window_dataset_layout():
