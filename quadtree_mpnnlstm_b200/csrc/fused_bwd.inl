@@ -93,7 +93,7 @@ __device__ __forceinline__ void conv_bwd_target(const FusedBwdArgs& a, int i, in
         float dal = fmaf(dz[DC], a0, fmaf(dz[DC + 1], a1, dz[DC + 2]));
 #pragma unroll
         for (int k = 0; k < DC; ++k) dal = fmaf(dz[k], xj[k], dal);
-        dal *= fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
+        dal *= fdropout_scale(QMP_SEED_SM, (long long)kk * a.NC + c, a.drop_p);
         const float al = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li;
         tsum = fmaf(al, dal, tsum);
         a.ds[(size_t)kk * a.NC + c] = dal;       // stash, finalised in pass 2
@@ -109,7 +109,7 @@ __device__ __forceinline__ void conv_bwd_target(const FusedBwdArgs& a, int i, in
         const float al = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li;
         const float dsv = al * (a.ds[(size_t)kk * a.NC + c] - tsum);
         a.ds[(size_t)kk * a.NC + c] = dsv;
-        const float alk = al * fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
+        const float alk = al * fdropout_scale(QMP_SEED_SM, (long long)kk * a.NC + c, a.drop_p);
 #pragma unroll
         for (int k = 0; k < DC; ++k) {
             du[k] = fmaf(dsv, xj[k], du[k]);
@@ -152,6 +152,7 @@ __device__ __forceinline__ void conv_bwd_target(const FusedBwdArgs& a, int i, in
 
 template <int DAC, int DBC>
 __global__ void __launch_bounds__(128) fused_bwd_target_kernel(FusedBwdArgs a) {
+    qmp_seed_init(a.seed, a.salt);
     extern __shared__ __align__(16) float sw[];
     constexpr int TA = (DAC > 0) ? BwdSizes<(DAC > 0 ? DAC : 4)>::TOTAL : 0;
     constexpr int TB = BwdSizes<DBC>::TOTAL;
@@ -196,7 +197,7 @@ __device__ __forceinline__ void conv_bwd_source(const FusedBwdArgs& a, int j, in
     for (int kk = a.ptr[j]; kk < k1; ++kk) {
         const int i = a.nbr[kk], kin = a.kin[kk];
         const float al = __expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
-                         fdropout_scale(QMP_SEED(a), (long long)kin * a.NC + c, a.drop_p);
+                         fdropout_scale(QMP_SEED_SM, (long long)kin * a.NC + c, a.drop_p);
         const float dsv = a.ds[(size_t)kin * a.NC + c];
         float g[FC];
         load_dP(g, a, i, c);
@@ -235,6 +236,7 @@ __device__ __forceinline__ void conv_bwd_source(const FusedBwdArgs& a, int j, in
 
 template <int DAC, int DBC>
 __global__ void __launch_bounds__(128) fused_bwd_source_kernel(FusedBwdArgs a) {
+    qmp_seed_init(a.seed, a.salt);
     extern __shared__ __align__(16) float sw[];
     constexpr int TA = (DAC > 0) ? BwdSizes<(DAC > 0 ? DAC : 4)>::TOTAL : 0;
     constexpr int TB = BwdSizes<DBC>::TOTAL;

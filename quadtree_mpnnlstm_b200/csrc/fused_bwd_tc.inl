@@ -195,7 +195,7 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
         float dal = fmaf(dz[DC], a0, fmaf(dz[DC + 1], a1, dz[DC + 2]));
 #pragma unroll
         for (int k = 0; k < DC; ++k) dal = fmaf(dz[k], xj[k], dal);
-        return dal * fdropout_scale(QMP_SEED(a), (long long)e * a.NC + c, a.drop_p);
+        return dal * fdropout_scale(QMP_SEED_SM, (long long)e * a.NC + c, a.drop_p);
     };
     if (j0 >= 0) dal4[0] = dalpha(k0, xa, te.e0[0], te.e1[0]);
     if (j1 >= 0) dal4[1] = dalpha(k0 + 1, xb, te.e0[1], te.e1[1]);
@@ -222,7 +222,7 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
     auto accum = [&](int e, const float(&xj)[DC], float a0, float a1, float al, float dal) {
         const float dsv = al * (dal - tsum);
         a.ds[(size_t)e * a.NC + c] = dsv;
-        const float alk = al * fdropout_scale(QMP_SEED(a), (long long)e * a.NC + c, a.drop_p);
+        const float alk = al * fdropout_scale(QMP_SEED_SM, (long long)e * a.NC + c, a.drop_p);
 #pragma unroll
         for (int k = 0; k < DC; ++k) {
             du[k] = fmaf(dsv, xj[k], du[k]);
@@ -288,14 +288,14 @@ __device__ __forceinline__ void conv_bwd_target_tc(TcCtx& cx, const FusedBwdArgs
             for (int e = 0; e < 4; ++e) {
                 const int j = e == 0 ? j0 : e == 1 ? j1 : e == 2 ? j2 : j3;
                 if (more(j >= 0))
-                    push(j, al4[e] * (dal4[e] - tsum), al4[e] * fdropout_scale(QMP_SEED(a), (long long)(k0 + e) * a.NC + c, a.drop_p));
+                    push(j, al4[e] * (dal4[e] - tsum), al4[e] * fdropout_scale(QMP_SEED_SM, (long long)(k0 + e) * a.NC + c, a.drop_p));
             }
             for (int kk = k0 + 4; more(kk < k1); ++kk) {
                 const bool on = kk < k1;
                 float dsv = 0.f, alk = 0.f;
                 if (on) {
                     dsv = a.ds[(size_t)kk * a.NC + c];
-                    alk = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li * fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
+                    alk = __expf(a.logit[(size_t)kk * a.NC + c] - m) * li * fdropout_scale(QMP_SEED_SM, (long long)kk * a.NC + c, a.drop_p);
                 }
                 push(on ? a.nbr[kk] : -1, dsv, alk);
             }
@@ -357,7 +357,7 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
     };
     auto coef = [&](int i, int kin, float& al, float& dsv) {
         al = __expf(a.logit[(size_t)kin * a.NC + c] - a.mstat[(size_t)i * a.NC + c]) * a.linv[(size_t)i * a.NC + c] *
-             fdropout_scale(QMP_SEED(a), (long long)kin * a.NC + c, a.drop_p);
+             fdropout_scale(QMP_SEED_SM, (long long)kin * a.NC + c, a.drop_p);
         dsv = a.ds[(size_t)kin * a.NC + c];
     };
     // out-edges 0..3: targets and in-CSR slots were loaded once per tile (te.j = target, te.e0 = slot as int bits)
@@ -424,6 +424,7 @@ __device__ __forceinline__ void conv_bwd_source_tc(TcCtx& cx, const FusedBwdArgs
 
 template <int DAC, int DBC, int KIND>
 __global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_constant__ FusedBwdArgs a) {
+    qmp_seed_init(a.seed, a.salt);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[3];
     __shared__ uint32_t tmem_slot;

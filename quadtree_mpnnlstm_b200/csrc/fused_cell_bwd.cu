@@ -117,7 +117,7 @@ __device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t*
         const int k0 = x.k0, k1 = x.k1;
         auto dalpha = [&](int kk, const float4& xj, const float2& ev, float lg, float& al, float& keep) {
             al = fast_exp(lg - m) * li;
-            keep = fdropout_scale(QMP_SEED(a), (long long)kk * 8 + c, a.drop_p);
+            keep = fdropout_scale(QMP_SEED_SM, (long long)kk * 8 + c, a.drop_p);
             return (fmaf(dz.w, xj.w, fmaf(dz.z, xj.z, fmaf(dz.y, xj.y, dz.x * xj.x))) + fmaf(dze.x, ev.x, fmaf(dze.y, ev.y, dze.z))) * keep;
         };
         auto fetch = [&](int kk, int& j, float4& xj, float2& ev, float& lg) {       // in-edges beyond the fourth (quadtree meshes)
@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
     __shared__ uint32_t tmem_slot;
     using L = CellBwdLayout;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    qmp_seed_init(a.seed, a.salt);
     float* exch = reinterpret_cast<float*>(smem + L::BYTES);
     if (t == 0) {
         tc::mbar_init(&bars[0], 1);
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
                         keep = 0.f;
                         if (on) {
                             al = fast_exp(lg - m) * li;
-                            keep = fdropout_scale(QMP_SEED(a), (long long)kk * 8 + crole, a.drop_p);
+                            keep = fdropout_scale(QMP_SEED_SM, (long long)kk * 8 + crole, a.drop_p);
                         }
                         return (tot + fmaf(dzt.x, ev.x, fmaf(dzt.y, ev.y, dzt.z))) * keep;
                     };

@@ -118,7 +118,7 @@ __device__ __forceinline__ void cell_xconv(const FusedFwdArgs& a, const uint8_t*
         a.logit[(size_t)kk * 8 + cg] = s;
         const float mn = fmaxf(m, s);
         const float sc = fast_exp(m - mn), pe = fast_exp(s - mn);
-        const float pk = pe * fdropout_scale(QMP_SEED(a), (long long)kk * 8 + cg, a.drop_p);
+        const float pk = pe * fdropout_scale(QMP_SEED_SM, (long long)kk * 8 + cg, a.drop_p);
         l = fmaf(l, sc, pe);
         zs = fmaf(zs, sc, pk);
         ze0 = fmaf(ze0, sc, pk * ev.x);
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
     __shared__ uint32_t tmem_slot;
     using L = CellLayout;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    qmp_seed_init(a.seed, a.salt);
     float* prm = reinterpret_cast<float*>(smem + L::BYTES);
     float* exch = prm + 13 * FC;
     CELL_CTA(0);
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
                     const float mn = fmaxf(m[r], gm);
                     sc[r] = (mn == -INFINITY) ? 1.f : fast_exp(m[r] - mn);
                     const float pe = on ? fast_exp(s - mn) : 0.f;
-                    pk[r] = pe * fdropout_scale(QMP_SEED(a), (long long)kk * 8 + c, a.drop_p);
+                    pk[r] = pe * fdropout_scale(QMP_SEED_SM, (long long)kk * 8 + c, a.drop_p);
                     l[r] = fmaf(l[r], sc[r], quad_sum(pe));
                     zs[r] = fmaf(zs[r], sc[r], quad_sum(pk[r]));
                     ze0[r] = fmaf(ze0[r], sc[r], quad_sum(pk[r] * ev.x));

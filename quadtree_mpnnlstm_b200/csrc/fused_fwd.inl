@@ -63,7 +63,7 @@ __device__ __forceinline__ void conv_accumulate(const FusedFwdArgs& a, int i, in
         a.logit[(size_t)kk * a.NC + c] = s;
         const float mn = fmaxf(m, s);
         const float sc = __expf(m - mn), p = __expf(s - mn);
-        const float pk = p * fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
+        const float pk = p * fdropout_scale(QMP_SEED_SM, (long long)kk * a.NC + c, a.drop_p);
         l = fmaf(l, sc, p);
         zs = fmaf(zs, sc, pk);
         ze0 = fmaf(ze0, sc, pk * a0);
@@ -181,6 +181,7 @@ __device__ __forceinline__ void gate_epilogue(const FusedFwdArgs& a, int i, int 
 
 template <int DAC, int DBC>
 __global__ void __launch_bounds__(128) fused_fwd_kernel(FusedFwdArgs a) {
+    qmp_seed_init(a.seed, a.salt);
     extern __shared__ __align__(16) float sw[];
     constexpr int TA = (DAC > 0) ? ConvSizes<(DAC > 0 ? DAC : 4)>::TOTAL : 0;
     constexpr int TB = ConvSizes<DBC>::TOTAL;

@@ -125,7 +125,7 @@ __device__ __forceinline__ void pw_edge(const FusedFwdArgs& a, int kk, int c, bo
     if (writer) a.logit[(size_t)kk * a.NC + c] = s;
     const float mn = fmaxf(m, s);
     const float sc = __expf(m - mn), p = __expf(s - mn);
-    const float pk = p * fdropout_scale(QMP_SEED(a), (long long)kk * a.NC + c, a.drop_p);
+    const float pk = p * fdropout_scale(QMP_SEED_SM, (long long)kk * a.NC + c, a.drop_p);
     l = fmaf(l, sc, p);
     zs = fmaf(zs, sc, pk);
     ze0 = fmaf(ze0, sc, pk * e0);
@@ -348,6 +348,7 @@ __device__ __forceinline__ void gate_epilogue_pw(TcCtx& cx, const PwCtx& pw, con
 
 template <int DAC>
 __global__ void __launch_bounds__(256, 2) fused_fwd_pw_kernel(const __grid_constant__ FusedFwdArgs a) {
+    qmp_seed_init(a.seed, a.salt);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[3];
     __shared__ uint32_t tmem_slot;
