@@ -48,6 +48,123 @@ def pack_fused(convs, DC):
     return torch.cat([W1p.flatten(1), b1p, W2p.flatten(1), W3p.flatten(1), b3p], dim=1).contiguous()
 
 
+_PARAMS_PER_CONV = 9      # lin_query.{weight,bias}, lin_key.{weight,bias}, lin_value.{weight,bias}, lin_edge.weight, lin_skip.{weight,bias}
+
+
+def _conv_params(c):
+    return (c.lin_query.weight, c.lin_query.bias, c.lin_key.weight, c.lin_key.bias, c.lin_value.weight, c.lin_value.bias,
+            c.lin_edge.weight, c.lin_skip.weight, c.lin_skip.bias)
+
+
+class _ParamView:
+    """The attribute shape ``pack_tconv`` reads (``conv.lin_query.weight`` ...) over plain tensors."""
+
+    class _Lin:
+        __slots__ = ("weight", "bias")
+
+        def __init__(self, weight, bias):
+            self.weight, self.bias = weight, bias
+
+    def __init__(self, ps, out_channels):
+        self.out_channels = out_channels
+        self.lin_query, self.lin_key = self._Lin(ps[0], ps[1]), self._Lin(ps[2], ps[3])
+        self.lin_value, self.lin_edge, self.lin_skip = self._Lin(ps[4], ps[5]), self._Lin(ps[6], None), self._Lin(ps[7], ps[8])
+
+
+class PackFusedFn(torch.autograd.Function):
+    """``pack_fused`` of G TransformerConvs as ONE autograd node with a closed-form backward.
+
+    Built from ~40 small tensor ops per group, the pack used to leave ~100 autograd nodes per group behind; their backward
+    (slice / pad / cat / bmm gradients, then one ``AccumulateGrad`` COPY per parameter because the gradients arrived as
+    strided views) was ~700 of the captured step's 2 181 launches.  Here the backward is a dozen batched ops per group and
+    hands every parameter a contiguous slice of one flat buffer, which ``AccumulateGrad`` adopts without copying -- the
+    parameters' ``.grad`` are views of a few flat buckets (one per conv group), which is also what the data-parallel
+    all-reduce wants (train.TrainStep)."""
+
+    @staticmethod
+    def forward(ctx, DC, C_out, *params):
+        G = len(params) // _PARAMS_PER_CONV
+        convs = [_ParamView(params[_PARAMS_PER_CONV * g:_PARAMS_PER_CONV * (g + 1)], C_out) for g in range(G)]
+        with torch.no_grad():
+            pack = pack_fused(convs, DC)
+        ctx.save_for_backward(*params)
+        ctx.DC, ctx.C_out = DC, C_out
+        return pack
+
+    @staticmethod
+    def backward(ctx, g):
+        import math
+        ps = ctx.saved_tensors
+        G, DC, C = len(ps) // _PARAMS_PER_CONV, ctx.DC, ctx.C_out
+        st = lambda k: torch.stack([ps[_PARAMS_PER_CONV * i + k] for i in range(G)])
+        Wq, bq, Wk, We = st(0), st(1), st(2), st(6)
+        D = Wq.shape[2]
+        o1 = (DC + 2) * DC
+        o2 = o1 + DC + 4
+        o3 = o2 + FC * (DC + 4)
+        o4 = o3 + FC * DC
+        g = g.contiguous()
+        gW1p = g[:, :o1].view(G, DC + 2, DC)
+        gb1p = g[:, o1:o2]
+        gW2p = g[:, o2:o3].view(G, FC, DC + 4)[:, :C]
+        gW3 = g[:, o3:o4].view(G, FC, DC)[:, :C, :D]
+        gb3 = g[:, o4:o4 + C]
+        # un-pad: rows / columns 0..D-1 = u part, DC, DC+1 = edge-attribute part
+        gW1b = torch.cat([torch.cat([gW1p[:, :D, :D], gW1p[:, DC:DC + 2, :D]], dim=1),
+                          torch.cat([gb1p[:, :D], gb1p[:, DC:DC + 2]], dim=1).unsqueeze(-1)], dim=2)        # [G, D+2, D+1]
+        s = 1.0 / math.sqrt(C)
+        KE = torch.cat([Wk, We], dim=2)                                   # [G, C, D+2]
+        QB = torch.cat([Wq, bq.unsqueeze(-1)], dim=2)                     # [G, C, D+1]
+        gKE = torch.bmm(QB, gW1b.transpose(1, 2)) * s                     # [G, C, D+2]
+        gQB = torch.bmm(KE, gW1b) * s                                     # [G, C, D+1]
+        pieces = [gQB[..., :D], gQB[..., D], gKE[..., :D], torch.zeros_like(bq), gW2p[..., :D], gW2p[..., DC + 2],
+                  gKE[..., D:] + gW2p[..., DC:DC + 2], gW3, gb3]
+        flat = torch.cat([t.reshape(G, -1) for t in pieces], dim=1)       # [G, per-conv parameter count]: one bucket per group
+        out, off = [None, None], 0
+        views = []
+        for k, t in enumerate(pieces):
+            n = t[0].numel()
+            views.append((off, n, tuple(ps[k].shape)))
+            off += n
+        grads = []
+        for i in range(G):
+            for k, (o, n, shape) in enumerate(views):
+                grads.append(flat[i, o:o + n].view(shape) if ctx.needs_input_grad[2 + _PARAMS_PER_CONV * i + k] else None)
+        return (None, None) + tuple(grads)
+
+
+def pack_fused_fn(convs, DC):
+    """``pack_fused(convs, DC)`` through PackFusedFn (one autograd node, copy-free parameter gradients)."""
+    ps = []
+    for c in convs:
+        ps.extend(_conv_params(c))
+    return PackFusedFn.apply(DC, convs[0].out_channels, *ps)
+
+
+class RowsPackFn(torch.autograd.Function):
+    """``torch.cat`` of flattened parameters into one vector / ``torch.stack`` of equal-length rows, with a backward that hands
+    every parameter a contiguous slice of the incoming gradient (adopted by ``AccumulateGrad`` without a copy)."""
+
+    @staticmethod
+    def forward(ctx, rows, *params):
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.rows = rows
+        flat = torch.cat([p.reshape(-1) for p in params])
+        return flat.view(rows, -1) if rows else flat
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().view(-1).clone()      # own storage: the slices outlive this node as the parameters' .grad
+        out, off = [], 0
+        for k, shape in enumerate(ctx.shapes):
+            n = 1
+            for d in shape:
+                n *= d
+            out.append(g[off:off + n].view(shape) if ctx.needs_input_grad[1 + k] else None)
+            off += n
+        return (None,) + tuple(out)
+
+
 def _pad8(v):
     return (v + 7) // 8 * 8
 
@@ -248,10 +365,9 @@ def pack_tconv1(conv):
     """P [136] = Wq | Wk | Wv | Ws (32 each) | bq bk bv bs | we0 we1 | 0 0 from a PyG-named TransformerConv(32 -> 1)
     (layout: csrc/tconv1.cu).  No 1/sqrt(C) factor: C = 1."""
     assert conv.out_channels == 1 and conv.in_channels == FC
-    v = lambda t: t.reshape(-1)
-    return torch.cat([v(conv.lin_query.weight), v(conv.lin_key.weight), v(conv.lin_value.weight), v(conv.lin_skip.weight),
-                      v(conv.lin_query.bias), v(conv.lin_key.bias), v(conv.lin_value.bias), v(conv.lin_skip.bias),
-                      v(conv.lin_edge.weight), conv.lin_edge.weight.new_zeros(2)]).contiguous()
+    return RowsPackFn.apply(0, conv.lin_query.weight, conv.lin_key.weight, conv.lin_value.weight, conv.lin_skip.weight,
+                            conv.lin_query.bias, conv.lin_key.bias, conv.lin_value.bias, conv.lin_skip.bias,
+                            conv.lin_edge.weight, conv.lin_edge.weight.new_zeros(2))
 
 
 class ScalarTConvFn(torch.autograd.Function):

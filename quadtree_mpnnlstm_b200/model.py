@@ -129,7 +129,7 @@ class GConvLSTM(nn.Module):
                     self.b_c.view(-1), self.b_o.view(-1)]
             for nm in (norm_h, norm_c, norm_o):
                 rows += [nm.weight, nm.bias] if nm is not None else [one, zero]
-            return torch.stack(rows)
+            return _fused.RowsPackFn.apply(len(rows), *rows)     # == torch.stack(rows), copy-free parameter gradients
         if self._fusable():         # consumed once per timestep by FusedGroupFn: gradients accumulate in place (fused._GradAccum)
             return self._cached(("gates", id(norm_h), id(norm_c), id(norm_o)), epoch, lambda: _fused.shared_pack(build()))
         return self._cached(("gates", id(norm_h), id(norm_c), id(norm_o)), epoch, build)
@@ -203,8 +203,8 @@ class GConvLSTM(nn.Module):
         p = self.conv_x_i.convolutions[0].dropout if self.training else 0.0
         seed = (lambda: next_seed()) if p > 0 else (lambda: 0)
         dac = _fused.cap_of(Fin, True)
-        wa = self._cached(("fa", 0), epoch, lambda: _fused.shared_pack(_fused.pack_fused(self._convs("x", 0), dac)))
-        wb = self._cached(("fb", 0), epoch, lambda: _fused.shared_pack(_fused.pack_fused(self._convs("h", 0), _fused.FC)))
+        wa = self._cached(("fa", 0), epoch, lambda: _fused.shared_pack(_fused.pack_fused_fn(self._convs("x", 0), dac)))
+        wb = self._cached(("fb", 0), epoch, lambda: _fused.shared_pack(_fused.pack_fused_fn(self._convs("h", 0), _fused.FC)))
         flags = (bool(norm_h), bool(norm_c), bool(norm_o), bool(want_head), float(eps))
 
         def cfg(DA, GA, DB, GB, shared, mode):
@@ -215,7 +215,7 @@ class GConvLSTM(nn.Module):
         cur = _fused.FusedGroupFn.apply(X, wa, H, wb, None, None, None, csr, cfg(Fin, 4, Cw, 4, True, 0))
         for l in range(1, S):
             w = self._cached(("fb", l), epoch,
-                             lambda: _fused.shared_pack(_fused.pack_fused(self._convs("x", l) + self._convs("h", l), _fused.FC)))
+                             lambda: _fused.shared_pack(_fused.pack_fused_fn(self._convs("x", l) + self._convs("h", l), _fused.FC)))
             if l < S - 1:
                 cur = _fused.FusedGroupFn.apply(None, None, cur, w, None, None, None, csr, cfg(0, 0, Cw, 8, False, 0))
             else:

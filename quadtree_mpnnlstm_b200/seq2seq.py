@@ -155,8 +155,7 @@ class Decoder(torch.nn.Module):
             sd = (lambda: next_seed()) if p > 0 else (lambda: 0)
             if _fused.ENABLED and self.hidden_size == _fused.FC and head.shape[1] == _fused.HEADW:
                 # two fused launches (csrc/fused_fwd.inl): fc_out1 on the 36-wide padded head rows, relu; fc_out2 -> 1
-                w1 = self._cached("ffc1", epoch, lambda: _fused.shared_pack(_fused.pack_fused([self.fc_out1], _fused.HEADW)))
-                w2 = self._cached("ffc2", epoch, lambda: _fused.shared_pack(_fused.pack_fused([self.fc_out2], _fused.FC)))
+                w1 = self._cached("ffc1", epoch, lambda: _fused.shared_pack(_fused.pack_fused_fn([self.fc_out1], _fused.HEADW)))
                 tail = (False, False, False, False, 1e-5, float(p))
                 h1 = _fused.FusedGroupFn.apply(None, None, head, w1, None, None, None, csr,
                                                (0, 0, _fused.HEADW, 1, True, 0, True, _fused.FC) + tail + (sd(),))
@@ -164,6 +163,7 @@ class Decoder(torch.nn.Module):
                     # one output channel: scalar query / key / value records instead of 32-wide rows (csrc/tconv1.cu)
                     P2 = self._cached("ftc1", epoch, lambda: _fused.shared_pack(_fused.pack_tconv1(self.fc_out2)))
                     return _fused.ScalarTConvFn.apply(h1, P2, csr, float(p), sd())
+                w2 = self._cached("ffc2", epoch, lambda: _fused.shared_pack(_fused.pack_fused_fn([self.fc_out2], _fused.FC)))
                 return _fused.FusedGroupFn.apply(None, None, h1, w2, None, None, None, csr,
                                                  (0, 0, _fused.FC, 1, True, 0, False, 1) + tail + (sd(),))
             pk1 = self._cached("fc1", epoch, lambda: pack_tconv([self.fc_out1]))
