@@ -230,7 +230,7 @@ def _classify(name, args):
     """(group, short kernel key) of one C-ABI call of the training step."""
     if name == "qmp_fused_cell_fwd":
         return "decoder_cell_fwd", name
-    if name in ("qmp_fused_cell_bwd", "qmp_fused_cell_bwd_full"):
+    if name in ("qmp_fused_cell_bwd", "qmp_fused_cell_bwd_full", "qmp_cell_wgrad"):
         return "decoder_cell_bwd", name
     if name == "qmp_lstm_gates_bwd":        # args: N C gates Craw Cp prm norm_h norm_c norm_o ...
         return ("decoder_cell_bwd" if args[8] else "encoder_bwd"), name

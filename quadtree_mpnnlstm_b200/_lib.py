@@ -45,13 +45,10 @@ SIGNATURES = {
     "qmp_head_finish_bwd": "pppppiiifuppp",
     "qmp_relu_mask": "pplp",
     "qmp_relu_mask_to": "ppplp",
-    "qmp_tc_gemm_probe": "pppiiiip",
     "qmp_fused_fwd": "ippppiiippiiiipiiipippiiifppppppippppfup",
     "qmp_fused_bwd_target": "ippppiiippiiiipiipippppppppppfup",
     "qmp_fused_bwd_source": "ippppiiippiiiipiipippppppfup",
     "qmp_fused_wgrad": "ipiiipiiiiiipippppppp",
-    "qmp_tc_probe2": "pppiiip",
-    "qmp_tc_probe3": "piiiip",
     "qmp_fused_fwd_tc": "ippppiiippiiiipiiipippiiifppppppippppfup",
     "qmp_fused_pack_tc": "piiipp",
     "qmp_fused_bwd_target_tc": "ippppiiippiiiipiipippppppppppfup",
@@ -59,7 +56,8 @@ SIGNATURES = {
     "qmp_fused_bwd_onepass_tc": "ippppiiippiiiipiipippppppppppfup",
     "qmp_fused_pack_cell": "pppp",
     "qmp_fused_pack_cell_bwd": "pppp",
-    "qmp_fused_cell_bwd": "ipppp" "i" "p" "i" "ppp" "i" "ppp" "pppp" "pp" "fup",
+    "qmp_fused_cell_bwd": "ipppp" "i" "p" "i" "ppp" "i" "pppp" "iiif" "pppp" "i" "pp" "ppp" "pppp" "pp" "fup",
+    "qmp_cell_wgrad": "ipipippppppp",
     "qmp_tconv1_fwd": "ipppp" "i" "ppp" "fup",
     "qmp_tconv1_bwd": "ipppp" "i" "ppppp" "i" "p" "fup",
     "qmp_fused_cell_fwd": "ippppipippp" "iiif" "pppppp" "i" "ppppp" "fup",
@@ -73,9 +71,9 @@ KERNELS_PER_CALL = {
     "qmp_adjacency_pixelwise": 5, "qmp_edge_attrs": 1, "qmp_add_positional_encoding": 1,
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
-    "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_relu_mask_to": 1, "qmp_tc_gemm_probe": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
+    "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_relu_mask_to": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
     "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1, "qmp_fused_bwd_target_tc": 1, "qmp_fused_bwd_source_tc": 1, "qmp_fused_bwd_onepass_tc": 1,
-    "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1, "qmp_tconv1_fwd": 2, "qmp_tconv1_bwd": 2, "qmp_fused_pack_cell_bwd": 1, "qmp_fused_cell_bwd": 1,
+    "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1, "qmp_tconv1_fwd": 2, "qmp_tconv1_bwd": 2, "qmp_fused_pack_cell_bwd": 1, "qmp_fused_cell_bwd": 1, "qmp_cell_wgrad": 1,
 }
 CALL_COUNTS = {}
 

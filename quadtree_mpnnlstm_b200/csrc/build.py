@@ -17,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 REPO = os.path.dirname(PKG)
 OUT = os.path.join(PKG, "libqmp_b200.so")
+PROBE_OUT = os.path.join(HERE, "probes", "libqmp_probe.so")      # test hooks only: NOT part of the product library / ABI
 HEADER = os.path.join(REPO, "include", "qmp_b200.h")
 
 NVCC_FLAGS = os.environ.get("QMP_EXTRA_FLAGS", "").split() + (["-DQMP_TIMING_TF32X1"] if os.environ.get("QMP_TIMING_TF32X1") else []) + (["-DQMP_PW_TRACE"] if os.environ.get("QMP_PW_TRACE") else []) + (["-DQMP_CELL_TRACE"] if os.environ.get("QMP_CELL_TRACE") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -62,16 +63,14 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_fused_cell_fwd": "model/model.py:394-463 GConvLSTM.forward of the decoder cell (4 X convs + 4 H convs, gates, norms, head input) -- one persistent launch, gates batched on tcgen05, edge phase 8 lanes per node",
     "qmp_fused_pack_cell": "(weight image of qmp_fused_cell_fwd: the eight convs of the decoder cell side by side)",
     "qmp_fused_cell_image_bytes": "(size of that image)",
-    "qmp_fused_cell_bwd": "autograd of qmp_fused_cell_fwd w.r.t. X and H (target and source side of every edge in one persistent launch) + rows for qmp_fused_wgrad",
+    "qmp_fused_cell_bwd": "autograd of qmp_fused_cell_fwd w.r.t. X and H (target and source side of every edge in one persistent launch) + rows for qmp_cell_wgrad",
+    "qmp_cell_wgrad": "autograd weight gradients of the decoder cell's eight convs (one streaming launch: TMA panels as MN-major tcgen05 operands, 3xTF32)",
     "qmp_fused_pack_cell_bwd": "(weight image of qmp_fused_cell_bwd)",
     "qmp_fused_cell_bwd_image_bytes": "(size of that image)",
     "qmp_tconv1_fwd": "PyG TransformerConv(hidden, 1) = the decoder's fc_out2 (model/seq2seq.py:117-121, 182-187): scalar query / key / value records",
     "qmp_tconv1_bwd": "autograd of the above (input gradient + parameter gradients)",
     "qmp_set_fused_paired": "(switch: two threads per node (paired warps) or one in the tcgen05 fused kernels)",
     "qmp_set_tensor_cores": "(switch: tcgen05 3xTF32 contractions on/off; parity tests run both)",
-    "qmp_tc_probe3": "(test hook: issue cost of small tcgen05 MMAs)",
-    "qmp_tc_probe2": "(test hook: MN-major shared-memory operands and TMEM-resident A operand of tcgen05.mma)",
-    "qmp_tc_gemm_probe": "(test hook for the tcgen05 contraction used by the fused cell kernels)",
     "qmp_exclusive_scan_i32": "(utility: numpy cumsum at model/graph_functions.py:511)",
     "qmp_last_error": "(error text; the reference raises Python exceptions)",
     "qmp_version": "(ABI version)",
@@ -167,7 +166,22 @@ def build(force=False, verbose=False):
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("nvcc failed linking libqmp_b200.so")
+    build_probes(force)
     return OUT
+
+
+def build_probes(force=False):
+    """csrc/probes/*.cu -> csrc/probes/libqmp_probe.so: hardware-convention probes and timing hooks used by tests/ and
+    scripts/ only (tests/probe_lib.py); nothing in the product imports or links it."""
+    srcs = sorted(glob.glob(os.path.join(HERE, "probes", "*.cu"))) + [os.path.join(HERE, "core.cu")]
+    deps = srcs + glob.glob(os.path.join(HERE, "*.cuh"))
+    if not force and os.path.isfile(PROBE_OUT) and os.path.getmtime(PROBE_OUT) >= max(os.path.getmtime(p) for p in deps):
+        return PROBE_OUT
+    res = subprocess.run(["nvcc"] + NVCC_FLAGS + srcs + ["-o", PROBE_OUT], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libqmp_probe.so")
+    return PROBE_OUT
 
 
 if __name__ == "__main__":

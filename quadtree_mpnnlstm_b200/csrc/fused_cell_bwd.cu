@@ -17,6 +17,7 @@
 // ordering is assumed.  Reference: autograd of GConvLSTM.forward (model/model.py:394-463) around PyG TransformerConv.
 #include "fused_fwd.inl"
 #include "fused_cell.cuh"
+#include "lstm_oct.cuh"
 
 namespace qmp {
 
@@ -42,9 +43,18 @@ struct CellBwdArgs {
     const int* ptr; const int* nbr; const float* ea;
     const float* xa; int lda; const float* xb; int ldb;
     const float* usave;                                    // [N, 128] logit projections of the H convs (forward kernel)
-    const float* dP; int lddp;                             // [N, 128] gate pre-activation gradients
+    float* dP; int lddp;                                   // [N, 128] gate pre-activation gradients: input, or -- with `gates` --
+                                                           // OUTPUT of the fused gate backward (the weight-gradient kernel reads it)
+    // gate backward fused into the prologue of every tile (north_star (c); lstm_oct.cuh).  gates == nullptr: dP is an input.
+    const float* gates; const float* Craw; const float* Cprev; const float* prm;      // [N, 128], [N, 32], [N, 32] or null, [13, 32]
+    const float* dHout; const float* dCout; const float* dOdirect; const float* dHead; int lddh;   // each [N, 32] or null; [N, lddh]
+    float* dCprev; float* dparams;                         // [N, 32] or null; [13, 32] accumulated with atomics, or null
+    int norm_h, norm_c, norm_o; float eps;
     const float* logit; const float* mstat; const float* linv;     // [E, 8], [N, 8], [N, 8]
-    float* ZsA; float* dUsA; float* ZsB; float* dUsB;      // [N, 4, 8] and [N, 4, 36]
+    float* zB; float* duB;                                 // [N, 128]: z / du of H conv c in columns 32 c .. 32 c + 31
+    float* sd;                                             // [N, 64]: x(4) | 1 0 0 0 | (ze0 ze1 zs 0) x 4 H convs | 0 (8) | (z(4) | ze0 ze1 zs 0) x 4 X convs
+    float* sg;                                             // [N, 32]: (dw0 dw1) x 4 H convs | du(4) x 4 X convs | (dw0 dw1) x 4 X convs
+                                                           // (panel layout of the weight-gradient kernel, cell_wgrad.cu)
     float* dxa; float* dxb;                                // [N, lda], [N, ldb]: zero on entry
     float drop_p; unsigned long long seed; const unsigned long long* salt;
 };
@@ -163,12 +173,18 @@ __device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t*
             const float dal = dalpha(kk, xj, ev, lg, al, keep);
             accumulate(j, xj, ev, al, keep, dal);
         }
-        float* zr = a.ZsA + ((size_t)i * 4 + c) * 8;
-        st4(zr, z.x, z.y, z.z, z.w);
-        st4(zr + 4, ze0, ze1, zs, 0.f);
-        float* dr = a.dUsA + ((size_t)i * 4 + c) * 8;
-        st4(dr, du.x, du.y, du.z, du.w);
-        st4(dr + 4, dw0, dw1, 0.f, 0.f);
+        float* sdr = a.sd + (size_t)i * 64;
+        st4(sdr + 32 + 8 * c, z.x, z.y, z.z, z.w);
+        st4(sdr + 36 + 8 * c, ze0, ze1, zs, 0.f);
+        if (c == 0) {                                      // the row's shared part: x | 1 0 0 0 ... 0 (8)
+            st4(sdr, xi.x, xi.y, xi.z, xi.w);
+            st4(sdr + 4, 1.f, 0.f, 0.f, 0.f);
+            st4(sdr + 24, 0.f, 0.f, 0.f, 0.f);
+            st4(sdr + 28, 0.f, 0.f, 0.f, 0.f);
+        }
+        float* sgr = a.sg + (size_t)i * 32;
+        st4(sgr + 8 + 4 * c, du.x, du.y, du.z, du.w);
+        *reinterpret_cast<float2*>(sgr + 24 + 2 * c) = make_float2(dw0, dw1);
         // self term: dX_i += W1x^T [du | dw]
         const float dU[6] = {du.x, du.y, du.z, du.w, dw0, dw1};
 #pragma unroll
@@ -221,9 +237,11 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t bars[2];                 // 0: MMA groups, 1: image landed
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_dp[P_COUNT * 32];         // parameter gradients of the fused gate backward, summed over this CTA's nodes
     using L = CellBwdLayout;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     qmp_seed_init(a.seed, a.salt);
+    if (t < P_COUNT * 32) s_dp[t] = 0.f;
     float* exch = reinterpret_cast<float*>(smem + L::BYTES);
     if (t == 0) {
         tc::mbar_init(&bars[0], 1);
@@ -259,7 +277,79 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
             const int tcount = (end - tile0 < T0) ? end - tile0 : T0;
 
             CELL_MARK(1);
-            {
+            if (a.gates) {
+                // ---- gate backward (sigmoid / tanh / peepholes / LayerNorms / head input) in octet layout: dP rows to global
+                // memory (for the weight-gradient kernel) and into exchange plane g (for the contraction below)
+                float dprm[P_COUNT][4];
+#pragma unroll
+                for (int p = 0; p < P_COUNT; ++p)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) dprm[p][k] = 0.f;
+                auto PRM = [&](int p, float (&v)[4]) { f4(v, ldg4(a.prm + p * 32 + 4 * l8)); };
+#pragma unroll 1
+                for (int p = 0; p < 2; ++p) {
+                    if (4 * (warp + 16 * p) >= tcount) continue;           // warp-uniform
+                    const int ln = 4 * (warp + 16 * p) + o8;
+                    const bool valid = ln < tcount;
+                    const int i = tile0 + ln;
+                    const size_t r32 = (size_t)i * 32 + 4 * l8;
+                    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float I[4], F[4], T[4], O[4], Cn[4], cp[4], dH[4], dC[4], dO[4], dhd[4];
+                    const float* gs = a.gates + (size_t)i * 128 + 4 * l8;
+                    f4(I, valid ? ldg4(gs) : zero);
+                    f4(F, valid ? ldg4(gs + 32) : zero);
+                    f4(T, valid ? ldg4(gs + 64) : zero);
+                    f4(O, valid ? ldg4(gs + 96) : zero);
+                    f4(Cn, valid ? ldg4(a.Craw + r32) : zero);
+                    f4(cp, (valid && a.Cprev) ? ldg4(a.Cprev + r32) : zero);
+                    f4(dH, (valid && a.dHout) ? ldg4(a.dHout + r32) : zero);
+                    f4(dC, (valid && a.dCout) ? ldg4(a.dCout + r32) : zero);
+                    f4(dO, (valid && a.dOdirect) ? ldg4(a.dOdirect + r32) : zero);
+                    f4(dhd, (valid && a.dHead) ? ldg4(a.dHead + (size_t)i * a.lddh + 4 * l8) : zero);
+                    float dI[4], dF[4], dT[4], dOp[4], dCp[4];
+                    oct_gate_bwd(I, F, T, O, Cn, cp, dH, dC, dO, dhd, a.dHead != nullptr, a.norm_h, a.norm_c, a.norm_o, a.eps, PRM, dprm, dI,
+                                 dF, dT, dOp, dCp);
+                    if (valid) {
+                        float* dpr = a.dP + (size_t)i * a.lddp + 4 * l8;
+                        st4(dpr, dI[0], dI[1], dI[2], dI[3]);
+                        st4(dpr + 32, dF[0], dF[1], dF[2], dF[3]);
+                        st4(dpr + 64, dT[0], dT[1], dT[2], dT[3]);
+                        st4(dpr + 96, dOp[0], dOp[1], dOp[2], dOp[3]);
+                        if (a.dCprev) st4(a.dCprev + r32, dCp[0], dCp[1], dCp[2], dCp[3]);
+                    }
+                    float* xr = exch + ln * XS + 4 * l8;
+                    st4(xr, dI[0], dI[1], dI[2], dI[3]);
+                    st4(xr + XPLANE, dF[0], dF[1], dF[2], dF[3]);
+                    st4(xr + 2 * XPLANE, dT[0], dT[1], dT[2], dT[3]);
+                    st4(xr + 3 * XPLANE, dOp[0], dOp[1], dOp[2], dOp[3]);
+                }
+                if (a.dparams) {
+#pragma unroll
+                    for (int p = 0; p < P_COUNT; ++p)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float v = dprm[p][k];
+                            v += __shfl_xor_sync(0xffffffffu, v, 8);
+                            v += __shfl_xor_sync(0xffffffffu, v, 16);
+                            if (o8 == 0 && v != 0.f) atomicAdd(&s_dp[p * 32 + 4 * l8 + k], v);
+                        }
+                }
+                cellb_sync();
+                const bool valid = nrow < tcount;
+                const float* row = exch + cg * XPLANE + nrow * XS;
+                const uint32_t base = lane_addr + TB_A + 64 * (uint32_t)cg;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float v[8];
+                    ld8(v, row + 8 * c8);
+                    if (!valid) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = 0.f;
+                    }
+                    cell_stage8(base + 8 * c8, base + 32 + 8 * c8, v);
+                }
+                tc::tmem_st_wait();
+            } else {
                 const int i = tile0 + nrow;
                 const bool valid = nrow < tcount;
                 const float* gp = a.dP + (size_t)i * a.lddp + 32 * cg;
@@ -430,16 +520,16 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
                         const int c = 2 * r2 + c2;
                         st4(xrow + c * XPLANE + 4 * l8, du[c2].x, du[c2].y, du[c2].z, du[c2].w);
                         if (valid) {
-                            st4(a.ZsB + ((size_t)i * 4 + c) * 36 + 4 * l8, z[c2].x, z[c2].y, z[c2].z, z[c2].w);
-                            st4(a.dUsB + ((size_t)i * 4 + c) * 36 + 4 * l8, du[c2].x, du[c2].y, du[c2].z, du[c2].w);
+                            st4(a.zB + (size_t)i * 128 + 32 * c + 4 * l8, z[c2].x, z[c2].y, z[c2].z, z[c2].w);
+                            st4(a.duB + (size_t)i * 128 + 32 * c + 4 * l8, du[c2].x, du[c2].y, du[c2].z, du[c2].w);
                         }
                     }
                     if (e4 == 0) {
                         const int c = 2 * r2 + cc;
                         st4(xrow + c * XPLANE + 32, dw0, dw1, 0.f, 0.f);
                         if (valid) {
-                            st4(a.ZsB + ((size_t)i * 4 + c) * 36 + 32, ze0, ze1, zs, 0.f);
-                            st4(a.dUsB + ((size_t)i * 4 + c) * 36 + 32, dw0, dw1, 0.f, 0.f);
+                            st4(a.sd + (size_t)i * 64 + 8 + 4 * c, ze0, ze1, zs, 0.f);
+                            *reinterpret_cast<float2*>(a.sg + (size_t)i * 32 + 2 * c) = make_float2(dw0, dw1);
                         }
                     }
                 }
@@ -520,6 +610,10 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
     tc::fence_before_sync();
     cellb_sync();
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    if (a.gates && a.dparams && t < P_COUNT * 32) {
+        const float v = s_dp[t];
+        if (v != 0.f) atomicAdd(a.dparams + t, v);
+    }
 }
 
 // ---- weight image ---------------------------------------------------------------------------------------------------
@@ -588,22 +682,34 @@ QMP_API int qmp_fused_pack_cell_bwd(const float* packA, const float* packB, void
 }
 
 // Backward of qmp_fused_cell_fwd with respect to X (dxa [N, lda]) and H (dxb [N, ldb]) -- both are OVERWRITTEN (zeroed here,
-// then accumulated with reductions) -- plus the rows ZsA / dUsA [N, 4, 8], ZsB / dUsB [N, 4, 36] for qmp_fused_wgrad.
+// then accumulated with reductions) -- plus the rows zB / duB [N, 128], sd [N, 64], sg [N, 32] for qmp_cell_wgrad (layout there).
 // usave [N, 128] is the forward kernel's output of that name; dP [N, lddp >= 128] the gate pre-activation gradients.
+// With gates != NULL the gate backward (qmp_lstm_gates_bwd's arguments: gates, Craw, Cprev, params, norm flags, eps, dHout,
+// dCout, dOdirect, dHead / lddh, dCprev, dparams) runs in the prologue of every tile and dP is an OUTPUT; with gates == NULL
+// dP is an input and those arguments are ignored.
 QMP_API int qmp_fused_cell_bwd(int N, const int* in_ptr, const int* in_src, const float* ea, const float* xa, int lda,
-                               const float* xb, int ldb, const void* image, const float* usave, const float* dP, int lddp,
-                               const float* logit, const float* mstat, const float* linv, float* ZsA, float* dUsA, float* ZsB,
-                               float* dUsB, float* dxa, float* dxb, float drop_p, unsigned long long seed, void* stream) {
+                               const float* xb, int ldb, const void* image, const float* usave, float* dP, int lddp,
+                               const float* gates, const float* Craw, const float* Cprev, const float* params, int norm_h, int norm_c,
+                               int norm_o, float eps, const float* dHout, const float* dCout, const float* dOdirect, const float* dHead,
+                               int lddh, float* dCprev, float* dparams,
+                               const float* logit, const float* mstat, const float* linv, float* zB, float* duB, float* sd,
+                               float* sg, float* dxa, float* dxb, float drop_p, unsigned long long seed, void* stream) {
     if (N <= 0) return 0;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     QMP_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ldb >= 32 && lddp % 4 == 0 && lddp >= 128 && al16(xa) && al16(xb) && al16(image) &&
-                    al16(usave) && al16(dP) && al16(ZsA) && al16(dUsA) && al16(ZsB) && al16(dUsB) && al16(dxa) && al16(dxb),
+                    al16(usave) && al16(dP) && al16(zB) && al16(duB) && al16(sd) && al16(sg) && al16(dxa) && al16(dxb),
                 "qmp_fused_cell_bwd: rows must be 16-byte aligned");
     QMP_REQUIRE(!ea || (reinterpret_cast<uintptr_t>(ea) & 7) == 0, "qmp_fused_cell_bwd: edge attributes must be 8-byte aligned");
     CellBwdArgs a{};
     a.N = N; a.ptr = in_ptr; a.nbr = in_src; a.ea = ea; a.xa = xa; a.lda = lda; a.xb = xb; a.ldb = ldb; a.usave = usave;
-    a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.ZsA = ZsA; a.dUsA = dUsA; a.ZsB = ZsB;
-    a.dUsB = dUsB; a.dxa = dxa; a.dxb = dxb; a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
+    a.dP = dP; a.lddp = lddp; a.logit = logit; a.mstat = mstat; a.linv = linv; a.zB = zB; a.duB = duB; a.sd = sd;
+    a.gates = gates; a.Craw = Craw; a.Cprev = Cprev; a.prm = params; a.norm_h = norm_h; a.norm_c = norm_c; a.norm_o = norm_o; a.eps = eps;
+    a.dHout = dHout; a.dCout = dCout; a.dOdirect = dOdirect; a.dHead = dHead; a.lddh = lddh; a.dCprev = dCprev; a.dparams = dparams;
+    if (gates)
+        QMP_REQUIRE(Craw && params && al16(gates) && al16(Craw) && al16(Cprev) && al16(params) && al16(dHout) && al16(dCout) &&
+                        al16(dOdirect) && al16(dHead) && al16(dCprev) && (!dHead || lddh % 4 == 0),
+                    "qmp_fused_cell_bwd: gate-backward rows must be 16-byte aligned");
+    a.sg = sg; a.dxa = dxa; a.dxb = dxb; a.drop_p = drop_p; a.seed = seed; a.salt = qmp::dropout_salt();
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;

@@ -10,10 +10,10 @@
 // One warp per node, lane = channel (C <= 128: up to 4 channels per lane), so every LayerNorm
 // statistic is a warp reduction and no intermediate leaves registers.
 #include "common.cuh"
+#include "lstm_oct.cuh"
 
 namespace qmp {
 
-enum { P_WCI = 0, P_WCF, P_WCO, P_BI, P_BF, P_BC, P_BO, P_GH, P_BH, P_GC, P_BCN, P_GO, P_BON, P_COUNT };
 
 struct LstmArgs {
     int N, C;
@@ -268,53 +268,6 @@ __global__ void __launch_bounds__(256) lstm_bwd_kernel(LstmArgs a) {
         }
 }
 
-// ---- C == 32: gate backward in OCTET layout -- 8 lanes per node, 4 channels (one float4) per lane, 4 nodes per warp
-// instruction.  Same math as lstm_bwd_kernel<1>; rows move as 16-byte accesses, the LayerNorm statistics are 3-step
-// reductions and a lane keeps its 13 x 4 parameter-gradient accumulators in registers over all its nodes.
-__device__ __forceinline__ float oct_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    return v + __shfl_xor_sync(0xffffffffu, v, 4);
-}
-__device__ __forceinline__ void f4(float (&v)[4], const float4 q) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float fast_tanh(float x) {
-    const float e = __expf(-2.f * fabsf(x));
-    return copysignf(__fdividef(1.f - e, 1.f + e), x);
-}
-
-// y = LN(x) * gamma + beta over the 32 channels of an octet: xhat of this lane's 4 channels and rstd
-__device__ __forceinline__ float oct_ln_fwd(const float (&x)[4], float eps, float (&xh)[4]) {
-    const float mean = oct_sum((x[0] + x[1]) + (x[2] + x[3])) * (1.f / 32.f);
-    float d[4], v = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        d[k] = x[k] - mean;
-        v = fmaf(d[k], d[k], v);
-    }
-    const float rstd = rsqrtf(oct_sum(v) * (1.f / 32.f) + eps);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) xh[k] = d[k] * rstd;
-    return rstd;
-}
-// dx given dy (in place), accumulating dgamma / dbeta
-__device__ __forceinline__ void oct_ln_bwd(const float (&xh)[4], float (&dy)[4], const float (&gamma)[4], float rstd,
-                                           float (&dgamma)[4], float (&dbeta)[4]) {
-    float g[4], s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        dgamma[k] = fmaf(dy[k], xh[k], dgamma[k]);
-        dbeta[k] += dy[k];
-        g[k] = dy[k] * gamma[k];
-        s1 += g[k];
-        s2 = fmaf(g[k], xh[k], s2);
-    }
-    s1 = oct_sum(s1) * (1.f / 32.f);
-    s2 = oct_sum(s2) * (1.f / 32.f);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) dy[k] = rstd * (g[k] - s1 - xh[k] * s2);
-}
-
 __global__ void __launch_bounds__(256, 2) lstm_bwd_oct_kernel(LstmArgs a) {
     __shared__ float s_dp[P_COUNT * 32];
     __shared__ __align__(16) float s_prm[P_COUNT * 32];
@@ -351,62 +304,9 @@ __global__ void __launch_bounds__(256, 2) lstm_bwd_oct_kernel(LstmArgs a) {
             f4(dO, (valid && a.dOdirect) ? ldg4(a.dOdirect + r32) : zero);
             f4(dhd, (valid && a.dHead) ? ldg4(a.dHead + (size_t)i * a.lddh + 4 * l8) : zero);
         }
-        float tc[4], H[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            tc[k] = fast_tanh(Cn[k]);
-            H[k] = O[k] * tc[k];
-        }
-        float xh[4];
-        if (a.norm_h) {                          // dH arrives w.r.t. LN_h(H')
-            float g[4];
-            PRM(P_GH, g);
-            const float rstd = oct_ln_fwd(H, a.eps, xh);
-            oct_ln_bwd(xh, dH, g, rstd, dprm[P_GH], dprm[P_BH]);
-        }
-        if (a.norm_c) {
-            float g[4];
-            PRM(P_GC, g);
-            const float rstd = oct_ln_fwd(Cn, a.eps, xh);
-            oct_ln_bwd(xh, dC, g, rstd, dprm[P_GC], dprm[P_BCN]);
-        }
-        if (a.dHead) {                           // head_in[:, :C] = relu(LN_o(O))
-            if (a.norm_o) {
-                float g[4], b[4];
-                PRM(P_GO, g);
-                PRM(P_BON, b);
-                const float rstd = oct_ln_fwd(O, a.eps, xh);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) dhd[k] = (fmaf(xh[k], g[k], b[k]) > 0.f) ? dhd[k] : 0.f;
-                oct_ln_bwd(xh, dhd, g, rstd, dprm[P_GO], dprm[P_BON]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) dhd[k] = (O[k] > 0.f) ? dhd[k] : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) dO[k] += dhd[k];
-        }
-        float dI[4], dF[4], dT[4], dOp[4], dCp[4], wci[4], wcf[4], wco[4];
-        PRM(P_WCI, wci);
-        PRM(P_WCF, wcf);
-        PRM(P_WCO, wco);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float dOt = fmaf(dH[k], tc[k], dO[k]);
-            dOp[k] = dOt * O[k] * (1.f - O[k]);
-            const float dCn = dC[k] + dH[k] * O[k] * (1.f - tc[k] * tc[k]) + dOp[k] * wco[k];
-            dI[k] = dCn * T[k] * I[k] * (1.f - I[k]);
-            dF[k] = dCn * cp[k] * F[k] * (1.f - F[k]);
-            dT[k] = dCn * I[k] * (1.f - T[k] * T[k]);
-            dCp[k] = dCn * F[k] + dI[k] * wci[k] + dF[k] * wcf[k];
-            dprm[P_WCI][k] = fmaf(dI[k], cp[k], dprm[P_WCI][k]);
-            dprm[P_WCF][k] = fmaf(dF[k], cp[k], dprm[P_WCF][k]);
-            dprm[P_WCO][k] = fmaf(dOp[k], Cn[k], dprm[P_WCO][k]);
-            dprm[P_BI][k] += dI[k];
-            dprm[P_BF][k] += dF[k];
-            dprm[P_BC][k] += dT[k];
-            dprm[P_BO][k] += dOp[k];
-        }
+        float dI[4], dF[4], dT[4], dOp[4], dCp[4];
+        oct_gate_bwd(I, F, T, O, Cn, cp, dH, dC, dO, dhd, a.dHead != nullptr, a.norm_h, a.norm_c, a.norm_o, a.eps, PRM, dprm, dI, dF, dT,
+                     dOp, dCp);
         if (valid) {
             float* dpr = a.dP + (size_t)i * a.lddp + 4 * l8;
             *reinterpret_cast<float4*>(dpr) = make_float4(dI[0], dI[1], dI[2], dI[3]);

@@ -2,8 +2,8 @@
 // 3xTF32 (or plain TF32), operands staged through shared memory by ordinary stores, accumulator in TMEM.
 // Exists so the descriptor / layout / fence conventions of tc.cuh are validated in isolation on the GPU
 // (tests/test_parity_convs.py::test_tcgen05_gemm) before the fused cell kernels rely on them.
-#include "common.cuh"
-#include "tc.cuh"
+#include "../common.cuh"
+#include "../tc.cuh"
 
 namespace qmp {
 

@@ -5,8 +5,8 @@
 //   variant 4:    C [128, N] = A B^T with A [128, K] taken from TENSOR MEMORY (written by tcgen05.st, lane = row,
 //                 column = k) and B [N, K] K-major in shared memory.
 // Plain TF32 (no split): layout questions show up as O(1) errors, TF32 rounding as ~1e-3.
-#include "common.cuh"
-#include "tc.cuh"
+#include "../common.cuh"
+#include "../tc.cuh"
 
 namespace qmp {
 

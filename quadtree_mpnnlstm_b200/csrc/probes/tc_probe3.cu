@@ -2,8 +2,8 @@
 // 128 x N x 8 (A from tensor memory or from shared memory; all into one accumulator or rotating over four), commits,
 // and the CTA measures the clock until the commit lands.  Results (cycles per MMA) drive the tile shapes of the
 // fused kernels; the numbers are recorded in DESIGN.md.
-#include "common.cuh"
-#include "tc.cuh"
+#include "../common.cuh"
+#include "../tc.cuh"
 
 namespace qmp {
 

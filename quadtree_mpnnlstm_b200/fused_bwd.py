@@ -11,6 +11,7 @@ from .ops import gemm_tn_acc
 FC = 32
 _f32 = torch.float32
 _bwd_cache = {}
+_NO_GATES = (None, None, None, None, 0, 0, 0, 0.0, None, None, None, None, 0, None, None)     # qmp_fused_cell_bwd with dP as an input
 
 
 def bwd_pack(w, DC):
@@ -78,13 +79,23 @@ def fused_group_backward(ctx, *grads):
     DBC = cap_of(DB, False)
     c_ = lambda t: t.contiguous() if t is not None else None
     dCprev = dparams = dconcat = None
+    need_dxa = GA > 0 and ctx.needs_input_grad[0]
+    need_dxb = ctx.needs_input_grad[2]
+    cell = (_fz.CELL_BWD and _fz.TC_BWD and usave is not None and need_dxa and need_dxb
+            and _fz.is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb))
+    gate_args = None
     if mode == 1:
         dO, dH, dC, dHead = (c_(g) for g in grads)
         dP = torch.empty(N, 4 * FC, dtype=_f32, device=dev)
         dCprev = torch.empty(N, FC, dtype=_f32, device=dev) if (Cp is not None and ctx.needs_input_grad[4]) else None
         dparams = hp.acc if hp is not None else torch.zeros(13, FC, dtype=_f32, device=dev)
-        _lib.call("qmp_lstm_gates_bwd", N, FC, gates, Craw, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps), dH, dC,
-                  dO, dHead, HEADW, dP, 4 * FC, dCprev, dparams)
+        if cell and _fz.CELL_BWD_GATES:
+            # the gate epilogue's backward runs in the prologue of the decoder-cell backward kernel (no launch of its own)
+            gate_args = (gates, Craw, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps), dH, dC, dO, dHead, HEADW, dCprev,
+                         dparams)
+        else:
+            _lib.call("qmp_lstm_gates_bwd", N, FC, gates, Craw, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps), dH, dC,
+                      dO, dHead, HEADW, dP, 4 * FC, dCprev, dparams)
         if dHead is not None and ctx.concat_shape is not None and ctx.needs_input_grad[6]:
             dconcat = dHead[:, FC].reshape(ctx.concat_shape).clone()
         lddp = 4 * FC
@@ -95,17 +106,19 @@ def fused_group_backward(ctx, *grads):
             _lib.call("qmp_relu_mask_to", out_relu, g0, dP, dP.numel())
         lddp = NC * C
 
-    need_dxa = GA > 0 and ctx.needs_input_grad[0]
-    need_dxb = ctx.needs_input_grad[2]
-    cell = (_fz.CELL_BWD and _fz.TC_BWD and usave is not None and need_dxa and need_dxb
-            and _fz.is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb))
     ds = None if cell else torch.empty(max(E, 1), NC, dtype=_f32, device=dev)
-    ZsA = dUsA = None
-    if GA:
-        ZsA = torch.empty(N, GA, DAC + 4, dtype=_f32, device=dev)
-        dUsA = torch.empty(N, GA, DAC + 4, dtype=_f32, device=dev)
-    ZsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
-    dUsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
+    ZsA = dUsA = ZsB = dUsB = None
+    if cell:        # panel layout of the streaming weight-gradient kernel (csrc/cell_wgrad.cu)
+        zB = torch.empty(N, 4 * FC, dtype=_f32, device=dev)
+        duB = torch.empty(N, 4 * FC, dtype=_f32, device=dev)
+        sd = torch.empty(N, 64, dtype=_f32, device=dev)
+        sg = torch.empty(N, 32, dtype=_f32, device=dev)
+    else:
+        if GA:
+            ZsA = torch.empty(N, GA, DAC + 4, dtype=_f32, device=dev)
+            dUsA = torch.empty(N, GA, DAC + 4, dtype=_f32, device=dev)
+        ZsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
+        dUsB = torch.empty(N, GB, DBC + 4, dtype=_f32, device=dev)
     from . import fused as _f
     tcb = _f.TC_BWD
     onepass = tcb and _f.ONEPASS_BWD and not cell and (need_dxa or need_dxb)
@@ -115,7 +128,7 @@ def fused_group_backward(ctx, *grads):
     ldb = xb.shape[1]
     if cell:        # target and source side of every edge in one persistent launch (csrc/fused_cell_bwd.cu)
         _lib.call("qmp_fused_cell_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda, xb, ldb, _f.cell_bwd_image(wa, wb),
-                  usave, dP, lddp, logit, mstat, linv, ZsA, dUsA, ZsB, dUsB, dxa, dxb, float(drop_p), int(seed))
+                  usave, dP, lddp, *(gate_args or _NO_GATES), logit, mstat, linv, zB, duB, sd, sg, dxa, dxb, float(drop_p), int(seed))
     elif tcb:
         pa = _f.tc_image(wa, DAC, 1) if GA else None
         pb = _f.tc_image(wb, DBC, 1)
@@ -135,7 +148,9 @@ def fused_group_backward(ctx, *grads):
 
     gwa = (ha.acc if ha is not None else torch.zeros_like(wa)) if GA else None
     gwb = hb.acc if hb is not None else torch.zeros_like(wb)
-    if _f.TC_WGRAD:
+    if cell:        # all eight convs in one streaming launch: TMA panels -> two wide tcgen05 products per 8 nodes
+        _lib.call("qmp_cell_wgrad", N, xb, ldb, dP, lddp, zB, duB, sd, sg, gwa, gwb)
+    elif _f.TC_WGRAD:
         _lib.call("qmp_fused_wgrad", N, xa, lda, DA, GA, xb, ldb, DB, GB, int(sharedB), mode, C, dP, lddp, ZsA, dUsA, ZsB,
                   dUsB, gwa, gwb)
     elif mode == 1:

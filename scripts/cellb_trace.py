@@ -29,13 +29,13 @@ o = dict(gates=z(N, 128), Craw=z(N, 32), O=z(N, 32), H=z(N, 32), C=z(N, 32), hea
          usave=z(N, 128))
 _lib.call("qmp_fused_cell_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, FZ.cell_image(wa, wb), Cp, prm, 1, 1, 1, 1e-5,
           o["gates"], o["Craw"], o["O"], o["H"], o["C"], o["head"], 36, None, o["logit"], o["mstat"], o["linv"], o["usave"], 0.0, 1)
-b = dict(ZsA=z(N, 4, 8), dUsA=z(N, 4, 8), ZsB=z(N, 4, 36), dUsB=z(N, 4, 36), dxa=z(N, 4), dxb=z(N, 32))
+b = dict(ZsA=z(N, 128), dUsA=z(N, 128), ZsB=z(N, 64), dUsB=z(N, 32), dxa=z(N, 4), dxb=z(N, 32))      # zB, duB, sd, sg of the panel layout
 img = FZ.cell_bwd_image(wa, wb)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
 def run():
-    _lib.call("qmp_fused_cell_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, img, o["usave"], dP, 128, o["logit"],
+    _lib.call("qmp_fused_cell_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, img, o["usave"], dP, 128, None, None, None, None, 0, 0, 0, 0.0, None, None, None, None, 0, None, None, o["logit"],
               o["mstat"], o["linv"], b["ZsA"], b["dUsA"], b["ZsB"], b["dUsB"], b["dxa"], b["dxb"], 0.0, 1)
 
 

@@ -1,7 +1,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from quadtree_mpnnlstm_b200 import _lib
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import probe_lib as _lib
 torch.manual_seed(0)
 for (M, N, K) in [(128, 32, 8), (128, 32, 32), (128, 136, 32), (300, 128, 40), (1000, 256, 72), (128, 8, 8)]:
     for split in (0, 1):

@@ -1,7 +1,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from quadtree_mpnnlstm_b200 import _lib
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import probe_lib as _lib
 torch.manual_seed(0)
 for (N, K) in [(16, 8), (32, 64), (80, 64)]:
     for variant in (0, 1, 2, 3, 4):

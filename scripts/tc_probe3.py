@@ -1,7 +1,8 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from quadtree_mpnnlstm_b200 import _lib
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+import probe_lib as _lib
 out = torch.zeros(1, dtype=torch.int64, device="cuda")
 for a_tmem in (0, 1):
     for rotate in (0, 1):

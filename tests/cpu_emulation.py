@@ -643,9 +643,62 @@ def qmp_fused_pack_cell_bwd(packA, packB, out):
     qmp_fused_pack_cell(packA, packB, out)
 
 
-def qmp_fused_cell_bwd(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, usave, dP, lddp, logit, mstat, linv, ZsA, dUsA, ZsB, dUsB,
+def qmp_fused_cell_bwd(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, usave, dP, lddp, gates, Craw, Cprev, params, norm_h, norm_c,
+                       norm_o, eps, dHout, dCout, dOdirect, dHead, lddh, dCprev, dparams, logit, mstat, linv, zB, duB, sd, sg,
                        dxa, dxb, drop_p, seed):
-    """Target side by the emulated per-conv kernel; source side of every edge added from the same in-CSR edge list."""
+    """Target side by the emulated per-conv kernel; source side of every edge added from the same in-CSR edge list; the rows
+    for the weight gradients repacked into the panel layout of csrc/cell_wgrad.cu."""
+    if gates is not None:       # the fused gate backward: dP is an output
+        qmp_lstm_gates_bwd(N, _FC, gates, Craw, Cprev, params, norm_h, norm_c, norm_o, eps, dHout, dCout, dOdirect, dHead, lddh, dP,
+                           lddp, dCprev, dparams)
+    ZsA, dUsA, ZsB, dUsB = torch.zeros(N, 4, 8), torch.zeros(N, 4, 8), torch.zeros(N, 4, 36), torch.zeros(N, 4, 36)
+    _cell_bwd_old_layout(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, usave, dP, lddp, logit, mstat, linv, ZsA, dUsA, ZsB, dUsB,
+                         dxa, dxb, drop_p, seed)
+    flat(zB, N * 128).view(N, 4, 32).copy_(ZsB[:, :, :32])
+    flat(duB, N * 128).view(N, 4, 32).copy_(dUsB[:, :, :32])
+    sdv, sgv = flat(sd, N * 64).view(N, 64), flat(sg, N * 32).view(N, 32)
+    sdv.zero_()
+    sdv[:, :4] = rows(xa, N, lda, 4)
+    sdv[:, 4] = 1.0
+    sdv[:, 8:24].view(N, 4, 4)[:, :, :3] = ZsB[:, :, 32:35]
+    sdv[:, 32:].view(N, 4, 8)[:, :, :7] = ZsA[:, :, :7]
+    sgv[:, :8] = dUsB[:, :, 32:34].reshape(N, 8)
+    sgv[:, 8:24] = dUsA[:, :, :4].reshape(N, 16)
+    sgv[:, 24:] = dUsA[:, :, 4:6].reshape(N, 8)
+
+
+def qmp_cell_wgrad(N, h, ldh, dP, lddp, zB, duB, sd, sg, gwa, gwb):
+    """Reductions over the nodes from the panel layout (csrc/cell_wgrad.cu) into the two padded packs."""
+    g = rows(dP, N, lddp, 128).view(N, 4, 32)
+    H = rows(h, N, ldh, 32)
+    z, du = flat(zB, N * 128).view(N, 4, 32), flat(duB, N * 128).view(N, 4, 32)
+    sdv, sgv = flat(sd, N * 64).view(N, 64), flat(sg, N * 32).view(N, 32)
+    x, one = sdv[:, :4], sdv[:, 4]
+    ga, gb = flat(gwa, 4 * _total(4)).view(4, -1), flat(gwb, 4 * _total(32)).view(4, -1)
+    for c in range(4):
+        gc = g[:, c]
+        # H conv c
+        Zh = torch.cat([z[:, c], sdv[:, 8 + 4 * c:12 + 4 * c]], 1)                  # [N, 36]
+        dUh = torch.cat([du[:, c], sgv[:, 2 * c:2 * c + 2]], 1)                     # [N, 34]
+        o1, o2, o3, o4 = 34 * 32, 34 * 32 + 36, 34 * 32 + 36 + 32 * 36, 34 * 32 + 36 + 32 * 36 + 32 * 32
+        gb[c, :o1] += (dUh.T @ H).reshape(-1)
+        gb[c, o1:o1 + 34] += (dUh * one[:, None]).sum(0)
+        gb[c, o2:o3] += (gc.T @ Zh).reshape(-1)
+        gb[c, o3:o4] += (gc.T @ H).reshape(-1)
+        gb[c, o4:] += (gc * one[:, None]).sum(0)
+        # X conv c
+        Zx = sdv[:, 32 + 8 * c:40 + 8 * c]
+        dUx = torch.cat([sgv[:, 8 + 4 * c:12 + 4 * c], sgv[:, 24 + 2 * c:26 + 2 * c]], 1)     # [N, 6]
+        o1, o2, o3, o4 = 24, 32, 32 + 256, 32 + 256 + 128
+        ga[c, :o1] += (dUx.T @ x).reshape(-1)
+        ga[c, o1:o1 + 6] += (dUx * one[:, None]).sum(0)
+        ga[c, o2:o3] += (gc.T @ Zx).reshape(-1)
+        ga[c, o3:o4] += (gc.T @ x).reshape(-1)
+        ga[c, o4:] += (gc * one[:, None]).sum(0)
+
+
+def _cell_bwd_old_layout(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, usave, dP, lddp, logit, mstat, linv, ZsA, dUsA, ZsB, dUsB,
+                         dxa, dxb, drop_p, seed):
     na, nb = 4 * _total(4) * 4, 4 * _total(32) * 4
     pa = _bwd_pack_from_image(image[:na].view(4, -1), 4, 4)
     pb = _bwd_pack_from_image(image[na:na + nb].view(4, -1), 4, 32)

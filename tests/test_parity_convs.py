@@ -96,7 +96,7 @@ def test_gcn_conv(be, d_in, d_out, self_loops):
                                                          ("ChebConv", 1, 4, 16), ("ChebConv", 2, 4, 16),
                                                          ("GCNConv", 2, 4, 16), ("TransformerConv", 2, 5, 8),
                                                          ("MHTransformerConv", 2, 5, 8)])
-@pytest.mark.parametrize("path", ["tc", "tc_pw", "tc_1t", "tc_2pass", "ffma", "modular"])
+@pytest.mark.parametrize("path", ["tc", "tc_pw", "tc_1t", "tc_2pass", "tc_sepgates", "ffma", "modular"])
 def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     import quadtree_mpnnlstm_b200.model as M
     import quadtree_mpnnlstm_b200.fused as FZ
@@ -117,6 +117,8 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
             pytest.skip("covered at kernel level on the device")
         monkeypatch.setattr(FZ, "ONEPASS_BWD", False)
         monkeypatch.setattr(FZ, "CELL_BWD", False)
+    if path == "tc_sepgates":                 # gate backward as its own launch instead of the cell backward kernel's prologue
+        monkeypatch.setattr(FZ, "CELL_BWD_GATES", False)
     monkeypatch.setattr(FZ, "ENABLED", fused)
     monkeypatch.setattr(FZ, "TC_FWD", path.startswith("tc"))
     monkeypatch.setattr(FZ, "TC_BWD", path.startswith("tc"))
@@ -239,7 +241,7 @@ def _gemm_checks(be, ops):
 @pytest.mark.gpu
 def test_tcgen05_gemm_probe():
     """tc.cuh conventions in isolation: 3xTF32 is fp32-accurate, plain TF32 is not."""
-    from quadtree_mpnnlstm_b200 import _lib
+    import probe_lib
     torch.manual_seed(0)
     for (M, N, K) in [(128, 32, 8), (128, 136, 32), (300, 128, 40), (1000, 48, 72)]:
         A, B = torch.randn(M, K, device="cuda"), torch.randn(N, K, device="cuda")
@@ -247,7 +249,7 @@ def test_tcgen05_gemm_probe():
         errs = []
         for split in (1, 0):
             C = torch.full((M, N), float("nan"), device="cuda")
-            _lib.call("qmp_tc_gemm_probe", A, B, C, M, N, K, split)
+            probe_lib.call("qmp_tc_gemm_probe", A, B, C, M, N, K, split)
             errs.append(rel_err(C, ref))
         assert errs[0] < 5e-6, (M, N, K, errs)
         assert 5e-5 < errs[1] < 5e-3, (M, N, K, errs)
@@ -432,8 +434,37 @@ def test_decoder_cell_backward_kernel_matches_per_conv_kernels(N, drop_p):
               a["dUsB"], a["dxa"], a["dxb"], drop_p, seed)
     _lib.call("qmp_fused_bwd_source_tc", N, csr.out_ptr, csr.out_dst, csr.out_kin, xa, 4, 4, 4, FZ.tc_image(wa, 4, 2), xb, 32, 32, 4, 1,
               FZ.tc_image(wb, 32, 2), 1, 32, dP, 128, o["logit"], o["mstat"], o["linv"], ds, a["dxa"], a["dxb"], drop_p, seed)
+    zB, duB, sd, sg = z(N, 128), z(N, 128), z(N, 64), z(N, 32)
     _lib.call("qmp_fused_cell_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, xb, 32, FZ.cell_bwd_image(wa, wb), o["usave"],
-              dP, 128, o["logit"], o["mstat"], o["linv"], b["ZsA"], b["dUsA"], b["ZsB"], b["dUsB"], b["dxa"], b["dxb"], drop_p, seed)
+              dP, 128, None, None, None, None, 0, 0, 0, 0.0, None, None, None, None, 0, None, None, o["logit"], o["mstat"], o["linv"],
+              zB, duB, sd, sg, b["dxa"], b["dxb"], drop_p, seed)
+    torch.cuda.synchronize()
+    for name, t in (("zB", zB), ("duB", duB), ("sd", sd), ("sg", sg)):
+        assert not torch.isnan(t).any(), f"{name}: unwritten / NaN entries"
+    # the panel layout of csrc/cell_wgrad.cu back to the per-conv rows
+    assert torch.equal(sd[:, :4], xa) and bool((sd[:, 4] == 1).all()) and not sd[:, 5:8].any() and not sd[:, 24:32].any()
+    b["ZsB"] = torch.cat([zB.view(N, 4, 32), sd[:, 8:24].view(N, 4, 4)], 2)
+    b["dUsB"] = torch.cat([duB.view(N, 4, 32), sg[:, :8].view(N, 4, 2), torch.zeros(N, 4, 2, device=dev)], 2)
+    b["ZsA"] = sd[:, 32:].reshape(N, 4, 8)
+    b["dUsA"] = torch.cat([sg[:, 8:24].view(N, 4, 4), sg[:, 24:].view(N, 4, 2), torch.zeros(N, 4, 2, device=dev)], 2)
+    # ... and the streaming weight-gradient kernel on those rows against the per-problem kernel on the per-conv rows
+    gwa, gwb = torch.zeros_like(wa), torch.zeros_like(wb)
+    ra, rb = torch.zeros_like(wa), torch.zeros_like(wb)
+    _lib.call("qmp_cell_wgrad", N, xb, 32, dP, 128, zB, duB, sd, sg, gwa, gwb)
+    _lib.call("qmp_fused_wgrad", N, xa, 4, 4, 4, xb, 32, 32, 4, 1, 1, 32, dP, 128, b["ZsA"].contiguous(), b["dUsA"].contiguous(),
+              b["ZsB"].contiguous(), b["dUsB"].contiguous(), ra, rb)
+    torch.cuda.synchronize()
+    g64 = dP.double().view(N, 4, 32)
+    for c in range(4):        # fp64 check of two blocks, so that the comparison is not kernel-against-kernel only
+        want = g64[:, c].T @ xb.double()
+        got = gwb[c, 34 * 32 + 36 + 32 * 36:34 * 32 + 36 + 32 * 36 + 1024].view(32, 32).double()
+        assert float((want - got).abs().max()) <= 2e-5 * max(float(want.abs().max()), 1.0), f"gW3_h[{c}]"
+        want = b["dUsB"][:, c, :34].double().T @ xb.double()
+        got = gwb[c, :34 * 32].view(34, 32).double()
+        assert float((want - got).abs().max()) <= 2e-5 * max(float(want.abs().max()), 1.0), f"gW1_h[{c}]"
+    for name, got, want in (("gwa", gwa, ra), ("gwb", gwb, rb)):
+        err = float((got - want).abs().max()) / max(float(want.abs().max()), 1e-6)
+        assert err < 2e-5, f"cell_wgrad {name}: {err}"
     # ... and the one-pass mode of the per-conv target kernel (source side by vector reductions, no out-CSR launch)
     c = outs()
     _lib.call("qmp_fused_bwd_onepass_tc", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, 4, 4, 4, FZ.tc_image(wa, 4, 1), xb, 32, 32, 4,
