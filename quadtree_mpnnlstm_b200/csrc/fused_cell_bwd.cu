@@ -231,6 +231,31 @@ __device__ __forceinline__ void cellb_h_load(CellbHPre& h, const CellBwdArgs& a,
     }
 }
 
+// everything tile [n0, n0 + cnt) streams from global memory, requested into L2 by one thread (rows of h are gathered through
+// the CSR and stay L2-resident anyway: 6 MB)
+__device__ __forceinline__ void cellb_prefetch_tile(const CellBwdArgs& a, int n0, int cnt) {
+    const size_t n = (size_t)n0;
+    if (a.gates) {
+        tc::l2_prefetch(a.gates + n * 128, (long long)cnt * 512);
+        tc::l2_prefetch(a.Craw + n * 32, (long long)cnt * 128);
+        if (a.Cprev) tc::l2_prefetch(a.Cprev + n * 32, (long long)cnt * 128);
+        if (a.dHout) tc::l2_prefetch(a.dHout + n * 32, (long long)cnt * 128);
+        if (a.dCout) tc::l2_prefetch(a.dCout + n * 32, (long long)cnt * 128);
+        if (a.dOdirect) tc::l2_prefetch(a.dOdirect + n * 32, (long long)cnt * 128);
+        if (a.dHead) tc::l2_prefetch(a.dHead + n * a.lddh, (long long)cnt * a.lddh * 4);
+    } else {
+        tc::l2_prefetch(a.dP + n * a.lddp, (long long)cnt * a.lddp * 4);
+    }
+    tc::l2_prefetch(a.usave + n * 128, (long long)cnt * 512);
+    tc::l2_prefetch(a.mstat + n * 8, (long long)cnt * 32);
+    tc::l2_prefetch(a.linv + n * 8, (long long)cnt * 32);
+    tc::l2_prefetch(a.xa + n * a.lda, (long long)cnt * a.lda * 4);
+    const int k0 = __ldg(a.ptr + n0), k1 = __ldg(a.ptr + n0 + cnt);
+    tc::l2_prefetch(a.logit + (size_t)k0 * 8, (long long)(k1 - k0) * 32);
+    tc::l2_prefetch(a.nbr + k0, (long long)(k1 - k0) * 4);
+    if (a.ea) tc::l2_prefetch(a.ea + (size_t)k0 * 2, (long long)(k1 - k0) * 8);
+}
+
 __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const __grid_constant__ CellBwdArgs a,
                                                                          const uint8_t* __restrict__ img, const int Q, const int R,
                                                                          const int T0) {
@@ -262,6 +287,7 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
     const int beg = (int)blockIdx.x * Q;
     int end = beg + Q;
     if (end > a.N) end = a.N;
+    if (t == 64 && beg < end) cellb_prefetch_tile(a, beg, end - beg < T0 ? end - beg : T0);      // first tile, under the image load
     tc::mbar_wait(&bars[1], 0);                                // weights in shared memory
 
     {
@@ -275,6 +301,7 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
             const int tile0 = beg + r * T0;
             if (tile0 >= end) break;
             const int tcount = (end - tile0 < T0) ? end - tile0 : T0;
+            if (t == 64 && tile0 + T0 < end) cellb_prefetch_tile(a, tile0 + T0, end - tile0 - T0 < T0 ? end - tile0 - T0 : T0);
 
             CELL_MARK(1);
             if (a.gates) {
@@ -324,15 +351,22 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
                     st4(xr + 3 * XPLANE, dOp[0], dOp[1], dOp[2], dOp[3]);
                 }
                 if (a.dparams) {
+                    // sum over the warp's 4 octets with a value-halving butterfly (39 shuffles for the 52 values instead of 104):
+                    // afterwards lane (b4, b3, l8) holds row i, channel 4 l8 + 2 b3 + b4 of every parameter row i -- 32 distinct
+                    // consecutive addresses per warp instruction (float atomics on shared memory are compare-and-swap loops)
+                    const bool b4 = lane & 16, b3 = lane & 8;
+                    float r1[2 * P_COUNT];
 #pragma unroll
-                    for (int p = 0; p < P_COUNT; ++p)
+                    for (int i = 0; i < 2 * P_COUNT; ++i) {
+                        const float e = dprm[i >> 1][2 * (i & 1)], o = dprm[i >> 1][2 * (i & 1) + 1];
+                        r1[i] = (b4 ? o : e) + __shfl_xor_sync(0xffffffffu, b4 ? e : o, 16);
+                    }
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            float v = dprm[p][k];
-                            v += __shfl_xor_sync(0xffffffffu, v, 8);
-                            v += __shfl_xor_sync(0xffffffffu, v, 16);
-                            if (o8 == 0 && v != 0.f) atomicAdd(&s_dp[p * 32 + 4 * l8 + k], v);
-                        }
+                    for (int i = 0; i < P_COUNT; ++i) {
+                        const float e = r1[2 * i], o = r1[2 * i + 1];
+                        const float v = (b3 ? o : e) + __shfl_xor_sync(0xffffffffu, b3 ? e : o, 8);
+                        atomicAdd(&s_dp[i * 32 + 4 * l8 + (b3 ? 2 : 0) + (b4 ? 1 : 0)], v);
+                    }
                 }
                 cellb_sync();
                 const bool valid = nrow < tcount;

@@ -87,6 +87,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  : "memory");
 }
 
+// L2 prefetch of a contiguous global range (TMA engine, no registers or shared memory involved): the streaming inputs of the
+// NEXT tile are requested while the current tile computes, so that its first loads find them in L2
+__device__ __forceinline__ void l2_prefetch(const void* p, long long bytes) {
+    if (p == nullptr || bytes <= 0) return;
+    const unsigned long long a = reinterpret_cast<unsigned long long>(p), a0 = a & ~15ull;
+    const unsigned int n = (unsigned int)((bytes + (long long)(a - a0) + 15) & ~15ll);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(n) : "memory");
+}
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

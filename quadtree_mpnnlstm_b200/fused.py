@@ -5,6 +5,8 @@ else runs the modular kernels (ops.py), which compute the same thing.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 
@@ -20,7 +22,7 @@ TC_FWD = True       # forward on tcgen05 (csrc/fused_fwd_tc.inl); False: the fp3
 SCALAR_HEAD = True  # decoder head's fc_out2 (hidden -> 1 channel): scalar query / key / value kernels (csrc/tconv1.cu)
 ONEPASS_BWD = True  # tcgen05 backward of the other groups: source side of every edge by vector reductions inside the target kernel (one launch)
 CELL_BWD = True     # ... and its backward: target + source side of every edge in one persistent launch (csrc/fused_cell_bwd.cu)
-CELL_BWD_GATES = True     # gate backward inside the decoder-cell backward kernel (False: qmp_lstm_gates_bwd launch first)
+CELL_BWD_GATES = os.environ.get("QMP_CELL_BWD_GATES", "1") != "0"     # gate backward inside the decoder-cell backward kernel (False: qmp_lstm_gates_bwd launch first)
 CELL_FWD = True     # decoder cell (4 X convs + 4 H convs, gate mode): the persistent gates-batched kernel (csrc/fused_cell_fwd.cu)
 _f32 = torch.float32
 
