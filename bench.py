@@ -251,7 +251,7 @@ def _classify(name, args):
         return ("decoder_cell_bwd" if (GA == 4 and DA == 4) else "encoder_bwd"), key
     if name in ("qmp_tconv1_fwd", "qmp_head_finish_fwd"):
         return "decoder_head_fwd", name
-    if name in ("qmp_tconv1_bwd", "qmp_head_finish_bwd", "qmp_relu_mask_to", "qmp_relu_mask"):
+    if name in ("qmp_tconv1_bwd", "qmp_head_finish_bwd", "qmp_relu_mask_to", "qmp_relu_mask", "qmp_panel_wgrad"):
         return "decoder_head_bwd", name
     return "other", name
 

@@ -150,6 +150,9 @@ def fused_group_backward(ctx, *grads):
     gwb = hb.acc if hb is not None else torch.zeros_like(wb)
     if cell:        # all eight convs in one streaming launch: TMA panels -> two wide tcgen05 products per 8 nodes
         _lib.call("qmp_cell_wgrad", N, xb, ldb, dP, lddp, zB, duB, sd, sg, gwa, gwb)
+    elif _f.TC_WGRAD and _f.PANEL_WGRAD and GA == 0 and GB == 1 and DBC == 36 and C == FC and mode == 0:
+        # the head conv fc_out1: one streaming launch (csrc/panel_wgrad.cu)
+        _lib.call("qmp_panel_wgrad", N, xb, ldb, DB, DBC, dP, lddp, ZsB, dUsB, gwb)
     elif _f.TC_WGRAD:
         _lib.call("qmp_fused_wgrad", N, xa, lda, DA, GA, xb, ldb, DB, GB, int(sharedB), mode, C, dP, lddp, ZsA, dUsA, ZsB,
                   dUsB, gwa, gwb)

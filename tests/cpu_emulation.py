@@ -697,6 +697,11 @@ def qmp_cell_wgrad(N, h, ldh, dP, lddp, zB, duB, sd, sg, gwa, gwb):
         ga[c, o4:] += (gc * one[:, None]).sum(0)
 
 
+def qmp_panel_wgrad(N, x, ldx, D, DC, g, ldg, Zs, dUs, gw):
+    assert DC == 36
+    qmp_fused_wgrad(N, None, 0, 0, 0, x, ldx, D, 1, 1, 0, _FC, g, ldg, None, None, Zs, dUs, None, gw)
+
+
 def _cell_bwd_old_layout(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, usave, dP, lddp, logit, mstat, linv, ZsA, dUsA, ZsB, dUsB,
                          dxa, dxb, drop_p, seed):
     na, nb = 4 * _total(4) * 4, 4 * _total(32) * 4

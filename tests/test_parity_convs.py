@@ -255,6 +255,36 @@ def test_tcgen05_gemm_probe():
         assert 5e-5 < errs[1] < 5e-3, (M, N, K, errs)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1, 15, 2048, 47200])
+@pytest.mark.parametrize("D", [36, 33])
+def test_panel_wgrad_kernel(N, D):
+    """qmp_panel_wgrad (head conv fc_out1: TMA panels as MN-major tcgen05 operands, 3xTF32) against float64 outer-product sums
+    and against the per-problem kernel qmp_fused_wgrad; rows wider than the valid columns (ldx = 36, D = 33)."""
+    from quadtree_mpnnlstm_b200 import _lib
+    torch.manual_seed(N + D)
+    dev = torch.device("cuda")
+    DC = 36
+    x = torch.randn(N, 36, device=dev)
+    x[:, D:] = 0
+    g = torch.randn(N, 32, device=dev)
+    Zs, dUs = torch.randn(N, 40, device=dev), torch.randn(N, 40, device=dev)
+    Zs[:, 39] = 0
+    dUs[:, 38:] = 0
+    tot = (DC + 2) * DC + DC + 4 + 32 * (DC + 4) + 32 * DC + 32
+    gw, ref = torch.zeros(1, tot, device=dev), torch.zeros(1, tot, device=dev)
+    _lib.call("qmp_panel_wgrad", N, x, 36, D, DC, g, 32, Zs, dUs, gw)
+    _lib.call("qmp_fused_wgrad", N, None, 0, 0, 0, x, 36, D, 1, 1, 0, 32, g, 32, None, None, Zs, dUs, None, ref)
+    torch.cuda.synchronize()
+    x64, g64, z64, d64 = x.double(), g.double(), Zs.double(), dUs.double()
+    want = torch.cat([(d64[:, :38].T @ x64).reshape(-1), d64[:, :38].sum(0), torch.zeros(2, device=dev, dtype=torch.float64),
+                      (g64.T @ z64).reshape(-1), (g64.T @ x64).reshape(-1), g64.sum(0)])
+    err = float((gw[0].double() - want).abs().max()) / max(float(want.abs().max()), 1.0)
+    assert err < 2e-5, f"vs float64: {err}"
+    err = float((gw - ref).abs().max()) / max(float(ref.abs().max()), 1.0)
+    assert err < 2e-5, f"vs qmp_fused_wgrad: {err}"
+
+
 @pytest.mark.parametrize("N,DA,GA,DB,GB,shared,mode,C", [(1000, 4, 4, 32, 4, 1, 1, 32), (4133, 8, 4, 32, 4, 1, 0, 32),
                                                         (777, 0, 0, 32, 8, 0, 1, 32), (2048, 0, 0, 36, 1, 1, 0, 32),
                                                         (300, 0, 0, 32, 1, 1, 0, 1), (50, 6, 4, 32, 4, 1, 1, 32)])
