@@ -243,7 +243,7 @@ def _classify(name, args):
         if GA == 4 and DA == 4:
             return ("decoder_cell_fwd" if fwd else "decoder_cell_bwd"), key
         return ("encoder_fwd" if fwd else "encoder_bwd"), key
-    if name == "qmp_fused_wgrad":
+    if name in ("qmp_fused_wgrad", "qmp_fused_wgrad_tma"):
         DA, GA, DB, GB, mode = args[3], args[4], args[7], args[8], args[10]
         key = f"{name}[DA={DA} GA={GA} DB={DB} GB={GB} mode={mode}]"
         if DB == 36:

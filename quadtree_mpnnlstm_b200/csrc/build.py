@@ -65,6 +65,7 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_fused_cell_image_bytes": "(size of that image)",
     "qmp_fused_cell_bwd": "autograd of qmp_fused_cell_fwd w.r.t. X and H (target and source side of every edge in one persistent launch) + rows for qmp_cell_wgrad",
     "qmp_cell_wgrad": "autograd weight gradients of the decoder cell's eight convs (one streaming launch: TMA panels as MN-major tcgen05 operands, 3xTF32)",
+    "qmp_fused_wgrad_tma": "autograd weight gradients of a fused layer group (same contract as qmp_fused_wgrad): streaming TMA panels as MN-major tcgen05 operands, one product per conv and 8 nodes",
     "qmp_panel_wgrad": "autograd weight gradients of one wide-input TransformerConv (the decoder head's fc_out1, model/seq2seq.py:117-121): streaming TMA panels -> one tcgen05 product per 8 nodes",
     "qmp_fused_pack_cell_bwd": "(weight image of qmp_fused_cell_bwd)",
     "qmp_fused_cell_bwd_image_bytes": "(size of that image)",

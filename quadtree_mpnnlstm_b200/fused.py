@@ -23,7 +23,7 @@ SCALAR_HEAD = True  # decoder head's fc_out2 (hidden -> 1 channel): scalar query
 ONEPASS_BWD = True  # tcgen05 backward of the other groups: source side of every edge by vector reductions inside the target kernel (one launch)
 CELL_BWD = True     # ... and its backward: target + source side of every edge in one persistent launch (csrc/fused_cell_bwd.cu)
 CELL_BWD_GATES = os.environ.get("QMP_CELL_BWD_GATES", "1") != "0"     # gate backward inside the decoder-cell backward kernel (False: qmp_lstm_gates_bwd launch first)
-PANEL_WGRAD = os.environ.get("QMP_PANEL_WGRAD", "1") != "0"   # head conv weight gradients: the streaming TMA -> tcgen05 kernel (csrc/panel_wgrad.cu)
+PANEL_WGRAD = os.environ.get("QMP_PANEL_WGRAD", "1") != "0"   # weight gradients of the per-conv groups: the streaming TMA -> tcgen05 kernel (csrc/panel_wgrad.cu)
 CELL_FWD = True     # decoder cell (4 X convs + 4 H convs, gate mode): the persistent gates-batched kernel (csrc/fused_cell_fwd.cu)
 _f32 = torch.float32
 

@@ -150,11 +150,10 @@ def fused_group_backward(ctx, *grads):
     gwb = hb.acc if hb is not None else torch.zeros_like(wb)
     if cell:        # all eight convs in one streaming launch: TMA panels -> two wide tcgen05 products per 8 nodes
         _lib.call("qmp_cell_wgrad", N, xb, ldb, dP, lddp, zB, duB, sd, sg, gwa, gwb)
-    elif _f.TC_WGRAD and _f.PANEL_WGRAD and GA == 0 and GB == 1 and DBC == 36 and C == FC and mode == 0:
-        # the head conv fc_out1: one streaming launch (csrc/panel_wgrad.cu)
-        _lib.call("qmp_panel_wgrad", N, xb, ldb, DB, DBC, dP, lddp, ZsB, dUsB, gwb)
     elif _f.TC_WGRAD:
-        _lib.call("qmp_fused_wgrad", N, xa, lda, DA, GA, xb, ldb, DB, GB, int(sharedB), mode, C, dP, lddp, ZsA, dUsA, ZsB,
+        # streaming TMA -> tcgen05 launch (csrc/panel_wgrad.cu) wherever it applies; the per-problem kernel is the cross-check
+        tma = _f.PANEL_WGRAD and (mode == 1 or C == FC or NC == 1) and lda % 4 == 0 and ldb % 4 == 0 and lddp % 4 == 0
+        _lib.call("qmp_fused_wgrad_tma" if tma else "qmp_fused_wgrad", N, xa, lda, DA, GA, xb, ldb, DB, GB, int(sharedB), mode, C, dP, lddp, ZsA, dUsA, ZsB,
                   dUsB, gwa, gwb)
     elif mode == 1:
         if GA:

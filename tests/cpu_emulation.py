@@ -697,6 +697,10 @@ def qmp_cell_wgrad(N, h, ldh, dP, lddp, zB, duB, sd, sg, gwa, gwb):
         ga[c, o4:] += (gc * one[:, None]).sum(0)
 
 
+def qmp_fused_wgrad_tma(*args):
+    qmp_fused_wgrad(*args)
+
+
 def qmp_panel_wgrad(N, x, ldx, D, DC, g, ldg, Zs, dUs, gw):
     assert DC == 36
     qmp_fused_wgrad(N, None, 0, 0, 0, x, ldx, D, 1, 1, 0, _FC, g, ldg, None, None, Zs, dUs, None, gw)

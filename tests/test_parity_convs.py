@@ -288,9 +288,13 @@ def test_panel_wgrad_kernel(N, D):
 @pytest.mark.parametrize("N,DA,GA,DB,GB,shared,mode,C", [(1000, 4, 4, 32, 4, 1, 1, 32), (4133, 8, 4, 32, 4, 1, 0, 32),
                                                         (777, 0, 0, 32, 8, 0, 1, 32), (2048, 0, 0, 36, 1, 1, 0, 32),
                                                         (300, 0, 0, 32, 1, 1, 0, 1), (50, 6, 4, 32, 4, 1, 1, 32)])
-def test_fused_wgrad_kernel(be, N, DA, GA, DB, GB, shared, mode, C):
-    """qmp_fused_wgrad (tcgen05, MN-major 3xTF32 reduction over the nodes) against float64 outer-product sums."""
+@pytest.mark.parametrize("entry", ["qmp_fused_wgrad", "qmp_fused_wgrad_tma"])
+def test_fused_wgrad_kernel(be, N, DA, GA, DB, GB, shared, mode, C, entry):
+    """qmp_fused_wgrad (per-problem kernel: operands through registers / tensor memory) and qmp_fused_wgrad_tma (streaming
+    kernel: TMA panels as MN-major operands) -- tcgen05 3xTF32 reductions over the nodes -- against float64 outer-product sums."""
     from quadtree_mpnnlstm_b200 import _lib
+    if entry == "qmp_fused_wgrad_tma" and (DA % 4 or (mode == 0 and ((GA + GB) * C) % 4)):
+        pytest.skip("the tensor maps need 16-byte row pitches")
     torch.manual_seed(N)
     dev = be.device
     dac = 0 if GA == 0 else (4 if DA <= 4 else 8)
@@ -310,7 +314,7 @@ def test_fused_wgrad_kernel(be, N, DA, GA, DB, GB, shared, mode, C):
     ZsB, dUsB = rows(GB, dbc, dbc + 3), rows(GB, dbc, dbc + 2)
     gwa = torch.zeros(GA, tot(dac), device=dev) if GA else None
     gwb = torch.zeros(GB, tot(dbc), device=dev)
-    _lib.call("qmp_fused_wgrad", N, xa, DA, DA, GA, xb, xb.shape[1], DB, GB, shared, mode, C, dP, lddp, ZsA, dUsA, ZsB, dUsB,
+    _lib.call(entry, N, xa, DA, DA, GA, xb, xb.shape[1], DB, GB, shared, mode, C, dP, lddp, ZsA, dUsA, ZsB, dUsB,
               gwa, gwb)
     for c in range(NC):
         segA = c < GA
