@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
     int end = beg + Q;
     if (end > a.N) end = a.N;
     if (t == 64 && beg < end) cellb_prefetch_tile(a, beg, end - beg < T0 ? end - beg : T0);      // first tile, under the image load
-    tc::mbar_wait(&bars[1], 0);                                // weights in shared memory
+    // the weight image (139 KB per CTA, ~4 us from L2) is awaited where it is first used -- by the thread that issues G1 and by
+    // every thread before the X convs -- so that the first tile's gate backward runs under the copy
 
     {
         const int q = warp & 3, cg = warp >> 2;
@@ -405,6 +406,7 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
             CELL_MARK(2);
             cellb_sync();
             if (t == 0) {                                      // G1: dz of the four gates, skip-path part of dx
+                tc::mbar_wait(&bars[1], 0);                    // weights in shared memory (returns at once after the first tile)
                 tc::fence_after_sync();
 #pragma unroll 1
                 for (int g = 0; g < 4; ++g) {
@@ -605,6 +607,7 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
             }
             __syncwarp();
             // ---- while G2 runs: X conv cg of node nrow (reads dz_x in columns 36..43 of its own exchange row, leaves its dX term there)
+            tc::mbar_wait(&bars[1], 0);
             cellb_xconv(a, smem, exch, tile0 + nrow, nrow < tcount, nrow, cg, xp);
             CELL_MARK(6);
             tc::mbar_wait(&bars[0], par);
