@@ -249,9 +249,9 @@ def _classify(name, args):
         if DB == 36:
             return "decoder_head_bwd", key
         return ("decoder_cell_bwd" if (GA == 4 and DA == 4) else "encoder_bwd"), key
-    if name in ("qmp_tconv1_fwd", "qmp_head_finish_fwd"):
+    if name in ("qmp_tconv1_fwd", "qmp_head_finish_fwd", "qmp_head_tail_fwd"):
         return "decoder_head_fwd", name
-    if name in ("qmp_tconv1_bwd", "qmp_head_finish_bwd", "qmp_relu_mask_to", "qmp_relu_mask", "qmp_panel_wgrad"):
+    if name in ("qmp_tconv1_bwd", "qmp_head_finish_bwd", "qmp_relu_mask_to", "qmp_relu_mask", "qmp_panel_wgrad", "qmp_head_tail_bwd"):
         return "decoder_head_bwd", name
     return "other", name
 

@@ -45,11 +45,29 @@ __global__ void __launch_bounds__(256) tconv1_node_fwd_kernel(int N, const float
     }
 }
 
+// decoder head tail (model/seq2seq.py:167-178, 427-428) on the conv's result y_i: out = tanh(drop(y)) + x0 [-> sigmoid];
+// x_next = [out, x[:, 1:]] -- the arithmetic of head_finish_fwd_kernel (lstm.cu), here as the epilogue of the edge kernel
+struct T1Finish {
+    const float* x; int F, binary; float drop_p; unsigned long long seed;      // step input [N, F], output dropout
+    float* out; float* x_next;                                                 // [N], [N, F] (optional)
+    const float* y; const float* d_out; const float* d_xnext; float* dx;       // backward: saved y / out, incoming gradients, d x [N, F]
+};
+__device__ __forceinline__ float t1_finish_keep(unsigned long long seed, int i, float drop_p) {
+    if (drop_p <= 0.f) return 1.f;
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return ((float)(z >> 40) * (1.0f / 16777216.0f) >= drop_p) ? 1.f / (1.f - drop_p) : 0.f;
+}
+
 // out_i = sum_j drop(alpha_ij) (v_j + e_ij) + r_i over the in-edges, online softmax; thread = node
+template <bool FINISH>
 __global__ void __launch_bounds__(256) tconv1_edge_fwd_kernel(int N, const int* __restrict__ ptr, const int* __restrict__ nbr,
                                                               const float* __restrict__ ea, const float4* __restrict__ s4,
                                                               const float* __restrict__ P, float* __restrict__ out, float drop_p,
-                                                              unsigned long long seed, const unsigned long long* __restrict__ salt) {
+                                                              unsigned long long seed, const unsigned long long* __restrict__ salt,
+                                                              const T1Finish fin) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     if (drop_p > 0.f) seed = salted_seed(seed, salt);
@@ -71,16 +89,31 @@ __global__ void __launch_bounds__(256) tconv1_edge_fwd_kernel(int N, const int* 
         acc = fmaf(acc, sc, pe * fdropout_scale(seed, kk, drop_p) * (sj.z + e));
         m = mn;
     }
-    out[i] = (l > 0.f ? acc / l : 0.f) + si.w;
+    const float y = (l > 0.f ? acc / l : 0.f) + si.w;
+    out[i] = y;
+    if constexpr (FINISH) {
+        const float keep = t1_finish_keep(fin.drop_p > 0.f ? salted_seed(fin.seed, salt) : 0ull, i, fin.drop_p);
+        const float* xr = fin.x + (size_t)i * fin.F;
+        float o = tanhf(y * keep) + xr[0];
+        if (fin.binary) o = 1.f / (1.f + expf(-o));
+        fin.out[i] = o;
+        if (fin.x_next) {
+            float* xn = fin.x_next + (size_t)i * fin.F;
+            xn[0] = o;
+            for (int c = 1; c < fin.F; ++c) xn[c] = xr[c];
+        }
+    }
 }
 
 // Backward over the in-edges of node i (g_i = d out_i): softmax recomputed; dq_i, dr_i stored; dk_j, dv_j reduced onto the
 // sources; d we accumulated per block.  ds4 must be zero on entry.
+template <bool FINISH>
 __global__ void __launch_bounds__(256) tconv1_edge_bwd_kernel(int N, const int* __restrict__ ptr, const int* __restrict__ nbr,
                                                               const float* __restrict__ ea, const float4* __restrict__ s4,
                                                               const float* __restrict__ P, const float* __restrict__ g,
                                                               float* __restrict__ ds4, float* __restrict__ gP, float drop_p,
-                                                              unsigned long long seed, const unsigned long long* __restrict__ salt) {
+                                                              unsigned long long seed, const unsigned long long* __restrict__ salt,
+                                                              const T1Finish fin) {
     if (drop_p > 0.f) seed = salted_seed(seed, salt);
     __shared__ float s_we[2];
     if (threadIdx.x < 2) s_we[threadIdx.x] = 0.f;
@@ -90,7 +123,19 @@ __global__ void __launch_bounds__(256) tconv1_edge_bwd_kernel(int N, const int* 
     if (i < N) {
         const float we0 = __ldg(P + 132), we1 = __ldg(P + 133);
         const float4 si = __ldg(s4 + i);
-        const float gi = __ldg(g + i);
+        float gi;
+        if constexpr (FINISH) {                                // backward of the head tail: d y_i and the row d x_i
+            const float keep = t1_finish_keep(fin.drop_p > 0.f ? salted_seed(fin.seed, salt) : 0ull, i, fin.drop_p);
+            float gg = (fin.d_out ? fin.d_out[i] : 0.f) + (fin.d_xnext ? fin.d_xnext[(size_t)i * fin.F] : 0.f);
+            if (fin.binary) gg *= fin.out[i] * (1.f - fin.out[i]);
+            const float th = tanhf(fin.y[i] * keep);
+            gi = gg * (1.f - th * th) * keep;
+            float* dxr = fin.dx + (size_t)i * fin.F;
+            dxr[0] = gg;
+            for (int f = 1; f < fin.F; ++f) dxr[f] = fin.d_xnext ? fin.d_xnext[(size_t)i * fin.F + f] : 0.f;
+        } else {
+            gi = __ldg(g + i);
+        }
         const int k0 = __ldg(ptr + i), k1 = __ldg(ptr + i + 1);
         float m = -INFINITY, l = 0.f, att = 0.f;               // pass 1: softmax statistics and the attention output
         for (int kk = k0; kk < k1; ++kk) {
@@ -146,7 +191,7 @@ __global__ void __launch_bounds__(256) tconv1_edge_bwd_kernel(int N, const int* 
 // dx_i = W4^T ds4_i (optional) and the parameter gradients dW4 += ds4 (x) x, db += ds4; octets, accumulators in registers
 __global__ void __launch_bounds__(256) tconv1_node_bwd_kernel(int N, const float* __restrict__ x, int ldx, const float* __restrict__ P,
                                                               const float4* __restrict__ ds4, float* __restrict__ dx, int lddx,
-                                                              float* __restrict__ gP) {
+                                                              float* __restrict__ gP, int relu_mask) {
     __shared__ float s_g[T1_P];
     for (int t = threadIdx.x; t < T1_P; t += blockDim.x) s_g[t] = 0.f;
     __syncthreads();
@@ -166,6 +211,9 @@ __global__ void __launch_bounds__(256) tconv1_node_bwd_kernel(int N, const float
             o.y = fmaf(ws.y, d.w, fmaf(wv.y, d.z, fmaf(wk.y, d.y, wq.y * d.x)));
             o.z = fmaf(ws.z, d.w, fmaf(wv.z, d.z, fmaf(wk.z, d.y, wq.z * d.x)));
             o.w = fmaf(ws.w, d.w, fmaf(wv.w, d.z, fmaf(wk.w, d.y, wq.w * d.x)));
+            if (relu_mask) {                               // x = relu(.): the gradient w.r.t. the pre-activation (model/seq2seq.py:184)
+                o.x = xv.x > 0.f ? o.x : 0.f; o.y = xv.y > 0.f ? o.y : 0.f; o.z = xv.z > 0.f ? o.z : 0.f; o.w = xv.w > 0.f ? o.w : 0.f;
+            }
             *(reinterpret_cast<float4*>(dx + (size_t)i * lddx) + l8) = o;
         }
         aq.x = fmaf(d.x, xv.x, aq.x); aq.y = fmaf(d.x, xv.y, aq.y); aq.z = fmaf(d.x, xv.z, aq.z); aq.w = fmaf(d.x, xv.w, aq.w);
@@ -217,7 +265,7 @@ QMP_API int qmp_tconv1_fwd(int N, const int* in_ptr, const int* in_src, const fl
     cudaStream_t st = (cudaStream_t)stream;
     tconv1_node_fwd_kernel<<<t1_grid(N), 256, 0, st>>>(N, x, ldx, P, reinterpret_cast<float4*>(s4));
     QMP_LAUNCH_CHECK("tconv1_node_fwd_kernel");
-    tconv1_edge_fwd_kernel<<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, out, drop_p, seed, qmp::dropout_salt());
+    tconv1_edge_fwd_kernel<false><<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, out, drop_p, seed, qmp::dropout_salt(), T1Finish{});
     QMP_LAUNCH_CHECK("tconv1_edge_fwd_kernel");
     return 0;
 }
@@ -233,11 +281,59 @@ QMP_API int qmp_tconv1_bwd(int N, const int* in_ptr, const int* in_src, const fl
                 "qmp_tconv1_bwd: rows must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     QMP_CUDA(cudaMemsetAsync(ds4, 0, (size_t)N * 4 * sizeof(float), st));
-    tconv1_edge_bwd_kernel<<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, g, ds4, gP,
-                                                         drop_p, seed, qmp::dropout_salt());
+    tconv1_edge_bwd_kernel<false><<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, g, ds4, gP,
+                                                                drop_p, seed, qmp::dropout_salt(), T1Finish{});
     QMP_LAUNCH_CHECK("tconv1_edge_bwd_kernel");
     tconv1_node_bwd_kernel<<<t1_grid(N) < 296 ? t1_grid(N) : 296, 256, 0, st>>>(N, x, ldx, P, reinterpret_cast<const float4*>(ds4), dx,
-                                                                               lddx, gP);
+                                                                               lddx, gP, 0);
+    QMP_LAUNCH_CHECK("tconv1_node_bwd_kernel");
+    return 0;
+}
+
+// The whole tail of the decoder head in two launches: y = TransformerConv(32 -> 1)(h) (qmp_tconv1_fwd), then -- in the same edge
+// kernel -- out = tanh(dropout(y)) + x[:, 0] (-> sigmoid if binary) and x_next = [out, x[:, 1:]] (qmp_head_finish_fwd;
+// model/seq2seq.py:167-187, 427-428).  h [N, ldh] (32 columns), x [N, F] the step's input; writes s4 [N, 4], y [N] (both saved
+// for the backward pass), out [N], x_next [N, F] (may be NULL).
+QMP_API int qmp_head_tail_fwd(int N, const int* in_ptr, const int* in_src, const float* ea, const float* h, int ldh, const float* P,
+                              const float* x, int F, int binary, float drop_attn, unsigned long long seed_attn, float drop_out,
+                              unsigned long long seed_out, float* s4, float* y, float* out, float* x_next, void* stream) {
+    if (N <= 0) return 0;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    QMP_REQUIRE(ldh % 4 == 0 && ldh >= T1_D && al16(h) && al16(P) && al16(s4), "qmp_head_tail_fwd: rows must be 16-byte aligned");
+    QMP_REQUIRE(!ea || (reinterpret_cast<uintptr_t>(ea) & 7) == 0, "qmp_head_tail_fwd: edge attributes must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    tconv1_node_fwd_kernel<<<t1_grid(N), 256, 0, st>>>(N, h, ldh, P, reinterpret_cast<float4*>(s4));
+    QMP_LAUNCH_CHECK("tconv1_node_fwd_kernel");
+    T1Finish fin{};
+    fin.x = x; fin.F = F; fin.binary = binary; fin.drop_p = drop_out; fin.seed = seed_out; fin.out = out; fin.x_next = x_next;
+    tconv1_edge_fwd_kernel<true><<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, y, drop_attn,
+                                                               seed_attn, qmp::dropout_salt(), fin);
+    QMP_LAUNCH_CHECK("tconv1_edge_fwd_kernel");
+    return 0;
+}
+
+// Backward of qmp_head_tail_fwd in two launches (+ one memset): the edge kernel first forms d y_i and the row d x_i [F] from
+// d_out [N] / d_xnext [N, F] (either may be NULL) as qmp_head_finish_bwd does, then runs the conv's edge backward; the node
+// kernel writes dh [N, lddh] -- masked by h > 0 when relu_mask != 0, i.e. the gradient w.r.t. the pre-activation of
+// h = relu(.) (model/seq2seq.py:184) -- and accumulates the parameter gradients into gP [136] (may be NULL).  ds4 [N, 4] scratch.
+QMP_API int qmp_head_tail_bwd(int N, const int* in_ptr, const int* in_src, const float* ea, const float* h, int ldh, const float* P,
+                              const float* s4, const float* y, const float* out, const float* x, int F, int binary, float drop_attn,
+                              unsigned long long seed_attn, float drop_out, unsigned long long seed_out, const float* d_out,
+                              const float* d_xnext, float* ds4, float* dh, int lddh, int relu_mask, float* dx, float* gP, void* stream) {
+    if (N <= 0) return 0;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    QMP_REQUIRE(ldh % 4 == 0 && ldh >= T1_D && al16(h) && al16(P) && al16(s4) && al16(ds4) && (!dh || (al16(dh) && lddh % 4 == 0)),
+                "qmp_head_tail_bwd: rows must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    QMP_CUDA(cudaMemsetAsync(ds4, 0, (size_t)N * 4 * sizeof(float), st));
+    T1Finish fin{};
+    fin.x = x; fin.F = F; fin.binary = binary; fin.drop_p = drop_out; fin.seed = seed_out; fin.out = const_cast<float*>(out); fin.y = y;
+    fin.d_out = d_out; fin.d_xnext = d_xnext; fin.dx = dx;
+    tconv1_edge_bwd_kernel<true><<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, nullptr, ds4,
+                                                               gP, drop_attn, seed_attn, qmp::dropout_salt(), fin);
+    QMP_LAUNCH_CHECK("tconv1_edge_bwd_kernel");
+    tconv1_node_bwd_kernel<<<t1_grid(N) < 296 ? t1_grid(N) : 296, 256, 0, st>>>(N, h, ldh, P, reinterpret_cast<const float4*>(ds4), dh,
+                                                                               lddh, gP, relu_mask);
     QMP_LAUNCH_CHECK("tconv1_node_bwd_kernel");
     return 0;
 }

@@ -347,9 +347,9 @@ class FusedGroupFn(torch.autograd.Function):
             _lib.call(entry, N, csr.in_ptr, csr.in_src, csr.edge_attr_in,
                       xa, xa.shape[1] if xa is not None else 0, DA, GA, wa_k,
                       xb, xb.shape[1], DB, GB, int(sharedB), wb_k,
-                      mode, int(relu_out), C, out, NC * C, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps),
+                      mode, int(bool(relu_out)), C, out, NC * C, Cp, prm, int(norm_h), int(norm_c), int(norm_o), float(eps),
                       gates, Craw, O, H, Cn, head, HEADW, cc, logit, mstat, linv, float(drop_p), int(seed))
-        ctx.save_for_backward(xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out if relu_out else None, usave)
+        ctx.save_for_backward(xa, wa, xb, wb, Cp, prm, logit, mstat, linv, gates, Craw, out if relu_out == 1 else None, usave)
         ctx.set_materialize_grads(False)          # unused outputs arrive as None, not as zero-filled tensors
         ctx.holders = tuple(getattr(t, "_qmp_acc", None) if t is not None else None for t in (wa, wb, prm))
         ctx.csr, ctx.cfg = csr, cfg
@@ -372,6 +372,54 @@ def pack_tconv1(conv):
     return RowsPackFn.apply(0, conv.lin_query.weight, conv.lin_key.weight, conv.lin_value.weight, conv.lin_skip.weight,
                             conv.lin_query.bias, conv.lin_key.bias, conv.lin_value.bias, conv.lin_skip.bias,
                             conv.lin_edge.weight, conv.lin_edge.weight.new_zeros(2))
+
+
+HEAD_TAIL = os.environ.get("QMP_HEAD_TAIL", "1") != "0"    # fc_out2 + tanh / residual tail of the decoder head as ONE autograd node (two launches each way)
+
+
+class HeadTailFn(torch.autograd.Function):
+    """The tail of the decoder head (model/seq2seq.py:167-187, 427-428) in two launches each way:
+    ``y = TransformerConv(32 -> 1)(h)``, ``out = tanh(dropout(y)) + x[:, :1]`` (-> sigmoid if binary), ``x_next = [out, x[:, 1:]]``
+    (qmp_head_tail_fwd / qmp_head_tail_bwd = ScalarTConvFn + ops.HeadFinishFn without the launches in between).  With
+    ``relu_mask`` the gradient returned for ``h`` is already masked by ``h > 0``: the producer of ``h = relu(.)``
+    (FusedGroupFn with ``relu_out = 2``) then skips its own mask launch."""
+
+    @staticmethod
+    def forward(ctx, h, P, x, csr, drop_attn, seed_attn, binary, drop_out, seed_out, relu_mask):
+        N = h.shape[0]
+        h, P, x = h.contiguous(), P.contiguous(), x.contiguous()
+        dev = h.device
+        s4 = torch.empty(N, 4, dtype=_f32, device=dev)
+        y = torch.empty(N, 1, dtype=_f32, device=dev)
+        out = torch.empty(N, 1, dtype=_f32, device=dev)
+        x_next = torch.empty_like(x)
+        cfg = (int(bool(binary)), float(drop_attn), int(seed_attn), float(drop_out), int(seed_out))
+        _lib.call("qmp_head_tail_fwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, h, h.shape[1], P, x, x.shape[1], cfg[0], cfg[1], cfg[2],
+                  cfg[3], cfg[4], s4, y, out, x_next)
+        ctx.save_for_backward(h, P, s4, y, out, x)
+        ctx.set_materialize_grads(False)
+        ctx.csr, ctx.cfg, ctx.relu_mask = csr, cfg, int(bool(relu_mask))
+        ctx.holder = getattr(P, "_qmp_acc", None)
+        return out, x_next
+
+    @staticmethod
+    def backward(ctx, d_out, d_xnext):
+        global ACC_HITS
+        h, P, s4, y, out, x = ctx.saved_tensors
+        N, csr, hd = h.shape[0], ctx.csr, ctx.holder
+        binary, drop_attn, seed_attn, drop_out, seed_out = ctx.cfg
+        ACC_HITS += hd is not None
+        dev = h.device
+        d_out = d_out.contiguous() if d_out is not None else None
+        d_xnext = d_xnext.contiguous() if d_xnext is not None else None
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        gP = (hd.acc if hd is not None else torch.zeros_like(P)) if ctx.needs_input_grad[1] else None
+        dx = torch.empty_like(x)
+        ds4 = torch.empty(N, 4, dtype=_f32, device=dev)
+        _lib.call("qmp_head_tail_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, h, h.shape[1], P, s4, y, out, x, x.shape[1], binary,
+                  drop_attn, seed_attn, drop_out, seed_out, d_out, d_xnext, ds4, dh, h.shape[1], ctx.relu_mask, dx, gP)
+        return (dh, (hand_over(hd, gP) if gP is not None else None), dx if ctx.needs_input_grad[2] else None, None, None, None, None, None,
+                None, None)
 
 
 class ScalarTConvFn(torch.autograd.Function):

@@ -101,7 +101,7 @@ def fused_group_backward(ctx, *grads):
         lddp = 4 * FC
     else:
         dP = c_(grads[0])
-        if relu_out:
+        if relu_out == 1:         # relu_out == 2: the consumer (fused.HeadTailFn) returns its gradient already masked by out > 0
             g0, dP = dP, torch.empty_like(dP)
             _lib.call("qmp_relu_mask_to", out_relu, g0, dP, dP.numel())
         lddp = NC * C

@@ -140,13 +140,32 @@ class Decoder(torch.nn.Module):
             hidden.append(h)
             cell.append(c)
             inp = h
-        y = self._gnn_out(head, csr, epoch)                 # fc_out1 -> relu -> fc_out2 (seq2seq.py:182-187)
         p = self.dropout.p if self.training else 0.0
-        out, x_next = HeadFinishFn.apply(y, X, self.binary, p, next_seed() if p > 0 else 0)
+        tail = self._head_tail(head, X, csr, epoch, p)      # fc_out1 -> relu -> fc_out2 -> tanh + residual, fewest launches
+        if tail is not None:
+            out, x_next = tail
+        else:
+            y = self._gnn_out(head, csr, epoch)             # fc_out1 -> relu -> fc_out2 (seq2seq.py:182-187)
+            out, x_next = HeadFinishFn.apply(y, X, self.binary, p, next_seed() if p > 0 else 0)
         hidden, cell = _stack_layers(hidden), _stack_layers(cell)
         if _want_next:
             return out, hidden, cell, x_next
         return out, hidden, cell
+
+    def _head_tail(self, head, X, csr, epoch, p_out):
+        """(out, x_next) through FusedGroupFn (fc_out1, relu) + fused.HeadTailFn (fc_out2 and the tanh / residual tail in one
+        autograd node), or None when that path does not apply (then _gnn_out + HeadFinishFn run)."""
+        if not (self.convolution_type == 'TransformerConv' and _fused.ENABLED and _fused.SCALAR_HEAD and _fused.HEAD_TAIL
+                and self.hidden_size == _fused.FC and head.shape[1] == _fused.HEADW and self.fc_out2.out_channels == 1):
+            return None
+        p = self.fc_out1.dropout if self.training else 0.0
+        sd = (lambda: next_seed()) if p > 0 else (lambda: 0)
+        w1 = self._cached("ffc1", epoch, lambda: _fused.shared_pack(_fused.pack_fused_fn([self.fc_out1], _fused.HEADW)))
+        tail = (False, False, False, False, 1e-5, float(p))
+        h1 = _fused.FusedGroupFn.apply(None, None, head, w1, None, None, None, csr,
+                                       (0, 0, _fused.HEADW, 1, True, 0, 2, _fused.FC) + tail + (sd(),))     # relu_out = 2: see HeadTailFn
+        P2 = self._cached("ftc1", epoch, lambda: _fused.shared_pack(_fused.pack_tconv1(self.fc_out2)))
+        return _fused.HeadTailFn.apply(h1, P2, X, csr, float(p), sd(), self.binary, float(p_out), next_seed() if p_out > 0 else 0, True)
 
     def _gnn_out(self, head, csr, epoch):
         kind = self.convolution_type

@@ -748,6 +748,21 @@ def _tconv1_common(N, in_ptr, in_src, ea, x, ldx, P, drop_p):
     return E, ti, sj, X, W4, S, EA, e, al
 
 
+def qmp_head_tail_fwd(N, in_ptr, in_src, ea, h, ldh, P, x, F, binary, drop_attn, seed_attn, drop_out, seed_out, s4, y, out, x_next):
+    qmp_tconv1_fwd(N, in_ptr, in_src, ea, h, ldh, P, s4, y, drop_attn, seed_attn)
+    qmp_head_finish_fwd(y, x, N, F, binary, drop_out, seed_out, out, x_next)
+
+
+def qmp_head_tail_bwd(N, in_ptr, in_src, ea, h, ldh, P, s4, y, out, x, F, binary, drop_attn, seed_attn, drop_out, seed_out, d_out, d_xnext,
+                      ds4, dh, lddh, relu_mask, dx, gP):
+    dy = torch.zeros(N)
+    qmp_head_finish_bwd(y, out, x, d_out, d_xnext, N, F, binary, drop_out, seed_out, dy, dx)
+    qmp_tconv1_bwd(N, in_ptr, in_src, ea, h, ldh, P, s4, dy, ds4, dh, lddh, gP, drop_attn, seed_attn)
+    if relu_mask and dh is not None:
+        d = rows(dh, N, lddh, 32)
+        d.mul_((rows(h, N, ldh, 32) > 0).float())
+
+
 def qmp_tconv1_fwd(N, in_ptr, in_src, ea, x, ldx, P, s4, out, drop_p, seed):
     E, ti, sj, X, W4, S, EA, e, al = _tconv1_common(N, in_ptr, in_src, ea, x, ldx, P, drop_p)
     flat(s4, 4 * N).view(N, 4).copy_(S)
