@@ -198,7 +198,7 @@ __device__ __forceinline__ void cellb_xconv(const CellBwdArgs& a, const uint8_t*
 struct CellbHPre {
     int k0, deg, jj0, jx0[4];
     float2 ev0;
-    float4 hr0[4], uu[4];
+    float4 hr0[4];
     float m[2], li[2], lg[2];
 };
 __device__ __forceinline__ void cellb_h_load(CellbHPre& h, const CellBwdArgs& a, int tile0, int tcount, int ln, int l8, int obase) {
@@ -217,11 +217,6 @@ __device__ __forceinline__ void cellb_h_load(CellbHPre& h, const CellBwdArgs& a,
         h.m[r2] = valid ? __ldg(a.mstat + (size_t)i * 8 + crole) : 0.f;
         h.li[r2] = valid ? __ldg(a.linv + (size_t)i * 8 + crole) : 0.f;
         h.lg[r2] = on0 ? __ldg(a.logit + (size_t)(h.k0 + e4) * 8 + crole) : 0.f;
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        h.uu[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (valid) h.uu[c] = __ldg(reinterpret_cast<const float4*>(a.usave + (size_t)i * 128 + 32 * c) + l8);
     }
 #pragma unroll
     for (int x = 0; x < 4; ++x) {
@@ -469,7 +464,10 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
 #pragma unroll
                     for (int c2 = 0; c2 < 2; ++c2) {
                         dz[c2] = ld4(xrow + (2 * r2 + c2) * XPLANE + 4 * l8);
-                        uu[c2] = pre.uu[2 * r2 + c2];
+                        // the saved logit projections u_i of this conv pair: read here (the tile's rows were prefetched into L2),
+                        // not carried in registers from the top of the tile
+                        uu[c2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid) uu[c2] = __ldg(reinterpret_cast<const float4*>(a.usave + (size_t)i * 128 + 32 * (2 * r2 + c2)) + l8);
                     }
                     const int crole = 4 + 2 * r2 + cc;                                         // conv index in logit / mstat / linv
                     const float4 dzt = ld4(xrow + (2 * r2 + cc) * XPLANE + 32);                 // dze0 dze1 dzs of the role conv
