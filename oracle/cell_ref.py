@@ -19,6 +19,8 @@ CONVOLUTION_KWARGS = {                                  # model/model.py:49-57
     "TransformerConv": dict(heads=1, edge_dim=2, dropout=0.1, concat=False),
     "ChebConv": dict(K=3, normalization="sym", bias=True),
     "MHTransformerConv": dict(heads=3, edge_dim=2, dropout=0.1),
+    "GATConv": dict(heads=1, edge_dim=2),
+    "GATv2Conv": dict(heads=1, edge_dim=2),
 }
 
 GATES = ("i", "f", "c", "o")

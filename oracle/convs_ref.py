@@ -1,4 +1,4 @@
-"""Oracle restatement of the three PyG convolutions the hot path uses.  TEST INFRASTRUCTURE.
+"""Oracle restatement of the PyG convolutions the reference can select (model/model.py:39-57).  TEST INFRASTRUCTURE.
 
 PARITY UNPINNED: the arithmetic belongs to ``torch-geometric==2.2.0`` (reference
 requirements.txt:13), which is not vendored in /root/reference and not installable here.
@@ -221,5 +221,93 @@ class MHTransformerConv(TransformerConv):
         return self.lin(super().forward(x, edge_index, edge_attr))
 
 
+def add_self_loops_mean(edge_index, edge_attr, n):
+    """torch_geometric.utils: remove_self_loops, then add_self_loops(fill_value='mean') -- the new loop of node i carries
+    scatter(edge_attr, edge_index[1], reduce='mean')[i] (zeros for a node without in-edges).  GATConv.forward / GATv2Conv.forward."""
+    keep = edge_index[0] != edge_index[1]
+    ei, ea = edge_index[:, keep], edge_attr[keep]
+    cnt = torch.zeros(n, dtype=ea.dtype).index_add(0, ei[1], torch.ones(ei.shape[1], dtype=ea.dtype))
+    mean = scatter_add_rows(ea, ei[1], n) / cnt.clamp(min=1)[:, None]
+    ar = torch.arange(n, dtype=ei.dtype)
+    return torch.cat([ei, torch.stack([ar, ar])], dim=1), torch.cat([ea, mean])
+
+
+class GATConv(nn.Module):
+    """PyG 2.2.0 ``GATConv`` as the reference configures it (model/model.py:43, 55: heads=1, edge_dim=2; PyG defaults
+    concat=True, negative_slope=0.2, dropout=0, add_self_loops=True, fill_value='mean', bias=True), H heads:
+    x' = lin_src(x) viewed [H, C] (lin_dst IS lin_src for an int in_channels); alpha_src = (x' * att_src).sum(-1), alpha_dst likewise;
+    self loops with mean attributes; alpha_e = alpha_src[j] + alpha_dst[i] + (lin_edge(e) * att_edge).sum(-1);
+    leaky_relu; softmax over the in-edges; out_i = sum_e alpha_e x'_j, heads concatenated, + bias."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0, add_self_loops=True,
+                 edge_dim=None, fill_value="mean", bias=True, **_):
+        super().__init__()
+        assert concat and add_self_loops and fill_value == "mean" and edge_dim is not None and bias
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.negative_slope, self.dropout = negative_slope, dropout
+        self.lin_src = Linear(in_channels, heads * out_channels, bias=False, weight_initializer="glorot")
+        self.lin_dst = self.lin_src
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.lin_edge = Linear(edge_dim, heads * out_channels, bias=False, weight_initializer="glorot")
+        self.att_edge = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.empty(heads * out_channels))
+        self.lin_src.reset_parameters()
+        self.lin_dst.reset_parameters()
+        self.lin_edge.reset_parameters()
+        glorot(self.att_src)
+        glorot(self.att_dst)
+        glorot(self.att_edge)
+        zeros(self.bias)
+
+    def forward(self, x, edge_index, edge_attr=None):
+        n, h, c = x.shape[0], self.heads, self.out_channels
+        xs = self.lin_src(x).view(-1, h, c)
+        a_src, a_dst = (xs * self.att_src).sum(-1), (xs * self.att_dst).sum(-1)                 # [N, H]
+        ei, ea = add_self_loops_mean(edge_index, edge_attr, n)
+        src, dst = ei[0], ei[1]
+        a_edge = (self.lin_edge(ea).view(-1, h, c) * self.att_edge).sum(-1)
+        alpha = F.leaky_relu(a_src[src] + a_dst[dst] + a_edge, self.negative_slope)
+        alpha = torch.stack([segment_softmax(alpha[:, i], dst, n) for i in range(h)], dim=1)
+        alpha = F.dropout(alpha, p=self.dropout, training=self.training)
+        out = scatter_add_rows(xs[src] * alpha[:, :, None], dst, n).reshape(n, h * c)
+        return out + self.bias
+
+
+class GATv2Conv(nn.Module):
+    """PyG 2.2.0 ``GATv2Conv`` as the reference configures it (model/model.py:44, 56; share_weights=False): x_l = lin_l(x),
+    x_r = lin_r(x) (both with bias, glorot weights); self loops with mean attributes; m_e = x_l[j] + x_r[i] + lin_edge(e);
+    alpha_e = (leaky_relu(m_e) * att).sum(-1); softmax over the in-edges; out_i = sum_e alpha_e x_l[j], + bias."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0, add_self_loops=True,
+                 edge_dim=None, fill_value="mean", bias=True, share_weights=False, **_):
+        super().__init__()
+        assert concat and add_self_loops and fill_value == "mean" and edge_dim is not None and bias and not share_weights
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.negative_slope, self.dropout = negative_slope, dropout
+        self.lin_l = Linear(in_channels, heads * out_channels, bias=True, weight_initializer="glorot")
+        self.lin_r = Linear(in_channels, heads * out_channels, bias=True, weight_initializer="glorot")
+        self.att = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.lin_edge = Linear(edge_dim, heads * out_channels, bias=False, weight_initializer="glorot")
+        self.bias = nn.Parameter(torch.empty(heads * out_channels))
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+        self.lin_edge.reset_parameters()
+        glorot(self.att)
+        zeros(self.bias)
+
+    def forward(self, x, edge_index, edge_attr=None):
+        n, h, c = x.shape[0], self.heads, self.out_channels
+        xl, xr = self.lin_l(x).view(-1, h, c), self.lin_r(x).view(-1, h, c)
+        ei, ea = add_self_loops_mean(edge_index, edge_attr, n)
+        src, dst = ei[0], ei[1]
+        m = F.leaky_relu(xl[src] + xr[dst] + self.lin_edge(ea).view(-1, h, c), self.negative_slope)
+        alpha = (m * self.att).sum(-1)
+        alpha = torch.stack([segment_softmax(alpha[:, i], dst, n) for i in range(h)], dim=1)
+        alpha = F.dropout(alpha, p=self.dropout, training=self.training)
+        out = scatter_add_rows(xl[src] * alpha[:, :, None], dst, n).reshape(n, h * c)
+        return out + self.bias
+
+
 CONVOLUTIONS = {"GCNConv": GCNConv, "TransformerConv": TransformerConv, "ChebConv": ChebConv,
-                "MHTransformerConv": MHTransformerConv}
+                "MHTransformerConv": MHTransformerConv, "GATConv": GATConv, "GATv2Conv": GATv2Conv}

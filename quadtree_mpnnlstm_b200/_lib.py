@@ -62,6 +62,8 @@ SIGNATURES = {
     "qmp_fused_wgrad_tma": "ipiiipiiiiiipippppppp",
     "qmp_head_tail_fwd": "ipppp" "i" "pp" "ii" "fufu" "pppp" "p",
     "qmp_head_tail_bwd": "ipppp" "i" "ppppp" "ii" "fufu" "ppp" "p" "i" "i" "pp" "p",
+    "qmp_gat_fwd": "iiippp" "pi" "ppp" "pipp" "f" "pi" "p" "p",
+    "qmp_gat_bwd": "iiippp" "pi" "ppp" "pipp" "f" "p" "pi" "p" "pppp" "ppp" "p",
     "qmp_tconv1_fwd": "ipppp" "i" "ppp" "fup",
     "qmp_tconv1_bwd": "ipppp" "i" "ppppp" "i" "p" "fup",
     "qmp_fused_cell_fwd": "ippppipippp" "iiif" "pppppp" "i" "ppppp" "fup",
@@ -77,7 +79,7 @@ KERNELS_PER_CALL = {
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
     "qmp_lstm_gates_bwd": 1, "qmp_head_finish_fwd": 1, "qmp_head_finish_bwd": 1, "qmp_relu_mask": 1, "qmp_relu_mask_to": 1, "qmp_fused_fwd": 1, "qmp_fused_bwd_target": 1, "qmp_fused_bwd_source": 1,
     "qmp_fused_wgrad": 1, "qmp_fused_fwd_tc": 1, "qmp_fused_pack_tc": 1, "qmp_fused_bwd_target_tc": 1, "qmp_fused_bwd_source_tc": 1, "qmp_fused_bwd_onepass_tc": 1,
-    "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1, "qmp_tconv1_fwd": 2, "qmp_tconv1_bwd": 2, "qmp_head_tail_fwd": 2, "qmp_head_tail_bwd": 2, "qmp_fused_pack_cell_bwd": 1, "qmp_fused_cell_bwd": 1, "qmp_cell_wgrad": 1, "qmp_panel_wgrad": 1, "qmp_fused_wgrad_tma": 1,
+    "qmp_fused_pack_cell": 1, "qmp_fused_cell_fwd": 1, "qmp_gat_fwd": 1, "qmp_gat_bwd": 1, "qmp_tconv1_fwd": 2, "qmp_tconv1_bwd": 2, "qmp_head_tail_fwd": 2, "qmp_head_tail_bwd": 2, "qmp_fused_pack_cell_bwd": 1, "qmp_fused_cell_bwd": 1, "qmp_cell_wgrad": 1, "qmp_panel_wgrad": 1, "qmp_fused_wgrad_tma": 1,
 }
 CALL_COUNTS = {}
 

@@ -241,16 +241,111 @@ class MHTransformerConv(nn.Module):
         return NodeLinearFn.apply(out, self.lin.weight.unsqueeze(0), self.lin.bias.unsqueeze(0), True)
 
 
-class _Unsupported(nn.Module):
-    def __init__(self, *a, **k):
+# ----------------------------------------------------------------------------- GATConv / GATv2Conv
+_meanloop_cache = {}
+
+
+def add_self_loops_mean(edge_index, edge_attr, n):
+    """PyG ``remove_self_loops`` + ``add_self_loops(fill_value='mean')`` (GATConv / GATv2Conv.forward): existing self loops go,
+    every node gets one whose attributes are the mean over its incoming edges (zeros without any).  Graph preprocessing on
+    the device, cached per ``edge_index`` / ``edge_attr`` pair."""
+    key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_attr.data_ptr(), n)
+    hit = _meanloop_cache.get(key)
+    if hit is not None and hit[0] is edge_index and hit[1] is edge_attr:
+        return hit[2], hit[3]
+    keep = edge_index[0] != edge_index[1]
+    ei, ea = edge_index[:, keep], edge_attr[keep].float()
+    dev = ei.device
+    cnt = torch.zeros(n, device=dev).index_add_(0, ei[1], torch.ones(ei.shape[1], device=dev))
+    mean = torch.zeros(n, ea.shape[1], device=dev).index_add_(0, ei[1], ea) / cnt.clamp(min=1).unsqueeze(1)
+    ar = torch.arange(n, device=dev, dtype=ei.dtype)
+    ei2 = torch.cat([ei, torch.stack([ar, ar])], dim=1).contiguous()
+    ea2 = torch.cat([ea, mean]).contiguous()
+    if len(_meanloop_cache) > 8:
+        _meanloop_cache.clear()
+    _meanloop_cache[key] = (edge_index, edge_attr, ei2, ea2)
+    return ei2, ea2
+
+
+def _glorot(t):
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    t.data.uniform_(-a, a)
+
+
+class _GatBase(nn.Module):
+    def _check(self, name, heads, concat, dropout, add_self_loops, edge_dim, fill_value, bias):
+        if heads != 1 or not concat or dropout != 0.0 or not add_self_loops or edge_dim != 2 or fill_value != "mean" or not bias:
+            raise NotImplementedError(f"{name}: heads=1, concat=True, dropout=0, add_self_loops=True, edge_dim=2, fill_value='mean', "
+                                      "bias=True (the reference's CONVOLUTION_KWARGS over PyG's defaults) is implemented")
+
+
+class GATConv(_GatBase):
+    """PyG 2.2.0 ``GATConv(in, out, heads=1, edge_dim=2)`` (model/model.py:43, 55): x' = lin_src(x) (``lin_dst`` is the same
+    module), alpha_ij = softmax_j(leaky_relu(att_src . x'_j + att_dst . x'_i + att_edge . lin_edge(e_ij), 0.2)) over the
+    in-edges incl. a mean-attribute self loop, out_i = sum_j alpha_ij x'_j + bias.  Node maps on qmp_gemm, the edge phase on
+    qmp_gat_fwd / qmp_gat_bwd (csrc/gat.cu)."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0, add_self_loops=True,
+                 edge_dim=None, fill_value="mean", bias=True, **kwargs):
         super().__init__()
-        raise NotImplementedError(f"{type(self).__name__} is not selected by any configuration of the hot path "
-                                  "(SURVEY.md section 2); not implemented")
+        self._check("GATConv", heads, concat, dropout, add_self_loops, edge_dim, fill_value, bias)
+        self.in_channels, self.out_channels, self.heads, self.negative_slope = in_channels, out_channels, heads, negative_slope
+        self.lin_src = Linear(in_channels, out_channels, bias=False, weight_initializer="glorot")
+        self.lin_dst = self.lin_src
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.lin_edge = Linear(edge_dim, out_channels, bias=False, weight_initializer="glorot")
+        self.att_edge = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.lin_src.reset_parameters()
+        self.lin_dst.reset_parameters()
+        self.lin_edge.reset_parameters()
+        for t in (self.att_src, self.att_dst, self.att_edge):
+            _glorot(t)
+
+    def forward(self, x, edge_index, edge_attr=None):
+        from .ops import GatFn
+        assert edge_attr is not None, "GATConv(edge_dim=2) needs edge attributes"
+        n, C = _n_nodes(x), self.out_channels
+        ei, ea = add_self_loops_mean(edge_index, edge_attr, n)
+        csr = get_csr(ei, ea, n)
+        xs = NodeLinearFn.apply(x.float(), self.lin_src.weight.unsqueeze(0), None, True)
+        att = torch.cat([self.att_src.view(1, C), self.att_dst.view(1, C)]).unsqueeze(0)            # [1, 2, C]
+        a = NodeLinearFn.apply(xs, att, None, True)                                                   # [N, 2] = (alpha_src, alpha_dst)
+        we = (self.lin_edge.weight * self.att_edge.view(C, 1)).sum(0)                                 # att_edge . lin_edge(e) = we . e
+        return GatFn.apply(xs, a[:, 0].contiguous(), a[:, 1].contiguous(), we, csr, 1, self.negative_slope) + self.bias
 
 
-class GATConv(_Unsupported):
-    pass
+class GATv2Conv(_GatBase):
+    """PyG 2.2.0 ``GATv2Conv(in, out, heads=1, edge_dim=2)`` (model/model.py:44, 56; share_weights=False): x_l = lin_l(x),
+    x_r = lin_r(x), alpha_ij = softmax_j(att . leaky_relu(x_l[j] + x_r[i] + lin_edge(e_ij), 0.2)) over the in-edges incl. a
+    mean-attribute self loop, out_i = sum_j alpha_ij x_l[j] + bias."""
 
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0, add_self_loops=True,
+                 edge_dim=None, fill_value="mean", bias=True, share_weights=False, **kwargs):
+        super().__init__()
+        self._check("GATv2Conv", heads, concat, dropout, add_self_loops, edge_dim, fill_value, bias)
+        if share_weights:
+            raise NotImplementedError("GATv2Conv: share_weights=False only")
+        self.in_channels, self.out_channels, self.heads, self.negative_slope = in_channels, out_channels, heads, negative_slope
+        self.lin_l = Linear(in_channels, out_channels, bias=True, weight_initializer="glorot")
+        self.lin_r = Linear(in_channels, out_channels, bias=True, weight_initializer="glorot")
+        self.att = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.lin_edge = Linear(edge_dim, out_channels, bias=False, weight_initializer="glorot")
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+        self.lin_l.reset_parameters()
+        self.lin_r.reset_parameters()
+        self.lin_edge.reset_parameters()
+        _glorot(self.att)
 
-class GATv2Conv(_Unsupported):
-    pass
+    def forward(self, x, edge_index, edge_attr=None):
+        from .ops import GatFn
+        assert edge_attr is not None, "GATv2Conv(edge_dim=2) needs edge attributes"
+        n, C = _n_nodes(x), self.out_channels
+        ei, ea = add_self_loops_mean(edge_index, edge_attr, n)
+        csr = get_csr(ei, ea, n)
+        W = torch.stack([self.lin_l.weight, self.lin_r.weight])                                       # [2, C, in]
+        b = torch.stack([self.lin_l.bias, self.lin_r.bias])
+        xlr = NodeLinearFn.apply(x.float(), W, b, True)                                               # [N, 2C] = x_l | x_r
+        return GatFn.apply(xlr[:, :C].contiguous(), xlr[:, C:].contiguous(), self.lin_edge.weight, self.att.view(C), csr, 2,
+                           self.negative_slope) + self.bias

@@ -72,6 +72,8 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_tconv1_fwd": "PyG TransformerConv(hidden, 1) = the decoder's fc_out2 (model/seq2seq.py:117-121, 182-187): scalar query / key / value records",
     "qmp_head_tail_fwd": "model/seq2seq.py:167-187, 427-428: fc_out2 (TransformerConv hidden -> 1) + dropout, tanh, residual, sigmoid, next input -- two launches",
     "qmp_head_tail_bwd": "autograd of the above (incl. the relu mask of fc_out1's output, model/seq2seq.py:184)",
+    "qmp_gat_fwd": "PyG GATConv / GATv2Conv edge phase, one head (model/model.py:43-44, 55-56): additive-attention segment softmax + aggregate",
+    "qmp_gat_bwd": "autograd of the above",
     "qmp_tconv1_bwd": "autograd of the above (input gradient + parameter gradients)",
     "qmp_set_fused_paired": "(switch: two threads per node (paired warps) or one in the tcgen05 fused kernels)",
     "qmp_set_tensor_cores": "(switch: tcgen05 3xTF32 contractions on/off; parity tests run both)",

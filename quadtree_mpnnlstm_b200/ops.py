@@ -211,6 +211,48 @@ class NodeLinearFn(torch.autograd.Function):
         return dx, dWb[..., :K], (dWb[..., K] if ctx.has_b else None), None
 
 
+# =============================================================================== GAT edge phase
+class GatFn(torch.autograd.Function):
+    """out [N, C] = sum_e alpha_e XL[j_e] with alpha = softmax over the in-edges of additive attention logits (csrc/gat.cu).
+    mode 1 (GATConv): (a1, a2, a3) = (alpha_src [N], alpha_dst [N], we [2]); mode 2 (GATv2Conv): (x_r [N, C], lin_edge W [C, 2],
+    att [C])."""
+
+    @staticmethod
+    def forward(ctx, XL, a1, a2, a3, csr, mode, slope):
+        XL, a1, a2, a3 = XL.contiguous(), a1.contiguous(), a2.contiguous(), a3.contiguous()
+        N, C = XL.shape
+        out = torch.empty(N, C, dtype=_f32, device=XL.device)
+        alpha = torch.empty(max(csr.n_edges, 1), dtype=_f32, device=XL.device)
+        m1 = (a1, a2, a3) if mode == 1 else (None, None, None)
+        m2 = (a1, C, a2, a3) if mode == 2 else (None, 0, None, None)
+        _lib.call("qmp_gat_fwd", N, C, mode, csr.in_ptr, csr.in_src, csr.edge_attr_in, XL, C, *m1, *m2, float(slope), out, C, alpha)
+        ctx.save_for_backward(XL, a1, a2, a3, alpha)
+        ctx.csr, ctx.mode, ctx.slope = csr, mode, float(slope)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        XL, a1, a2, a3, alpha = ctx.saved_tensors
+        csr, mode, slope = ctx.csr, ctx.mode, ctx.slope
+        N, C = XL.shape
+        dev = XL.device
+        dOut = dOut.contiguous()
+        dlog = torch.empty(max(csr.n_edges, 1), dtype=_f32, device=dev)
+        dXL = torch.empty_like(XL)
+        m1 = (a1, a2, a3) if mode == 1 else (None, None, None)
+        m2 = (a1, C, a2, a3) if mode == 2 else (None, 0, None, None)
+        if mode == 1:
+            das, dad, dwe = torch.empty(N, dtype=_f32, device=dev), torch.empty(N, dtype=_f32, device=dev), torch.zeros(2, dtype=_f32, device=dev)
+            g = (das, dad, dwe, None, None, None)
+            ret = (das, dad, dwe)
+        else:
+            dXR, dWe, datt = torch.empty_like(XL), torch.zeros(C, 2, dtype=_f32, device=dev), torch.zeros(C, dtype=_f32, device=dev)
+            g = (None, None, None, dXR, dWe, datt)
+            ret = (dXR, dWe, datt)
+        _lib.call("qmp_gat_bwd", N, C, mode, csr.in_ptr, csr.in_src, csr.edge_attr_in, XL, C, *m1, *m2, slope, alpha, dOut, C, dlog, dXL, *g)
+        return (dXL,) + ret + (None, None, None)
+
+
 # =============================================================================== LSTM gates
 class LstmGatesFn(torch.autograd.Function):
     """Gate epilogue + LayerNorms (+ decoder head input).  P [N, 4C]; Cprev [N, C] or None;

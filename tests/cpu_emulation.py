@@ -763,6 +763,59 @@ def qmp_head_tail_bwd(N, in_ptr, in_src, ea, h, ldh, P, s4, y, out, x, F, binary
         d.mul_((rows(h, N, ldh, 32) > 0).float())
 
 
+def _gat_logits(N, C, mode, ti, sj, EA, XL, as_, ad, we, XR, We, att, slope):
+    lr = lambda v: torch.where(v > 0, v, slope * v)
+    if mode == 1:
+        pre = flat(as_, N)[sj] + flat(ad, N)[ti] + EA @ flat(we, 2)
+        return pre, lr(pre)
+    m = XL[sj] + XR[ti] + EA @ flat(We, 2 * C).view(C, 2).T
+    return m, (lr(m) * flat(att, C)).sum(1)
+
+
+def qmp_gat_fwd(N, C, mode, in_ptr, in_src, ea, XL, ldl, as_, ad, we, XR, ldr, We, att, slope, out, ldo, alpha):
+    E, ti, sj = _edge_lists(N, in_ptr, in_src)
+    EA = flat(ea, 2 * E).view(E, 2) if ea is not None else torch.zeros(E, 2)
+    xl = rows(XL, N, ldl, C)
+    xr = rows(XR, N, ldr, C) if XR is not None else None
+    _, lg = _gat_logits(N, C, mode, ti, sj, EA, xl, as_, ad, we, xr, We, att, slope)
+    mx = torch.full((N,), -float("inf")).scatter_reduce(0, ti, lg, "amax", include_self=True)
+    ex = torch.exp(lg - mx[ti])
+    al = ex / (torch.zeros(N).index_add(0, ti, ex) + 1e-16)[ti]
+    flat(alpha, E).copy_(al)
+    rows(out, N, ldo, C).copy_(torch.zeros(N, C).index_add(0, ti, al[:, None] * xl[sj]))
+
+
+def qmp_gat_bwd(N, C, mode, in_ptr, in_src, ea, XL, ldl, as_, ad, we, XR, ldr, We, att, slope, alpha, dOut, lddo, dlog, dXL, das, dad, dwe,
+                dXR, dWe, datt):
+    E, ti, sj = _edge_lists(N, in_ptr, in_src)
+    EA = flat(ea, 2 * E).view(E, 2) if ea is not None else torch.zeros(E, 2)
+    xl = rows(XL, N, ldl, C)
+    xr = rows(XR, N, ldr, C) if XR is not None else None
+    g = rows(dOut, N, lddo, C)
+    al = flat(alpha, E)
+    dal = (g[ti] * xl[sj]).sum(1)
+    t = torch.zeros(N).index_add(0, ti, al * dal)
+    dl = al * (dal - t[ti])
+    gxl = torch.zeros(N, C).index_add(0, sj, al[:, None] * g[ti])
+    pre, _ = _gat_logits(N, C, mode, ti, sj, EA, xl, as_, ad, we, xr, We, att, slope)
+    d = torch.where(pre > 0, torch.ones_like(pre), torch.full_like(pre, slope))
+    if mode == 1:
+        gg = dl * d
+        flat(das, N).copy_(torch.zeros(N).index_add(0, sj, gg))
+        flat(dad, N).copy_(torch.zeros(N).index_add(0, ti, gg))
+        if dwe is not None:
+            flat(dwe, 2).add_(gg @ EA)
+    else:
+        dm = dl[:, None] * flat(att, C) * d
+        gxl = gxl + torch.zeros(N, C).index_add(0, sj, dm)
+        rows(dXR, N, ldr, C).copy_(torch.zeros(N, C).index_add(0, ti, dm))
+        if dWe is not None:
+            flat(dWe, 2 * C).view(C, 2).add_(dm.T @ EA)
+        if datt is not None:
+            flat(datt, C).add_((dl[:, None] * torch.where(pre > 0, pre, slope * pre)).sum(0))
+    rows(dXL, N, ldl, C).copy_(gxl)
+
+
 def qmp_tconv1_fwd(N, in_ptr, in_src, ea, x, ldx, P, s4, out, drop_p, seed):
     E, ti, sj, X, W4, S, EA, e, al = _tconv1_common(N, in_ptr, in_src, ea, x, ldx, P, drop_p)
     flat(s4, 4 * N).view(N, 4).copy_(S)

@@ -112,3 +112,40 @@ def test_init_matches_torch_linear_stream():
     torch.manual_seed(4)
     b = torch.nn.Linear(7, 5)
     assert torch.equal(a.weight, b.weight) and torch.equal(a.bias, b.bias)
+
+
+def test_gat_dense():
+    """GATConv / GATv2Conv restatements (heads=1, edge_dim=2) against per-node dense formulas: softmax over the in-edges plus one
+    self loop whose attributes are the mean of the node's incoming attributes; existing self loops are replaced."""
+    import torch.nn.functional as F
+    ei, _, n = _graph(seed=7)
+    ei = torch.cat([ei, torch.tensor([[0, 2], [0, 2]])], dim=1)          # two explicit self loops: must be dropped and re-added
+    torch.manual_seed(2)
+    C = 4
+    x = torch.randn(n, 5, dtype=torch.float64)
+    ea = torch.randn(ei.shape[1], 2, dtype=torch.float64)
+    for kind in ("GATConv", "GATv2Conv"):
+        conv = getattr(R, kind)(5, C, heads=1, edge_dim=2).double().eval()
+        with torch.no_grad():
+            conv.bias.copy_(torch.randn(C))
+        out = conv.bias.expand(n, C).clone()
+        for i in range(n):
+            idx = torch.nonzero((ei[1] == i) & (ei[0] != i)).squeeze(1)
+            src = torch.cat([ei[0, idx], torch.tensor([i])])
+            attrs = torch.cat([ea[idx], ea[idx].mean(0, keepdim=True) if idx.numel() else torch.zeros(1, 2, dtype=torch.float64)])
+            if kind == "GATConv":
+                xs = conv.lin_src(x)
+                logit = (xs[src] * conv.att_src.view(C)).sum(1) + (xs[i] * conv.att_dst.view(C)).sum() \
+                    + (conv.lin_edge(attrs) * conv.att_edge.view(C)).sum(1)
+                alpha = torch.softmax(F.leaky_relu(logit, 0.2), 0)
+                out[i] += (alpha[:, None] * xs[src]).sum(0)
+            else:
+                xl, xr = conv.lin_l(x), conv.lin_r(x)
+                m = F.leaky_relu(xl[src] + xr[i] + conv.lin_edge(attrs), 0.2)
+                alpha = torch.softmax((m * conv.att.view(C)).sum(1), 0)
+                out[i] += (alpha[:, None] * xl[src]).sum(0)
+        assert torch.allclose(conv(x, ei, ea), out, atol=1e-10), kind
+    keys = set(R.GATConv(5, C, heads=1, edge_dim=2).state_dict())
+    assert {"att_src", "att_dst", "att_edge", "lin_src.weight", "lin_dst.weight", "lin_edge.weight", "bias"} == keys
+    keys = set(R.GATv2Conv(5, C, heads=1, edge_dim=2).state_dict())
+    assert {"att", "lin_l.weight", "lin_l.bias", "lin_r.weight", "lin_r.bias", "lin_edge.weight", "bias"} == keys

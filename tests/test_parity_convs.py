@@ -72,6 +72,19 @@ def test_mh_transformer_conv(be, d_in, d_out, heads, quadtree):
     _check_module(be, lambda: R.MHTransformerConv(d_in, d_out, **kw), lambda: C.MHTransformerConv(d_in, d_out, **kw), ei, ea, n, d_in)
 
 
+@pytest.mark.parametrize("kind", ["GATConv", "GATv2Conv"])
+@pytest.mark.parametrize("d_in,d_out", [(4, 32), (32, 32), (5, 8), (16, 1)])
+@pytest.mark.parametrize("quadtree", [True, False])
+def test_gat_convs(be, kind, d_in, d_out, quadtree):
+    """SURVEY 8(f).3: PyG GATConv / GATv2Conv as the reference configures them (model/model.py:43-44, 55-56: heads=1, edge_dim=2;
+    self loops with mean edge attributes): forward, input gradient and every parameter gradient against the oracle restatement."""
+    import quadtree_mpnnlstm_b200.convs as C
+    from oracle import convs_ref as R
+    ei, ea, n = _graph(6, quadtree=quadtree)
+    kw = dict(heads=1, edge_dim=2)
+    _check_module(be, lambda: getattr(R, kind)(d_in, d_out, **kw), lambda: getattr(C, kind)(d_in, d_out, **kw), ei, ea, n, d_in)
+
+
 @pytest.mark.parametrize("d_in,d_out", [(4, 16), (16, 16), (17, 16), (16, 1), (32, 32)])
 @pytest.mark.parametrize("weighted", [True, False])
 def test_cheb_conv(be, d_in, d_out, weighted):
@@ -95,7 +108,7 @@ def test_gcn_conv(be, d_in, d_out, self_loops):
 @pytest.mark.parametrize("conv,n_conv_layers,f_in,hid", [("TransformerConv", 1, 4, 32), ("TransformerConv", 3, 8, 32),
                                                          ("ChebConv", 1, 4, 16), ("ChebConv", 2, 4, 16),
                                                          ("GCNConv", 2, 4, 16), ("TransformerConv", 2, 5, 8),
-                                                         ("MHTransformerConv", 2, 5, 8)])
+                                                         ("MHTransformerConv", 2, 5, 8), ("GATConv", 2, 5, 8), ("GATv2Conv", 1, 4, 16)])
 @pytest.mark.parametrize("path", ["tc", "tc_pw", "tc_1t", "tc_2pass", "tc_sepgates", "ffma", "modular"])
 def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     import quadtree_mpnnlstm_b200.model as M
@@ -124,7 +137,7 @@ def test_gconv_lstm_cell(be, conv, n_conv_layers, f_in, hid, path, monkeypatch):
     monkeypatch.setattr(FZ, "TC_BWD", path.startswith("tc"))
     n_fused = lambda: sum(_lib.CALL_COUNTS.get(k, 0) for k in ("qmp_fused_fwd", "qmp_fused_fwd_tc", "qmp_fused_cell_fwd"))
     calls_before = n_fused()
-    ei, ea, n = _graph(4, use_edge_attrs=(conv in ("TransformerConv", "MHTransformerConv")))
+    ei, ea, n = _graph(4, use_edge_attrs=(conv in ("TransformerConv", "MHTransformerConv", "GATConv", "GATv2Conv")))
     torch.manual_seed(11)
     ref = R.GConvLSTM(f_in, hid, n_conv_layers, conv)
     gpu = be.dev(M.GConvLSTM(f_in, hid, n_conv_layers, conv))
