@@ -145,6 +145,19 @@ def test_multi_head_transformer_seq2seq(be):
     _run_pair(be, kw, x, y, cl, mask)
 
 
+@pytest.mark.parametrize("kind", ["GATConv"])
+def test_gat_seq2seq(be, kind):
+    """the driver with convolution_type='GATConv' (model/model.py:43, 55) on a dynamic quadtree mesh with edge
+    attributes: forecasts and gradients against the oracle driver.  ('GATv2Conv' cannot run through the reference driver: it is
+    built with edge_dim=2, model/model.py:56, but seq2seq.py:243 hands it 1-D edge weights; it is covered at conv and cell level.)"""
+    H, W = 24, 32
+    x, y, cl = _data(7, 3, 3, H, W, c=2)
+    mask = np.random.default_rng(3).random((H, W)) > 0.85
+    kw = dict(hidden_size=8, dropout=0.0, thresh=0.15, input_timesteps=3, input_features=5, output_timesteps=3,
+              n_layers=1, n_conv_layers=1, convolution_type=kind, transform_func=dist_from_05)
+    _run_pair(be, kw, x, y, cl, mask)
+
+
 def test_state_dict_keys_match_reference_layout(be):
     import quadtree_mpnnlstm_b200 as q
     m = q.Seq2Seq(hidden_size=8, dropout=0.1, thresh=-np.inf, input_features=8, n_layers=1, n_conv_layers=2,
