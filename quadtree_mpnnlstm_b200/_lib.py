@@ -41,6 +41,10 @@ SIGNATURES = {
     "qmp_spmm": "iippppp iffpipip".replace(" ", ""),
     "qmp_lstm_gates_fwd": "iipippiiifppppppipp",
     "qmp_lstm_gates_bwd": "iippppiiifppppipippp",
+    "qmp_gru_gates1_fwd": "lppppppppp",
+    "qmp_gru_gates1_bwd": "lpppppppppp",
+    "qmp_gru_gates2_fwd": "lppppppp",
+    "qmp_gru_gates2_bwd": "lpppppppp",
     "qmp_head_finish_fwd": "ppiiifuppp",
     "qmp_head_finish_bwd": "pppppiiifuppp",
     "qmp_relu_mask": "pplp",

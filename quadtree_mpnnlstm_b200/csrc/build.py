@@ -46,6 +46,10 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_spmm": "PyG GCNConv/ChebConv propagate (model/model.py:96)",
     "qmp_lstm_gates_fwd": "model/model.py:394-463 GConvLSTM gates; model/seq2seq.py:59-66, 138-165 norms + head input",
     "qmp_lstm_gates_bwd": "autograd of the above",
+    "qmp_gru_gates1_fwd": "model/model.py:240-250 GConvGRU update / reset gates and H * R",
+    "qmp_gru_gates1_bwd": "autograd of the above",
+    "qmp_gru_gates2_fwd": "model/model.py:251-258 GConvGRU candidate state and H'",
+    "qmp_gru_gates2_bwd": "autograd of the above",
     "qmp_head_finish_fwd": "model/seq2seq.py:167-178 (dropout, tanh, residual, sigmoid) and :427-428 (next input)",
     "qmp_head_finish_bwd": "autograd of the above",
     "qmp_relu_mask": "model/seq2seq.py:184 F.relu backward",

@@ -499,3 +499,84 @@ QMP_API int qmp_relu_mask_to(const float* y, const float* g, float* out, long lo
     QMP_LAUNCH_CHECK("qmp_relu_mask_to");
     return 0;
 }
+
+
+// ---- GConvGRU gate arithmetic (model/model.py:236-259) as two element-wise stages around conv_h_h, which reads H * R ----------
+namespace qmp {
+__device__ __forceinline__ float gru_sig(float v) { return 1.f / (1.f + expf(-v)); }
+
+__global__ void gru_gates1_fwd_kernel(long long n, const float* __restrict__ az, const float* __restrict__ bz, const float* __restrict__ ar,
+                                      const float* __restrict__ br, const float* __restrict__ H, float* __restrict__ Z,
+                                      float* __restrict__ R, float* __restrict__ HR) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float z = gru_sig(az[i] + bz[i]), r = gru_sig(ar[i] + br[i]);
+    Z[i] = z;
+    R[i] = r;
+    HR[i] = H[i] * r;
+}
+__global__ void gru_gates1_bwd_kernel(long long n, const float* __restrict__ Z, const float* __restrict__ R, const float* __restrict__ H,
+                                      const float* __restrict__ dZ, const float* __restrict__ dR, const float* __restrict__ dHR,
+                                      float* __restrict__ dpz, float* __restrict__ dpr, float* __restrict__ dH) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float z = Z[i], r = R[i], ghr = dHR ? dHR[i] : 0.f;
+    dpz[i] = (dZ ? dZ[i] : 0.f) * z * (1.f - z);
+    dpr[i] = ((dR ? dR[i] : 0.f) + ghr * H[i]) * r * (1.f - r);
+    dH[i] = ghr * r;
+}
+__global__ void gru_gates2_fwd_kernel(long long n, const float* __restrict__ ah, const float* __restrict__ bh, const float* __restrict__ Z,
+                                      const float* __restrict__ H, float* __restrict__ Ht, float* __restrict__ Hn) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float t = tanhf(ah[i] + bh[i]), z = Z[i];
+    Ht[i] = t;
+    Hn[i] = z * H[i] + (1.f - z) * t;
+}
+__global__ void gru_gates2_bwd_kernel(long long n, const float* __restrict__ Z, const float* __restrict__ H, const float* __restrict__ Ht,
+                                      const float* __restrict__ dHn, float* __restrict__ dph, float* __restrict__ dZ, float* __restrict__ dH) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = dHn[i], z = Z[i], t = Ht[i];
+    dZ[i] = g * (H[i] - t);
+    dH[i] = g * z;
+    dph[i] = g * (1.f - z) * (1.f - t * t);
+}
+}  // namespace qmp
+
+// GConvGRU, first gate stage on n = N * C elements: Z = sigmoid(az + bz), R = sigmoid(ar + br), HR = H * R (model/model.py:240-250;
+// az / bz / ar / br are the outputs of conv_x_z / conv_h_z / conv_x_r / conv_h_r).
+QMP_API int qmp_gru_gates1_fwd(long long n, const float* az, const float* bz, const float* ar, const float* br, const float* H, float* Z,
+                               float* R, float* HR, void* stream) {
+    if (n <= 0) return 0;
+    gru_gates1_fwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, az, bz, ar, br, H, Z, R, HR);
+    QMP_LAUNCH_CHECK("qmp_gru_gates1_fwd");
+    return 0;
+}
+
+// Backward of qmp_gru_gates1_fwd: dZ / dR / dHR may be NULL (zero).  dpz = d az = d bz, dpr = d ar = d br, dH = dHR * R.
+QMP_API int qmp_gru_gates1_bwd(long long n, const float* Z, const float* R, const float* H, const float* dZ, const float* dR,
+                               const float* dHR, float* dpz, float* dpr, float* dH, void* stream) {
+    if (n <= 0) return 0;
+    gru_gates1_bwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, Z, R, H, dZ, dR, dHR, dpz, dpr, dH);
+    QMP_LAUNCH_CHECK("qmp_gru_gates1_bwd");
+    return 0;
+}
+
+// GConvGRU, second gate stage: Ht = tanh(ah + bh), Hn = Z * H + (1 - Z) * Ht (model/model.py:251-258); Ht is saved.
+QMP_API int qmp_gru_gates2_fwd(long long n, const float* ah, const float* bh, const float* Z, const float* H, float* Ht, float* Hn,
+                               void* stream) {
+    if (n <= 0) return 0;
+    gru_gates2_fwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, ah, bh, Z, H, Ht, Hn);
+    QMP_LAUNCH_CHECK("qmp_gru_gates2_fwd");
+    return 0;
+}
+
+// Backward of qmp_gru_gates2_fwd: dph = d ah = d bh, dZ, dH (the Z * H term).
+QMP_API int qmp_gru_gates2_bwd(long long n, const float* Z, const float* H, const float* Ht, const float* dHn, float* dph, float* dZ,
+                               float* dH, void* stream) {
+    if (n <= 0) return 0;
+    gru_gates2_bwd_kernel<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(n, Z, H, Ht, dHn, dph, dZ, dH);
+    QMP_LAUNCH_CHECK("qmp_gru_gates2_bwd");
+    return 0;
+}

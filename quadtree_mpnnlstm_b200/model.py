@@ -272,10 +272,12 @@ class GConvGRU(nn.Module):
         X = X.float()
         if H is None:
             H = torch.zeros(X.shape[0], self.out_channels, device=X.device)
-        Z = torch.sigmoid(self.conv_x_z(X, edge_index, edge_weight) + self.conv_h_z(H, edge_index, edge_weight))
-        R = torch.sigmoid(self.conv_x_r(X, edge_index, edge_weight) + self.conv_h_r(H, edge_index, edge_weight))
-        Ht = torch.tanh(self.conv_x_h(X, edge_index, edge_weight) + self.conv_h_h(H * R, edge_index, edge_weight))
-        Hn = Z * H + (1 - Z) * Ht
+        from .ops import GruGates1Fn, GruGates2Fn
+        H = H.float()
+        # gate arithmetic as two element-wise launches around conv_h_h (csrc/lstm.cu: qmp_gru_gates1/2)
+        Z, _, HR = GruGates1Fn.apply(self.conv_x_z(X, edge_index, edge_weight), self.conv_h_z(H, edge_index, edge_weight),
+                                     self.conv_x_r(X, edge_index, edge_weight), self.conv_h_r(H, edge_index, edge_weight), H)
+        Hn = GruGates2Fn.apply(self.conv_x_h(X, edge_index, edge_weight), self.conv_h_h(HR, edge_index, edge_weight), Z, H)
         return Hn, Hn, None
 
 

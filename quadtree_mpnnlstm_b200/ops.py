@@ -253,6 +253,47 @@ class GatFn(torch.autograd.Function):
         return (dXL,) + ret + (None, None, None)
 
 
+# =============================================================================== GRU gates
+class GruGates1Fn(torch.autograd.Function):
+    """(Z, R, H * R) from the four conv outputs of the update / reset gates (model/model.py:240-250)."""
+
+    @staticmethod
+    def forward(ctx, az, bz, ar, br, H):
+        az, bz, ar, br, H = (t.contiguous() for t in (az, bz, ar, br, H))
+        Z, R, HR = torch.empty_like(H), torch.empty_like(H), torch.empty_like(H)
+        _lib.call("qmp_gru_gates1_fwd", H.numel(), az, bz, ar, br, H, Z, R, HR)
+        ctx.save_for_backward(Z, R, H)
+        ctx.set_materialize_grads(False)
+        return Z, R, HR
+
+    @staticmethod
+    def backward(ctx, dZ, dR, dHR):
+        Z, R, H = ctx.saved_tensors
+        c_ = lambda t: t.contiguous() if t is not None else None
+        dpz, dpr, dH = torch.empty_like(H), torch.empty_like(H), torch.empty_like(H)
+        _lib.call("qmp_gru_gates1_bwd", H.numel(), Z, R, H, c_(dZ), c_(dR), c_(dHR), dpz, dpr, dH)
+        return dpz, dpz, dpr, dpr, dH
+
+
+class GruGates2Fn(torch.autograd.Function):
+    """H' = Z * H + (1 - Z) * tanh(ah + bh) (model/model.py:251-258)."""
+
+    @staticmethod
+    def forward(ctx, ah, bh, Z, H):
+        ah, bh, Z, H = (t.contiguous() for t in (ah, bh, Z, H))
+        Ht, Hn = torch.empty_like(H), torch.empty_like(H)
+        _lib.call("qmp_gru_gates2_fwd", H.numel(), ah, bh, Z, H, Ht, Hn)
+        ctx.save_for_backward(Z, H, Ht)
+        return Hn
+
+    @staticmethod
+    def backward(ctx, dHn):
+        Z, H, Ht = ctx.saved_tensors
+        dph, dZ, dH = torch.empty_like(H), torch.empty_like(H), torch.empty_like(H)
+        _lib.call("qmp_gru_gates2_bwd", H.numel(), Z, H, Ht, dHn.contiguous(), dph, dZ, dH)
+        return dph, dph, dZ, dH
+
+
 # =============================================================================== LSTM gates
 class LstmGatesFn(torch.autograd.Function):
     """Gate epilogue + LayerNorms (+ decoder head input).  P [N, 4C]; Cprev [N, C] or None;

@@ -391,6 +391,34 @@ def qmp_lstm_gates_bwd(N, C, gates, Craw, Cprev, params, norm_h, norm_c, norm_o,
         flat(dparams, 13 * C).view(13, C).add_(dprm)
 
 
+def qmp_gru_gates1_fwd(n, az, bz, ar, br, H, Z, R, HR):
+    z, r = torch.sigmoid(flat(az, n) + flat(bz, n)), torch.sigmoid(flat(ar, n) + flat(br, n))
+    flat(Z, n).copy_(z)
+    flat(R, n).copy_(r)
+    flat(HR, n).copy_(flat(H, n) * r)
+
+
+def qmp_gru_gates1_bwd(n, Z, R, H, dZ, dR, dHR, dpz, dpr, dH):
+    z, r, h = flat(Z, n), flat(R, n), flat(H, n)
+    g = lambda t: flat(t, n) if t is not None else torch.zeros(n)
+    flat(dpz, n).copy_(g(dZ) * z * (1 - z))
+    flat(dpr, n).copy_((g(dR) + g(dHR) * h) * r * (1 - r))
+    flat(dH, n).copy_(g(dHR) * r)
+
+
+def qmp_gru_gates2_fwd(n, ah, bh, Z, H, Ht, Hn):
+    t = torch.tanh(flat(ah, n) + flat(bh, n))
+    flat(Ht, n).copy_(t)
+    flat(Hn, n).copy_(flat(Z, n) * flat(H, n) + (1 - flat(Z, n)) * t)
+
+
+def qmp_gru_gates2_bwd(n, Z, H, Ht, dHn, dph, dZ, dH):
+    z, h, t, g = flat(Z, n), flat(H, n), flat(Ht, n), flat(dHn, n)
+    flat(dZ, n).copy_(g * (h - t))
+    flat(dH, n).copy_(g * z)
+    flat(dph, n).copy_(g * (1 - z) * (1 - t * t))
+
+
 def qmp_head_finish_fwd(y, x, N, F, binary, drop_p, seed, out, x_next):
     xv = flat(x, N * F).view(N, F)
     o = torch.tanh(flat(y, N)) + xv[:, 0]
