@@ -66,6 +66,8 @@ SIGNATURES = {
     "qmp_fused_wgrad_tma": "ipiiipiiiiiipippppppp",
     "qmp_head_tail_fwd": "ipppp" "i" "pp" "ii" "fufu" "pppp" "p",
     "qmp_head_tail_bwd": "ipppp" "i" "ppppp" "ii" "fufu" "ppp" "p" "i" "i" "pp" "p",
+    "qmp_pack_tconv_fwd": "piiiipp",
+    "qmp_pack_tconv_bwd": "piiiippp",
     "qmp_gat_fwd": "iiippp" "pi" "ppp" "pipp" "f" "pi" "p" "p",
     "qmp_gat_bwd": "iiippp" "pi" "ppp" "pipp" "f" "p" "pi" "p" "pppp" "ppp" "p",
     "qmp_tconv1_fwd": "ipppp" "i" "ppp" "fup",

@@ -75,60 +75,89 @@ class _ParamView:
         self.lin_value, self.lin_edge, self.lin_skip = self._Lin(ps[4], ps[5]), self._Lin(ps[6], None), self._Lin(ps[7], ps[8])
 
 
+_ptr_tables = {}     # parameter data_ptrs of a conv group -> (device int64 table [G, 9], the parameters): built once per group (the
+                     # optimizer updates parameters in place, so the addresses are stable and a captured step can reuse the table)
+PACK_KERNEL = os.environ.get("QMP_PACK_KERNEL", "1") != "0"    # weight packs by qmp_pack_tconv_fwd / _bwd (False: tensor ops, the cross-check)
+
+
+def _ptr_table(params):
+    key = tuple(p.data_ptr() for p in params)
+    hit = _ptr_tables.get(key)
+    if hit is None:
+        if len(_ptr_tables) > 64:
+            _ptr_tables.clear()
+        hit = (torch.tensor(key, dtype=torch.int64, device=params[0].device), tuple(params))
+        _ptr_tables[key] = hit
+    return hit[0]
+
+
 class PackFusedFn(torch.autograd.Function):
-    """``pack_fused`` of G TransformerConvs as ONE autograd node with a closed-form backward.
+    """``pack_fused`` of G TransformerConvs as ONE autograd node: forward and backward are one launch each
+    (csrc/pack_params.cu: the parameters are read through a device pointer table, the pack is a bilinear form per conv).
 
     Built from ~40 small tensor ops per group, the pack used to leave ~100 autograd nodes per group behind; their backward
     (slice / pad / cat / bmm gradients, then one ``AccumulateGrad`` COPY per parameter because the gradients arrived as
-    strided views) was ~700 of the captured step's 2 181 launches.  Here the backward is a dozen batched ops per group and
-    hands every parameter a contiguous slice of one flat buffer, which ``AccumulateGrad`` adopts without copying -- the
-    parameters' ``.grad`` are views of a few flat buckets (one per conv group), which is also what the data-parallel
-    all-reduce wants (train.TrainStep)."""
+    strided views) was ~700 of the captured step's 2 181 launches in round 1, and even as one autograd node with batched
+    tensor ops the eight packs of a step cost ~400 launches (1.9 ms).  The backward hands every parameter a contiguous slice
+    of one flat buffer, which ``AccumulateGrad`` adopts without copying."""
 
     @staticmethod
     def forward(ctx, DC, C_out, *params):
         G = len(params) // _PARAMS_PER_CONV
+        D = params[0].shape[1]
+        ctx.DC, ctx.C_out, ctx.G, ctx.D = DC, C_out, G, D
+        ctx.shapes = [tuple(p.shape) for p in params[:_PARAMS_PER_CONV]]
+        kernel = PACK_KERNEL and params[0].is_cuda and all(p.is_contiguous() and p.dtype == _f32 for p in params)
+        ctx.kernel = kernel
+        if kernel:
+            ctx.tab = _ptr_table(params)
+            pack = torch.empty(G, conv_total(DC), dtype=_f32, device=params[0].device)
+            _lib.call("qmp_pack_tconv_fwd", ctx.tab, G, D, DC, C_out, pack)
+            return pack
         convs = [_ParamView(params[_PARAMS_PER_CONV * g:_PARAMS_PER_CONV * (g + 1)], C_out) for g in range(G)]
         with torch.no_grad():
             pack = pack_fused(convs, DC)
         ctx.save_for_backward(*params)
-        ctx.DC, ctx.C_out = DC, C_out
         return pack
 
     @staticmethod
     def backward(ctx, g):
         import math
-        ps = ctx.saved_tensors
-        G, DC, C = len(ps) // _PARAMS_PER_CONV, ctx.DC, ctx.C_out
-        st = lambda k: torch.stack([ps[_PARAMS_PER_CONV * i + k] for i in range(G)])
-        Wq, bq, Wk, We = st(0), st(1), st(2), st(6)
-        D = Wq.shape[2]
-        o1 = (DC + 2) * DC
-        o2 = o1 + DC + 4
-        o3 = o2 + FC * (DC + 4)
-        o4 = o3 + FC * DC
+        G, DC, C, D = ctx.G, ctx.DC, ctx.C_out, ctx.D
         g = g.contiguous()
-        gW1p = g[:, :o1].view(G, DC + 2, DC)
-        gb1p = g[:, o1:o2]
-        gW2p = g[:, o2:o3].view(G, FC, DC + 4)[:, :C]
-        gW3 = g[:, o3:o4].view(G, FC, DC)[:, :C, :D]
-        gb3 = g[:, o4:o4 + C]
-        # un-pad: rows / columns 0..D-1 = u part, DC, DC+1 = edge-attribute part
-        gW1b = torch.cat([torch.cat([gW1p[:, :D, :D], gW1p[:, DC:DC + 2, :D]], dim=1),
-                          torch.cat([gb1p[:, :D], gb1p[:, DC:DC + 2]], dim=1).unsqueeze(-1)], dim=2)        # [G, D+2, D+1]
-        s = 1.0 / math.sqrt(C)
-        KE = torch.cat([Wk, We], dim=2)                                   # [G, C, D+2]
-        QB = torch.cat([Wq, bq.unsqueeze(-1)], dim=2)                     # [G, C, D+1]
-        gKE = torch.bmm(QB, gW1b.transpose(1, 2)) * s                     # [G, C, D+2]
-        gQB = torch.bmm(KE, gW1b) * s                                     # [G, C, D+1]
-        pieces = [gQB[..., :D], gQB[..., D], gKE[..., :D], torch.zeros_like(bq), gW2p[..., :D], gW2p[..., DC + 2],
-                  gKE[..., D:] + gW2p[..., DC:DC + 2], gW3, gb3]
-        flat = torch.cat([t.reshape(G, -1) for t in pieces], dim=1)       # [G, per-conv parameter count]: one bucket per group
-        out, off = [None, None], 0
-        views = []
-        for k, t in enumerate(pieces):
-            n = t[0].numel()
-            views.append((off, n, tuple(ps[k].shape)))
+        if ctx.kernel:
+            flat = torch.empty(G, C * (4 * D + 6), dtype=_f32, device=g.device)
+            _lib.call("qmp_pack_tconv_bwd", ctx.tab, G, D, DC, C, g, flat)
+        else:
+            ps = ctx.saved_tensors
+            st = lambda k: torch.stack([ps[_PARAMS_PER_CONV * i + k] for i in range(G)])
+            Wq, bq, Wk, We = st(0), st(1), st(2), st(6)
+            o1 = (DC + 2) * DC
+            o2 = o1 + DC + 4
+            o3 = o2 + FC * (DC + 4)
+            o4 = o3 + FC * DC
+            gW1p = g[:, :o1].view(G, DC + 2, DC)
+            gb1p = g[:, o1:o2]
+            gW2p = g[:, o2:o3].view(G, FC, DC + 4)[:, :C]
+            gW3 = g[:, o3:o4].view(G, FC, DC)[:, :C, :D]
+            gb3 = g[:, o4:o4 + C]
+            # un-pad: rows / columns 0..D-1 = u part, DC, DC+1 = edge-attribute part
+            gW1b = torch.cat([torch.cat([gW1p[:, :D, :D], gW1p[:, DC:DC + 2, :D]], dim=1),
+                              torch.cat([gb1p[:, :D], gb1p[:, DC:DC + 2]], dim=1).unsqueeze(-1)], dim=2)        # [G, D+2, D+1]
+            s = 1.0 / math.sqrt(C)
+            KE = torch.cat([Wk, We], dim=2)                                   # [G, C, D+2]
+            QB = torch.cat([Wq, bq.unsqueeze(-1)], dim=2)                     # [G, C, D+1]
+            gKE = torch.bmm(QB, gW1b.transpose(1, 2)) * s                     # [G, C, D+2]
+            gQB = torch.bmm(KE, gW1b) * s                                     # [G, C, D+1]
+            pieces = [gQB[..., :D], gQB[..., D], gKE[..., :D], torch.zeros_like(bq), gW2p[..., :D], gW2p[..., DC + 2],
+                      gKE[..., D:] + gW2p[..., DC:DC + 2], gW3, gb3]
+            flat = torch.cat([t.reshape(G, -1) for t in pieces], dim=1)       # [G, per-conv parameter count]: one bucket per group
+        views, off = [], 0
+        for shape in ctx.shapes:
+            n = 1
+            for d in shape:
+                n *= d
+            views.append((off, n, shape))
             off += n
         grads = []
         for i in range(G):

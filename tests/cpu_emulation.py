@@ -791,6 +791,36 @@ def qmp_head_tail_bwd(N, in_ptr, in_src, ea, h, ldh, P, s4, y, out, x, F, binary
         d.mul_((rows(h, N, ldh, 32) > 0).float())
 
 
+def _pack_params_of(tab):
+    from quadtree_mpnnlstm_b200 import fused as FZ
+    for table, params in FZ._ptr_tables.values():
+        if table is tab:
+            return params
+    raise KeyError("unknown parameter table")
+
+
+def qmp_pack_tconv_fwd(tab, G, D, DC, C, out):
+    from quadtree_mpnnlstm_b200 import fused as FZ
+    ps = _pack_params_of(tab)
+    convs = [FZ._ParamView(ps[9 * g:9 * (g + 1)], C) for g in range(G)]
+    with torch.no_grad():
+        flat(out, G * FZ.conv_total(DC)).view(G, -1).copy_(FZ.pack_fused(convs, DC))
+
+
+def qmp_pack_tconv_bwd(tab, G, D, DC, C, g, grads):
+    from quadtree_mpnnlstm_b200 import fused as FZ
+    ps = [p.detach().clone().requires_grad_(True) for p in _pack_params_of(tab)]
+    convs = [FZ._ParamView(ps[9 * i:9 * (i + 1)], C) for i in range(G)]
+    with torch.enable_grad():
+        pack = FZ.pack_fused(convs, DC)
+        gs = torch.autograd.grad(pack, ps, flat(g, pack.numel()).view_as(pack), allow_unused=True)
+    rows_ = []
+    for i in range(G):
+        rows_.append(torch.cat([(gs[9 * i + k] if gs[9 * i + k] is not None else torch.zeros_like(ps[9 * i + k])).reshape(-1)
+                                for k in range(9)]))
+    flat(grads, G * rows_[0].numel()).view(G, -1).copy_(torch.stack(rows_))
+
+
 def _gat_logits(N, C, mode, ti, sj, EA, XL, as_, ad, we, XR, We, att, slope):
     lr = lambda v: torch.where(v > 0, v, slope * v)
     if mode == 1:
