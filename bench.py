@@ -184,7 +184,7 @@ def run_reference(args):
             "cpu_baseline": {"value": rate, "unit": "graph-frames/s", "cores": threads, "kind": "port", "sample": what},
             "e2e": {"value": rate, "unit": "graph-frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -409,6 +409,26 @@ def extra_inference(dev, mask, cube, clim, n_dates=12):
             "qmp_launches_per_date": ro.launches_per_replay}
 
 
+_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner to file
+    descriptor 1 when NCCL_DEBUG asks for it -- and the environment's NCCL_DEBUG is left alone), so descriptor 1 is pointed
+    at stderr for the run and the line goes to a private duplicate of the original stdout."""
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def _init_dist(dev):
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -557,7 +577,7 @@ def run_gpu(args):
             line["cpu_baseline"] = {"value": rate, "unit": "graph-frames/s", "cores": os.cpu_count() or 1,
                                     "kind": "port", "sample": what, "same_config": (t_in, t_out) == (T_IN, T_OUT),
                                     "same_frame_mix": True}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     _finish(world)
 
 
@@ -619,7 +639,7 @@ def run_infer(args):
                         "h2d_bytes_per_step": sum(t.numel() * 4 for t in (pinned[0][0], pinned[0][2])),
                         "d2h_bytes_per_step": int(host[0].numel() * 4)},
                 "gpu_launches": launches, "clocks": clocks.summary()}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     _finish(world)
 
 
@@ -637,6 +657,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
     ap.add_argument("--pixel-mesh", action="store_true", help="--mode infer on the pixel-wise mesh (N = 47 200) instead of configs[4]'s")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.mode == "infer":
