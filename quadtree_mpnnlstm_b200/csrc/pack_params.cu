@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) pack_tconv_fwd_kernel(const long long* __
     const int o1 = (DC + 2) * DC, o2 = o1 + DC + 4, o3 = o2 + FC * (DC + 4), o4 = o3 + FC * DC, total = o4 + FC;
     float* o = out + (size_t)blockIdx.x * total;
     const float s = rsqrtf((float)C);
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < total; idx += gridDim.y * blockDim.x) {
         float v = 0.f;
         if (idx < o2) {                                       // W1 | b1: the bilinear form
             int rr, c;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) pack_tconv_bwd_kernel(const long long* __
     // gradient of the bilinear form's output [D+2][D+1] read through the padding
     auto gW1b = [&](int rr, int c) { return c < D ? gp[pk_pad(rr, D, DC) * DC + c] : gp[o1 + pk_pad(rr, D, DC)]; };
     const int nq = C * D, q0 = 0, q1 = nq, q2 = q1 + C, q3 = q2 + nq, q4 = q3 + C, q5 = q4 + nq, q6 = q5 + C, q7 = q6 + 2 * C, q8 = q7 + nq;
-    for (int idx = threadIdx.x; idx < P; idx += blockDim.x) {
+    for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < P; idx += gridDim.y * blockDim.x) {
         float v = 0.f;
         if (idx < q2) {                                       // gWq | gbq = s [Wk | We] gW1b
             const int k = idx < q1 ? (idx - q0) / D : idx - q1, c = idx < q1 ? (idx - q0) % D : D;
@@ -119,7 +119,7 @@ using namespace qmp;
 QMP_API int qmp_pack_tconv_fwd(const long long* tab, int G, int D, int DC, int C, float* out, void* stream) {
     if (G <= 0) return 0;
     QMP_REQUIRE(D >= 1 && D <= DC && C >= 1 && C <= FC, "qmp_pack_tconv_fwd: need 1 <= D <= DC, 1 <= C <= 32");
-    pack_tconv_fwd_kernel<<<G, 256, 0, (cudaStream_t)stream>>>(tab, D, DC, C, out);
+    pack_tconv_fwd_kernel<<<dim3(G, 16), 256, 0, (cudaStream_t)stream>>>(tab, D, DC, C, out);      // 16 slices of a conv's pack per CTA row
     QMP_LAUNCH_CHECK("pack_tconv_fwd_kernel");
     return 0;
 }
@@ -128,7 +128,7 @@ QMP_API int qmp_pack_tconv_fwd(const long long* tab, int G, int D, int DC, int C
 QMP_API int qmp_pack_tconv_bwd(const long long* tab, int G, int D, int DC, int C, const float* g, float* grads, void* stream) {
     if (G <= 0) return 0;
     QMP_REQUIRE(D >= 1 && D <= DC && C >= 1 && C <= FC, "qmp_pack_tconv_bwd: need 1 <= D <= DC, 1 <= C <= 32");
-    pack_tconv_bwd_kernel<<<G, 256, 0, (cudaStream_t)stream>>>(tab, D, DC, C, g, grads);
+    pack_tconv_bwd_kernel<<<dim3(G, 16), 256, 0, (cudaStream_t)stream>>>(tab, D, DC, C, g, grads);
     QMP_LAUNCH_CHECK("pack_tconv_bwd_kernel");
     return 0;
 }
