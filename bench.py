@@ -251,7 +251,7 @@ def _classify(name, args):
         return ("decoder_cell_bwd" if (GA == 4 and DA == 4) else "encoder_bwd"), key
     if name in ("qmp_tconv1_fwd", "qmp_head_finish_fwd", "qmp_head_tail_fwd"):
         return "decoder_head_fwd", name
-    if name in ("qmp_tconv1_bwd", "qmp_head_finish_bwd", "qmp_relu_mask_to", "qmp_relu_mask", "qmp_panel_wgrad", "qmp_head_tail_bwd"):
+    if name in ("qmp_tconv1_bwd", "qmp_head_finish_bwd", "qmp_relu_mask_to", "qmp_relu_mask", "qmp_panel_wgrad", "qmp_head_tail_bwd", "qmp_head_bwd"):
         return "decoder_head_bwd", name
     if name.startswith("qmp_pack_") or name.startswith("qmp_fused_pack") or name in ("qmp_add_positional_encoding", "qmp_segment_sum",
                                                                                    "qmp_gather_by_label"):

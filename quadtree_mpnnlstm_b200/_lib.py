@@ -66,6 +66,8 @@ SIGNATURES = {
     "qmp_fused_wgrad_tma": "ipiiipiiiiiipippppppp",
     "qmp_head_tail_fwd": "ipppp" "i" "pp" "ii" "fufu" "pppp" "p",
     "qmp_head_tail_bwd": "ipppp" "i" "ppppp" "ii" "fufu" "ppp" "p" "i" "i" "pp" "p",
+    "qmp_pack_head_bwd": "ppp",
+    "qmp_head_bwd": "ipppp" "i" "p" "p" "i" "ppp" "pp" "p" "fup",
     "qmp_pack_tconv_fwd": "piiiipp",
     "qmp_pack_tconv_bwd": "piiiippp",
     "qmp_gat_fwd": "iiippp" "pi" "ppp" "pipp" "f" "pi" "p" "p",
@@ -125,6 +127,8 @@ def lib():
         L.qmp_fused_cell_image_bytes.argtypes = []
         L.qmp_fused_cell_bwd_image_bytes.restype = _L
         L.qmp_fused_cell_bwd_image_bytes.argtypes = []
+        L.qmp_head_bwd_image_bytes.restype = _L
+        L.qmp_head_bwd_image_bytes.argtypes = []
         L.qmp_set_dropout_salt.restype = _I
         L.qmp_set_dropout_salt.argtypes = [_P]
         for name, sig in SIGNATURES.items():
@@ -180,4 +184,4 @@ def set_dropout_salt(t):
 
 
 def exported_symbols():
-    return ["qmp_set_dropout_salt", "qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes"] + list(SIGNATURES)
+    return ["qmp_set_dropout_salt", "qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes", "qmp_head_bwd_image_bytes"] + list(SIGNATURES)

@@ -76,6 +76,9 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_tconv1_fwd": "PyG TransformerConv(hidden, 1) = the decoder's fc_out2 (model/seq2seq.py:117-121, 182-187): scalar query / key / value records",
     "qmp_head_tail_fwd": "model/seq2seq.py:167-187, 427-428: fc_out2 (TransformerConv hidden -> 1) + dropout, tanh, residual, sigmoid, next input -- two launches",
     "qmp_head_tail_bwd": "autograd of the above (incl. the relu mask of fc_out1's output, model/seq2seq.py:184)",
+    "qmp_head_bwd": "autograd of the decoder head conv fc_out1 (model/seq2seq.py:117-121, 182-187) w.r.t. its input + rows for the weight gradients: persistent launch, octet edge phase, source side by vector reductions",
+    "qmp_pack_head_bwd": "(weight image of qmp_head_bwd)",
+    "qmp_head_bwd_image_bytes": "(size of that image)",
     "qmp_pack_tconv_fwd": "(weight pack of a TransformerConv group from the PyG-named parameters, model/model.py:51: one launch instead of ~40 tensor ops)",
     "qmp_pack_tconv_bwd": "autograd of the above (contiguous per-parameter gradient slices)",
     "qmp_gat_fwd": "PyG GATConv / GATv2Conv edge phase, one head (model/model.py:43-44, 55-56): additive-attention segment softmax + aggregate",

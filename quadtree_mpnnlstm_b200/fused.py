@@ -324,6 +324,24 @@ def cell_bwd_image(wa, wb):
     return img
 
 
+_headb_cache = {}
+HEAD_BWD = os.environ.get("QMP_HEAD_BWD", "1") != "0"     # head conv fc_out1 backward: the persistent octet kernel (csrc/head_bwd.cu)
+
+
+def head_bwd_image(wb):
+    """uint8 image for qmp_head_bwd (qmp_pack_head_bwd), cached per pack."""
+    key = (wb.data_ptr(), wb._version)
+    hit = _headb_cache.get(key)
+    if hit is not None and hit[0] is wb:
+        return hit[1]
+    img = torch.empty(int(_lib.lib().qmp_head_bwd_image_bytes()), dtype=torch.uint8, device=wb.device)
+    _lib.call("qmp_pack_head_bwd", wb.detach().contiguous(), img)
+    if len(_headb_cache) > 64:
+        _headb_cache.clear()
+    _headb_cache[key] = (wb, img)
+    return img
+
+
 def is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb):
     return (mode == 1 and GA == 4 and GB == 4 and sharedB and DA == 4 and DB == 32 and C == FC and xa is not None
             and xa.shape[1] % 4 == 0 and xb.shape[1] % 4 == 0)

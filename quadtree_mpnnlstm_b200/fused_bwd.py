@@ -135,7 +135,12 @@ def fused_group_backward(ctx, *grads):
     else:
         pa = bwd_pack(wa, DAC) if GA else None
         pb = bwd_pack(wb, DBC)
-    if not cell:
+    head = (not cell and onepass and _f.HEAD_BWD and GA == 0 and GB == 1 and DB == 36 and C == FC and mode == 0 and need_dxb
+            and ldb % 4 == 0 and lddp % 4 == 0)
+    if head:        # the head conv fc_out1: persistent octet kernel (csrc/head_bwd.cu), same outputs as the one-pass kernel
+        _lib.call("qmp_head_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xb, ldb, _f.head_bwd_image(wb), dP, lddp, logit, mstat,
+                  linv, ZsB, dUsB, dxb, float(drop_p), int(seed))
+    elif not cell:
         _lib.call(("qmp_fused_bwd_onepass_tc" if onepass else "qmp_fused_bwd_target_tc") if tcb else "qmp_fused_bwd_target", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xa, lda,
                   DA, GA, pa, xb, ldb, DB, GB, int(sharedB), pb, mode, C, dP, lddp, logit, mstat, linv, ds, ZsA, dUsA, ZsB, dUsB, dxa,
                   dxb, float(drop_p), int(seed))

@@ -667,6 +667,16 @@ def qmp_fused_cell_fwd(N, in_ptr, in_src, ea, xa, lda, xb, ldb, image, Cprev, pa
         flat(usave, N * 128).view(N, 4, 32).copy_(torch.stack([h @ W1[g, :32].T + b1[g, :32] for g in range(4)], 1))
 
 
+def qmp_pack_head_bwd(pack, out):
+    qmp_fused_pack_tc(pack, 1, 36, 1, out)
+
+
+def qmp_head_bwd(N, in_ptr, in_src, ea, x, ldx, image, g, ldg, logit, mstat, linv, Zs, dUs, dx, drop_p, seed):
+    E, _, _ = _edge_lists(N, in_ptr, in_src)
+    qmp_fused_bwd_onepass_tc(N, in_ptr, in_src, ea, None, 0, 0, 0, None, x, ldx, 36, 1, 1, image, 0, _FC, g, ldg, logit, mstat, linv,
+                             torch.zeros(max(E, 1), 1), None, None, Zs, dUs, None, dx, drop_p, seed)
+
+
 def qmp_fused_pack_cell_bwd(packA, packB, out):
     qmp_fused_pack_cell(packA, packB, out)
 
@@ -990,6 +1000,10 @@ class Emulated:
             @staticmethod
             def qmp_fused_cell_bwd_image_bytes():
                 return 4 * 4 * (_total(4) + _total(32))
+
+            @staticmethod
+            def qmp_head_bwd_image_bytes():
+                return 4 * _total(36)
 
         _lib.call = call
         _lib.lib = lambda: _FakeLib

@@ -603,3 +603,46 @@ def test_onepass_backward_matches_target_plus_source(N, DA, GA, DB, GB, shared, 
         assert not torch.isnan(vb).any(), f"{k}: unwritten / NaN entries"
         err = float((va - vb).abs().max()) / max(float(va.abs().max()), 1e-6)
         assert err < 5e-5, f"{k}: {err}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,drop_p", [(1, 0.0), (130, 0.0), (333, 0.1), (5001, 0.1), (47200, 0.0)])
+def test_head_bwd_kernel_matches_onepass(N, drop_p):
+    """qmp_head_bwd (persistent octet kernel for the head conv fc_out1, csrc/head_bwd.cu) against qmp_fused_bwd_onepass_tc on the
+    same inputs: input gradient and the rows for the weight-gradient kernel.  Ragged in-degrees 0..9 (0..4 at the full size),
+    isolated nodes, partial tiles, attention dropout; softmax statistics made consistent with random logits on the host."""
+    from quadtree_mpnnlstm_b200 import _lib, fused as FZ
+    from quadtree_mpnnlstm_b200.graph_csr import get_csr
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(N + 5)
+    deg = torch.randint(0, 10, (N,), generator=g)
+    if N > 20000:
+        deg = deg.clamp(max=4)
+    dst = torch.repeat_interleave(torch.arange(N), deg)
+    E = int(dst.numel())
+    src = torch.randint(0, N, (E,), generator=g)
+    csr = get_csr(torch.stack([src, dst]).to(dev), torch.rand(E, 2, generator=g).to(dev), N)
+    xb = torch.randn(N, 36, generator=g).to(dev)
+    wb = (torch.randn(1, FZ.conv_total(36), generator=g) * 0.2).to(dev)
+    dP = torch.randn(N, 32, generator=g).to(dev)
+    logit = torch.randn(max(E, 1), 1, generator=g).to(dev)
+    ptr = csr.in_ptr.long()
+    seg = torch.repeat_interleave(torch.arange(N, device=dev), ptr[1:] - ptr[:-1])
+    mstat = torch.full((N, 1), -1e30, device=dev).scatter_reduce(0, seg[:, None], logit[:E], "amax")
+    ssum = torch.zeros(N, 1, device=dev).index_add_(0, seg, (logit[:E] - mstat[seg]).exp())
+    linv = torch.where(ssum > 0, 1.0 / ssum.clamp(min=1e-30), torch.zeros_like(ssum))
+    z = lambda *s: torch.full(s, float("nan"), device=dev)
+    a = dict(Zs=z(N, 1, 40), dUs=z(N, 1, 40), dx=z(N, 36))
+    b = dict(Zs=z(N, 1, 40), dUs=z(N, 1, 40), dx=z(N, 36))
+    seed = 4242
+    _lib.call("qmp_fused_bwd_onepass_tc", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, None, 0, 0, 0, None, xb, 36, 36, 1, 1,
+              FZ.tc_image(wb, 36, 1), 0, 32, dP, 32, logit, mstat, linv, z(max(E, 1), 1), None, None, a["Zs"], a["dUs"], None, a["dx"],
+              drop_p, seed)
+    _lib.call("qmp_head_bwd", N, csr.in_ptr, csr.in_src, csr.edge_attr_in, xb, 36, FZ.head_bwd_image(wb), dP, 32, logit, mstat, linv,
+              b["Zs"], b["dUs"], b["dx"], drop_p, seed)
+    torch.cuda.synchronize()
+    for k, width in (("dx", 36), ("Zs", 39), ("dUs", 38)):
+        va, vb = a[k][..., :width], b[k][..., :width]
+        assert not torch.isnan(vb).any(), f"{k}: unwritten / NaN entries"
+        err = float((va - vb).abs().max()) / max(float(va.abs().max()), 1e-6)
+        assert err < 5e-5, f"{k}: {err}"
