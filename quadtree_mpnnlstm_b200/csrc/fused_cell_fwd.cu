@@ -225,6 +225,10 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
         tc::mbar_init(&bars[0], 1);
         tc::mbar_init(&bars[1], 1);
         tc::fence_mbar_init();
+        // the weight image (130 KB, ~4 us from L2) starts moving before the tensor-memory allocation and the first barrier
+        tc::mbar_expect_tx(&bars[1], (uint32_t)L::BYTES);
+        for (int off = 0; off < L::BYTES; off += 16384)
+            tc::bulk_g2s(smem + off, img + off, (uint32_t)(L::BYTES - off < 16384 ? L::BYTES - off : 16384), &bars[1]);
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
@@ -232,11 +236,6 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
     tc::fence_before_sync();
     cell_sync();
     tc::fence_after_sync();
-    if (t == 0) {
-        tc::mbar_expect_tx(&bars[1], (uint32_t)L::BYTES);
-        for (int off = 0; off < L::BYTES; off += 16384)
-            tc::bulk_g2s(smem + off, img + off, (uint32_t)(L::BYTES - off < 16384 ? L::BYTES - off : 16384), &bars[1]);
-    }
     const uint32_t tmem = tmem_slot;
     const int q = warp & 3, cg = warp >> 2;                    // TMEM lane quarter; column group = conv = gate of the TMEM-side phases
     const int nrow = q * 32 + lane;                            // node row this thread owns in the TMEM-side phases

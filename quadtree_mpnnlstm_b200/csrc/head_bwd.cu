@@ -21,10 +21,10 @@ namespace qmp {
 struct HeadBwdLayout {
     static constexpr int DC = 36, KX = 40, NP = 48;               // row width, its K padding, N of every contraction (multiple of 16)
     static constexpr int BU = 2 * NP * KX * 4;                     // W1   as [n = r][k]: u_r = sum_k x_k W1[r][k]       (hi then lo)
-    static constexpr int BZ = 2 * NP * FC * 4;                     // W2^T as [n][k = o]: dz_n = sum_o g_o W2[o][n]
-    static constexpr int BS = 2 * NP * FC * 4;                     // W3^T as [n][k = o]: dx_n = sum_o g_o W3[o][n]
+    static constexpr int BZS = 2 * 2 * NP * FC * 4;                // [W2^T ; W3^T] as ONE operand of 96 rows [n][k = o]: dz_n = sum_o g_o W2[o][n]
+                                                                   // (rows 0..47), dx_n = sum_o g_o W3[o][n] (rows 48..95) -- one chain, N = 96
     static constexpr int BD = 2 * NP * KX * 4;                     // W1^T as [n = k][r]: dx_k += sum_r dU_r W1[r][k]
-    static constexpr int OU = 0, OZ = OU + BU, OS = OZ + BZ, OD = OS + BS, OB1 = OD + BD;
+    static constexpr int OU = 0, OZS = OU + BU, OD = OZS + BZS, OB1 = OD + BD;
     static constexpr int BYTES = OB1 + KX * 4;                     // + b1 (40 floats)
 };
 static_assert(HeadBwdLayout::BYTES % 16 == 0, "bulk copies move 16-byte units");
@@ -33,7 +33,8 @@ constexpr uint32_t HB_AG = 0;          // g rows: hi 32 | lo 32
 constexpr uint32_t HB_AX = 64;         // x rows: hi 40 | lo 40; later [du | dw]
 constexpr uint32_t HB_DU = 144;        // u, 48 columns
 constexpr uint32_t HB_DZ = 192;        // dz, 48 columns
-constexpr uint32_t HB_DX = 240;        // dx, 48 columns
+constexpr uint32_t HB_DX = 240;        // dx, 48 columns (= HB_DZ + 48: dz and the skip part of dx come out of one N = 96 chain)
+static_assert(HB_DX == HB_DZ + 48, "one contraction writes dz | dx");
 constexpr size_t HEADB_SMEM = HeadBwdLayout::BYTES + 2 * XPLANE * sizeof(float);
 constexpr int HEADB_THREADS = CELL_WORKERS;
 
@@ -99,17 +100,15 @@ __global__ void __launch_bounds__(HEADB_THREADS, 1) head_bwd_kernel(const __grid
         tc::mbar_init(&bars[0], 1);
         tc::mbar_init(&bars[1], 1);
         tc::fence_mbar_init();
+        tc::mbar_expect_tx(&bars[1], (uint32_t)L::BYTES);      // the weight image starts moving before the tensor-memory allocation
+        for (int off = 0; off < L::BYTES; off += 16384)
+            tc::bulk_g2s(smem + off, img + off, (uint32_t)(L::BYTES - off < 16384 ? L::BYTES - off : 16384), &bars[1]);
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
     tc::fence_before_sync();
     headb_sync();
     tc::fence_after_sync();
-    if (t == 0) {
-        tc::mbar_expect_tx(&bars[1], (uint32_t)L::BYTES);
-        for (int off = 0; off < L::BYTES; off += 16384)
-            tc::bulk_g2s(smem + off, img + off, (uint32_t)(L::BYTES - off < 16384 ? L::BYTES - off : 16384), &bars[1]);
-    }
     const uint32_t tmem = tmem_slot;
     const int beg = (int)blockIdx.x * Q;
     int end = beg + Q;
@@ -159,10 +158,8 @@ __global__ void __launch_bounds__(HEADB_THREADS, 1) head_bwd_kernel(const __grid
             tc::fence_after_sync();
             tc_mma3_at(0, tmem + HB_DU, tmem + HB_AX, tmem + HB_AX + 40, tc::smem_u32(smem + L::OU), tc::smem_u32(smem + L::OU + L::BU / 2),
                        L::NP, L::KX, false);
-            tc_mma3_at(0, tmem + HB_DZ, tmem + HB_AG, tmem + HB_AG + 32, tc::smem_u32(smem + L::OZ), tc::smem_u32(smem + L::OZ + L::BZ / 2),
-                       L::NP, FC, false);
-            tc_mma3_at(0, tmem + HB_DX, tmem + HB_AG, tmem + HB_AG + 32, tc::smem_u32(smem + L::OS), tc::smem_u32(smem + L::OS + L::BS / 2),
-                       L::NP, FC, false);
+            tc_mma3_at(0, tmem + HB_DZ, tmem + HB_AG, tmem + HB_AG + 32, tc::smem_u32(smem + L::OZS), tc::smem_u32(smem + L::OZS + L::BZS / 2),
+                       2 * L::NP, FC, false);                  // dz (columns HB_DZ ..) and the skip part of dx (HB_DX = HB_DZ + 48) in one chain
             tc::commit(&bars[0]);
         }
         __syncwarp();
@@ -388,8 +385,8 @@ __global__ void __launch_bounds__(256) pack_head_bwd_kernel(const float* __restr
     }
     for (int idx = tid; idx < L::NP * FC; idx += nth) {        // W2^T, W3^T as [n][k = o]
         const int n = idx / FC, k = idx % FC;
-        headb_put(img, L::OZ, L::BZ / 2, n, k, FC, n < 40 ? W2[k * 40 + n] : 0.f);
-        headb_put(img, L::OS, L::BS / 2, n, k, FC, n < 36 ? W3[k * 36 + n] : 0.f);
+        headb_put(img, L::OZS, L::BZS / 2, n, k, FC, n < 40 ? W2[k * 40 + n] : 0.f);
+        headb_put(img, L::OZS, L::BZS / 2, L::NP + n, k, FC, n < 36 ? W3[k * 36 + n] : 0.f);
     }
     float* b = reinterpret_cast<float*>(img + L::OB1);
     for (int idx = tid; idx < L::KX; idx += nth) b[idx] = idx < 38 ? b1[idx] : 0.f;
