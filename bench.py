@@ -259,44 +259,58 @@ def _classify(name, args):
     return "other", name
 
 
-def per_kernel_times(dev, mask, cube, clim, dropout, t_in=2, t_out=4, reps=2):
-    """Every C-ABI call of one eager training sample (full mesh, ``t_in + t_out`` frames) timed ALONE with CUDA events on the
-    launching stream, L2 flushed by a 256 MB write before each call.  Returns {key: (group, avg us, calls per frame)}."""
+def per_kernel_times(dev, mask, cube, clim, dropout, shapes=((2, 4), (3, 5)), reps=2):
+    """Every C-ABI call of one eager training sample (full mesh) timed ALONE with CUDA events on the launching stream, L2
+    flushed by a 256 MB write before each call.  Two sample shapes (t_in, t_out) are run so that the number of calls of
+    every kernel in a T_IN + T_OUT-frame step follows from a linear fit (a kernel that runs once per sample -- e.g. the
+    first forecast step's -- is not charged to every frame).  Returns {key: (group, avg us, calls per frame at 10 + 90)}."""
     import quadtree_mpnnlstm_b200 as q
     from quadtree_mpnnlstm_b200 import _lib
     from quadtree_mpnnlstm_b200.train import TrainStep
-    torch.manual_seed(21)
-    model = q.Seq2Seq(**model_kwargs(t_in, t_out, dropout), device=dev).to(dev).train()
-    step = TrainStep(model, mask, lr=1e-4, use_cuda_graph=False)
-    smp = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in sample(cube, clim, 0, t_in, t_out)]
-    step(*smp)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
-    records, orig = [], _lib.call
-
-    def timed(name, *args):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        orig(name, *args)
-        e1.record()
-        records.append((_classify(name, args), e0, e1))
-
-    _lib.call = timed
-    try:
-        for _ in range(reps):
-            step(*smp)
-    finally:
-        _lib.call = orig
-    torch.cuda.synchronize()
     tot, cnt = {}, {}
-    for (group, key), a, b in records:
-        tot[(group, key)] = tot.get((group, key), 0.0) + a.elapsed_time(b) * 1e3
-        cnt[(group, key)] = cnt.get((group, key), 0) + 1
+    N = E = 0
+    pdl_was = _lib.set_pdl(False)        # a kernel timed alone starts after the flush write has finished
+    for si, (t_in, t_out) in enumerate(shapes):
+        torch.manual_seed(21)
+        model = q.Seq2Seq(**model_kwargs(t_in, t_out, dropout), device=dev).to(dev).train()
+        step = TrainStep(model, mask, lr=1e-4, use_cuda_graph=False)
+        smp = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in sample(cube, clim, 0, t_in, t_out)]
+        step(*smp)
+        records, orig = [], _lib.call
+
+        def timed(name, *args):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            orig(name, *args)
+            e1.record()
+            records.append((_classify(name, args), e0, e1))
+
+        _lib.call = timed
+        try:
+            for _ in range(reps):
+                step(*smp)
+        finally:
+            _lib.call = orig
+        torch.cuda.synchronize()
+        for gk, a, b in records:
+            tot[gk] = tot.get(gk, 0.0) + a.elapsed_time(b) * 1e3
+            cnt.setdefault(gk, [0] * len(shapes))[si] += 1
+        N, E = int(model.graph.pyg.x.shape[0]), int(model.graph.pyg.edge_index.shape[1])
+        del model, step
+    _lib.set_pdl(pdl_was)
     out = {}
+    (i0, o0), (i1, o1) = shapes
     for (group, key), t in tot.items():
-        frames = 1 if group == "per_step" else (t_in if group.startswith("encoder") else t_out)
-        out[key] = (group, t / cnt[(group, key)], cnt[(group, key)] / (reps * frames))
-    N, E = int(model.graph.pyg.x.shape[0]), int(model.graph.pyg.edge_index.shape[1])
+        c0, c1 = (c / reps for c in cnt[(group, key)])
+        if group == "per_step":
+            frames, calls = 1, max(c0, c1)
+        else:       # calls = slope * frames + once-per-sample part, from the two shapes
+            f0, f1, frames = (i0, i1, T_IN) if group.startswith("encoder") else (o0, o1, T_OUT)
+            slope = (c1 - c0) / (f1 - f0)
+            calls = slope * frames + (c0 - slope * f0)
+        out[key] = (group, t / sum(cnt[(group, key)]), calls / frames)
     return out, N, E
 
 
@@ -471,6 +485,7 @@ def run_gpu(args):
     torch.cuda.set_device(dev)
     world = _init_dist(dev)
     _lib.lib()   # fail loudly if the CUDA library is missing
+    _lib.set_pdl(bool(args.pdl))
 
     mask = ocean_mask()
     n_dates = args.warmup + args.steps + 2
@@ -556,7 +571,7 @@ def run_gpu(args):
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD % (N, E),
-                           "dropout": args.dropout, "attention_dropout": 0.1, "cuda_graph": not args.no_graph,
+                           "dropout": args.dropout, "attention_dropout": 0.1, "cuda_graph": not args.no_graph, "pdl": bool(args.pdl),
                            "parallelism": f"dp{world}" if world > 1 else "single",
                            "l2": "inputs + saved activations per step (~10 GB) exceed the 126 MB L2; per-kernel times taken "
                                  "with a 256 MB flush write before every launch",
@@ -658,6 +673,7 @@ def main():
                     "TransformerConv attention dropout is 0.1 in train mode regardless, as in the reference")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip extra.dynamic_quadtree / extra.inference")
+    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the hot kernels (qmp_set_pdl); 0 = plain stream order")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
     ap.add_argument("--pixel-mesh", action="store_true", help="--mode infer on the pixel-wise mesh (N = 47 200) instead of configs[4]'s")
     args = ap.parse_args()

@@ -131,6 +131,8 @@ def lib():
         L.qmp_head_bwd_image_bytes.argtypes = []
         L.qmp_set_dropout_salt.restype = _I
         L.qmp_set_dropout_salt.argtypes = [_P]
+        L.qmp_set_pdl.restype = _I
+        L.qmp_set_pdl.argtypes = [_I]
         for name, sig in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = _I
@@ -183,5 +185,10 @@ def set_dropout_salt(t):
         fn(_ptr(t))
 
 
+def set_pdl(on):
+    """Programmatic dependent launch of the hot kernels on (default) / off; returns the previous setting (csrc/core.cu)."""
+    return bool(lib().qmp_set_pdl(1 if on else 0))
+
+
 def exported_symbols():
-    return ["qmp_set_dropout_salt", "qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes", "qmp_head_bwd_image_bytes"] + list(SIGNATURES)
+    return ["qmp_set_dropout_salt", "qmp_set_pdl", "qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes", "qmp_head_bwd_image_bytes"] + list(SIGNATURES)

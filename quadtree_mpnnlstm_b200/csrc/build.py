@@ -85,6 +85,7 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_gat_bwd": "autograd of the above",
     "qmp_tconv1_bwd": "autograd of the above (input gradient + parameter gradients)",
     "qmp_set_fused_paired": "(switch: two threads per node (paired warps) or one in the tcgen05 fused kernels)",
+    "qmp_set_pdl": "(switch: programmatic dependent launch of the hot kernels; stream order is what eager PyTorch gives the reference)",
     "qmp_set_tensor_cores": "(switch: tcgen05 3xTF32 contractions on/off; parity tests run both)",
     "qmp_exclusive_scan_i32": "(utility: numpy cumsum at model/graph_functions.py:511)",
     "qmp_last_error": "(error text; the reference raises Python exceptions)",

@@ -105,6 +105,8 @@ __global__ void __launch_bounds__(CW_THREADS, 1)
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    pdl_wait();
+    pdl_launch();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -313,7 +315,8 @@ QMP_API int qmp_cell_wgrad(int N, const float* h, int ldh, const float* dP, int 
     CwgArgs a{};
     a.N = N; a.gwa = gwa; a.gwb = gwb;
     const int nstages = cdiv(N, CW_NODES);
-    cell_wgrad_kernel<<<nstages < n_sm ? nstages : n_sm, CW_THREADS, CW_SMEM, (cudaStream_t)stream>>>(tm_dp, tm_z, tm_sd, tm_h, tm_du, tm_sg, a);
+    QMP_CUDA(launch_pdl(cell_wgrad_kernel, dim3(nstages < n_sm ? nstages : n_sm), dim3(CW_THREADS), CW_SMEM, (cudaStream_t)stream, tm_dp, tm_z, tm_sd,
+                        tm_h, tm_du, tm_sg, a));
     QMP_LAUNCH_CHECK("cell_wgrad_kernel");
     return 0;
 }

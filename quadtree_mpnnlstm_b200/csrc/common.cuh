@@ -54,6 +54,39 @@ __device__ __forceinline__ unsigned long long salted_seed(unsigned long long see
 #endif
 #endif
 
+// Programmatic dependent launch (PDL).  A kernel launched through launch_pdl() may start while its predecessor in the stream
+// (or captured graph) is still running: its prologue -- barrier init, tensor-memory allocation, the bulk copy of the weight
+// image -- overlaps the predecessor's tail.  Rules kept by every kernel that is launched this way:
+//   * nothing an earlier kernel of the same step wrote is read, and no global memory is written, before pdl_wait()
+//     (griddepcontrol.wait: the predecessor grid has completed and its writes are visible);
+//   * pdl_launch() (griddepcontrol.launch_dependents) comes AFTER the kernel's own pdl_wait(), so when a dependent starts, the
+//     kernel before its predecessor is complete: a prologue may read data that is two or more launches old (weight images,
+//     packed parameters, the dropout salt).
+// qmp_set_pdl(0) (or QMP_PDL=0) turns the launch attribute off: the same kernels then run fully serialised.
+// The kernels that BUILD those step constants (weight packs and images) call after_producer(): the next launch_pdl() of the
+// process is then an ordinary stream-ordered launch, so a prologue never reads an image its direct predecessor wrote.
+bool pdl_enabled();
+void after_producer();
+bool pdl_allowed_now();         // pdl_enabled() and no producer since the last launch_pdl(); clears the producer mark
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_allowed_now() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // Exclusive scan of n int32 (n <= 4M).  `blocksums` is caller scratch of >= cdiv(n,1024)+1 ints.
 // Writes the grand total to *total (device) when total != nullptr.
 int exclusive_scan_i32(const int* in, int* out, int n, int* total, int* blocksums, cudaStream_t st);

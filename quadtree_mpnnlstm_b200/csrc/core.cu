@@ -1,6 +1,7 @@
 // Error string, version, and the int32 exclusive scan shared by the graph kernels.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace qmp {
 
@@ -15,6 +16,22 @@ void set_error(const char* fmt, ...) {
 
 static const unsigned long long* g_salt = nullptr;
 const unsigned long long* dropout_salt() { return g_salt; }
+
+static int g_pdl = -1;      // -1: not decided yet (QMP_PDL, default on)
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("QMP_PDL");
+        g_pdl = e ? (atoi(e) != 0) : 1;
+    }
+    return g_pdl != 0;
+}
+static bool g_producer = true;
+void after_producer() { g_producer = true; }
+bool pdl_allowed_now() {
+    const bool ok = pdl_enabled() && !g_producer;
+    g_producer = false;
+    return ok;
+}
 
 // ---- scan: 1024 items per block (256 threads x 4), then a single block scans the block sums.
 __global__ void __launch_bounds__(256) scan_block_kernel(const int* __restrict__ in, int* __restrict__ out, int n,
@@ -110,6 +127,15 @@ QMP_API int qmp_exclusive_scan_i32(const int* in, int* out, int n, int* total, i
 // a captured CUDA graph (whose kernel arguments are frozen) resample its dropout masks every replay (the reference resamples
 // per call: torch.nn.functional.dropout in PyG TransformerConv.message, nn.Dropout in model/seq2seq.py:169).  Process-wide
 // host state, read at launch time; returns 0.
+// Programmatic dependent launch of the hot kernels (common.cuh, launch_pdl): on = 1 (default; the prologue of a kernel overlaps
+// the tail of its predecessor in the stream / captured graph), off = 0 (plain stream order; what per-kernel timing wants).
+// Process-wide host state, read at launch time; returns the previous setting.
+QMP_API int qmp_set_pdl(int on) {
+    const int prev = qmp::pdl_enabled() ? 1 : 0;
+    qmp::g_pdl = on ? 1 : 0;
+    return prev;
+}
+
 QMP_API int qmp_set_dropout_salt(const unsigned long long* salt) {
     qmp::g_salt = salt;
     return 0;

@@ -441,6 +441,8 @@ __global__ void __launch_bounds__(128, 2) fused_bwd_tc_kernel(const __grid_const
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, TC_COLS);
+    pdl_wait();
+    pdl_launch();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -543,7 +545,7 @@ int launch_bwd_tc(const FusedBwdArgs& a, cudaStream_t st) {
     const int ntiles = cdiv(a.N, 128);
     const int work = (KIND == 1 && DAC == 0 && tc_bwd_conv_items(a)) ? ntiles * a.NC : ntiles;
     const int grid = work < 2 * n_sm ? work : 2 * n_sm;
-    kern<<<grid, 128, smem, st>>>(a);
+    QMP_CUDA(launch_pdl(kern, dim3(grid), dim3(128), smem, st, a));
     QMP_LAUNCH_CHECK("fused_bwd_tc_kernel");
     return 0;
 }

@@ -278,6 +278,8 @@ __global__ void __launch_bounds__(CELLB_THREADS, 1) fused_cell_bwd_kernel(const 
         for (int off = 0; off < L::BYTES; off += 16384)
             tc::bulk_g2s(smem + off, img + off, (uint32_t)(L::BYTES - off < 16384 ? L::BYTES - off : 16384), &bars[1]);
     }
+    pdl_wait();            // barrier init, tensor-memory allocation and the image copy run under the predecessor's tail
+    pdl_launch();
     const uint32_t tmem = tmem_slot;
     const int beg = (int)blockIdx.x * Q;
     int end = beg + Q;
@@ -713,6 +715,7 @@ QMP_API long long qmp_fused_cell_bwd_image_bytes(void) { return CellBwdLayout::B
 QMP_API int qmp_fused_pack_cell_bwd(const float* packA, const float* packB, void* out, void* stream) {
     fused_pack_cell_bwd_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(packA, packB, (uint8_t*)out);
     QMP_LAUNCH_CHECK("fused_pack_cell_bwd_kernel");
+    qmp::after_producer();
     return 0;
 }
 
@@ -759,7 +762,8 @@ QMP_API int qmp_fused_cell_bwd(int N, const int* in_ptr, const int* in_src, cons
     const int Q = (cdiv(N, G) + 3) & ~3;
     const int R = cdiv(Q, 128);
     const int T0 = (cdiv(Q, R) + 3) & ~3;
-    fused_cell_bwd_kernel<<<cdiv(N, Q), CELLB_THREADS, CELLB_SMEM, st>>>(a, reinterpret_cast<const uint8_t*>(image), Q, R, T0);
+    QMP_CUDA(launch_pdl(fused_cell_bwd_kernel, dim3(cdiv(N, Q)), dim3(CELLB_THREADS), CELLB_SMEM, st, a, reinterpret_cast<const uint8_t*>(image), Q,
+                        R, T0));
     QMP_LAUNCH_CHECK("fused_cell_bwd_kernel");
     return 0;
 }

@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(CELL_THREADS, 1) fused_cell_fwd_kernel(const _
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
     for (int idx = t; idx < 13 * FC; idx += CELL_THREADS) prm[idx] = a.params[idx];
+    pdl_wait();            // everything above reads step constants only (weight image, gate parameters)
+    pdl_launch();
     tc::fence_before_sync();
     cell_sync();
     tc::fence_after_sync();
@@ -698,6 +700,7 @@ QMP_API long long qmp_fused_cell_image_bytes(void) { return CellLayout::BYTES; }
 QMP_API int qmp_fused_pack_cell(const float* packA, const float* packB, void* out, void* stream) {
     fused_pack_cell_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(packA, packB, (uint8_t*)out);
     QMP_LAUNCH_CHECK("fused_pack_cell_kernel");
+    qmp::after_producer();
     return 0;
 }
 
@@ -742,8 +745,8 @@ QMP_API int qmp_fused_cell_fwd(int N, const int* in_ptr, const int* in_src, cons
     tl.R = cdiv(tl.Q, 128);
     tl.T0 = (cdiv(tl.Q, tl.R) + 3) & ~3;
     tl.stagger = 128 - tl.T0 < g_cell_stagger ? (128 - tl.T0) & ~3 : g_cell_stagger;
-    fused_cell_fwd_kernel<<<cdiv(N, tl.Q), CELL_THREADS, CELL_SMEM, (cudaStream_t)stream>>>(a, reinterpret_cast<const uint8_t*>(image), tl,
-                                                                                          usave);
+    QMP_CUDA(launch_pdl(fused_cell_fwd_kernel, dim3(cdiv(N, tl.Q)), dim3(CELL_THREADS), CELL_SMEM, (cudaStream_t)stream, a,
+                        reinterpret_cast<const uint8_t*>(image), tl, usave));
     QMP_LAUNCH_CHECK("fused_cell_fwd_kernel");
     return 0;
 }

@@ -321,6 +321,8 @@ __global__ void __launch_bounds__(128, 2) fused_fwd_tc_kernel(const __grid_const
     if (warp == 0) tc::tmem_alloc(&tmem_slot[0], TC_COLS);    // U 48 | A_hi 40 | A_lo 40 | P 32 | stash 96 (I, F, C')
     if (a.mode == 1)
         for (int idx = t; idx < 13 * FC; idx += 128) prm[idx] = a.params[idx];
+    pdl_wait();
+    pdl_launch();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -419,7 +421,7 @@ int launch_fwd_tc(const FusedFwdArgs& a, cudaStream_t st) {
     QMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ntiles = cdiv(a.N, 128);
     const int grid = ntiles < 2 * n_sm ? ntiles : 2 * n_sm;
-    kern<<<grid, 128, smem, st>>>(a);
+    QMP_CUDA(launch_pdl(kern, dim3(grid), dim3(128), smem, st, a));
     QMP_LAUNCH_CHECK("fused_fwd_tc_kernel");
     return 0;
 }

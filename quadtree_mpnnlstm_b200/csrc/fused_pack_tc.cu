@@ -96,5 +96,6 @@ QMP_API int qmp_fused_pack_tc(const float* pack, int G, int DC, int which, void*
     QMP_REQUIRE(which >= 0 && which <= 2, "qmp_fused_pack_tc: unknown image kind %d", which);
     fused_pack_tc_kernel<<<G, 256, 0, (cudaStream_t)stream>>>(pack, G, DC, which, (uint8_t*)out);
     QMP_LAUNCH_CHECK("fused_pack_tc_kernel");
+    qmp::after_producer();
     return 0;
 }

@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(HEADB_THREADS, 1) head_bwd_kernel(const __grid
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    pdl_wait();
+    pdl_launch();
     tc::fence_before_sync();
     headb_sync();
     tc::fence_after_sync();
@@ -402,6 +404,7 @@ QMP_API long long qmp_head_bwd_image_bytes(void) { return HeadBwdLayout::BYTES; 
 QMP_API int qmp_pack_head_bwd(const float* pack, void* out, void* stream) {
     pack_head_bwd_kernel<<<8, 256, 0, (cudaStream_t)stream>>>(pack, (uint8_t*)out);
     QMP_LAUNCH_CHECK("pack_head_bwd_kernel");
+    qmp::after_producer();
     return 0;
 }
 
@@ -433,7 +436,7 @@ QMP_API int qmp_head_bwd(int N, const int* in_ptr, const int* in_src, const floa
     const int Q = (cdiv(N, G) + 3) & ~3;
     const int R = cdiv(Q, 128);
     const int T0 = (cdiv(Q, R) + 3) & ~3;
-    head_bwd_kernel<<<cdiv(N, Q), HEADB_THREADS, HEADB_SMEM, st>>>(a, reinterpret_cast<const uint8_t*>(image), Q, R, T0);
+    QMP_CUDA(launch_pdl(head_bwd_kernel, dim3(cdiv(N, Q)), dim3(HEADB_THREADS), HEADB_SMEM, st, a, reinterpret_cast<const uint8_t*>(image), Q, R, T0));
     QMP_LAUNCH_CHECK("head_bwd_kernel");
     return 0;
 }

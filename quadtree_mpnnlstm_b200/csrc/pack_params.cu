@@ -121,6 +121,7 @@ QMP_API int qmp_pack_tconv_fwd(const long long* tab, int G, int D, int DC, int C
     QMP_REQUIRE(D >= 1 && D <= DC && C >= 1 && C <= FC, "qmp_pack_tconv_fwd: need 1 <= D <= DC, 1 <= C <= 32");
     pack_tconv_fwd_kernel<<<dim3(G, 16), 256, 0, (cudaStream_t)stream>>>(tab, D, DC, C, out);      // 16 slices of a conv's pack per CTA row
     QMP_LAUNCH_CHECK("pack_tconv_fwd_kernel");
+    qmp::after_producer();
     return 0;
 }
 

@@ -90,6 +90,8 @@ __global__ void __launch_bounds__(PW_THREADS, 1) panel_wgrad_kernel(const __grid
     }
     __syncwarp();
     if (warp == 0) tc::tmem_alloc(&tmem_slot, 512);
+    pdl_wait();
+    pdl_launch();
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -291,7 +293,7 @@ QMP_API int qmp_fused_wgrad_tma(int N, const float* xa, int lda, int DA, int GA,
     int cpg = n_sm / ngroups;
     if (cpg > nstages) cpg = nstages;
     a.cpg = cpg;
-    panel_wgrad_kernel<<<cpg * ngroups, PW_THREADS, PW_SMEM, (cudaStream_t)stream>>>(m, a);
+    QMP_CUDA(launch_pdl(panel_wgrad_kernel, dim3(cpg * ngroups), dim3(PW_THREADS), PW_SMEM, (cudaStream_t)stream, m, a));
     QMP_LAUNCH_CHECK("panel_wgrad_kernel");
     return 0;
 }

@@ -30,6 +30,8 @@ __device__ __forceinline__ float t1_dot(const float4& a, const float4& b) { retu
 // s4[i] = (q, k, v, r) of node i: 8 lanes per row, one float4 of x and of each weight row per lane
 __global__ void __launch_bounds__(256) tconv1_node_fwd_kernel(int N, const float* __restrict__ x, int ldx, const float* __restrict__ P,
                                                               float4* __restrict__ s4) {
+    pdl_wait();
+    pdl_launch();
     const int lane = threadIdx.x & 31, o8 = lane >> 3, l8 = lane & 7;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const float4 wq = __ldg(reinterpret_cast<const float4*>(P) + l8), wk = __ldg(reinterpret_cast<const float4*>(P + 32) + l8),
@@ -68,6 +70,8 @@ __global__ void __launch_bounds__(256) tconv1_edge_fwd_kernel(int N, const int* 
                                                               const float* __restrict__ P, float* __restrict__ out, float drop_p,
                                                               unsigned long long seed, const unsigned long long* __restrict__ salt,
                                                               const T1Finish fin) {
+    pdl_wait();
+    pdl_launch();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     if (drop_p > 0.f) seed = salted_seed(seed, salt);
@@ -114,6 +118,8 @@ __global__ void __launch_bounds__(256) tconv1_edge_bwd_kernel(int N, const int* 
                                                               float* __restrict__ ds4, float* __restrict__ gP, float drop_p,
                                                               unsigned long long seed, const unsigned long long* __restrict__ salt,
                                                               const T1Finish fin) {
+    pdl_wait();
+    pdl_launch();
     if (drop_p > 0.f) seed = salted_seed(seed, salt);
     __shared__ float s_we[2];
     if (threadIdx.x < 2) s_we[threadIdx.x] = 0.f;
@@ -192,6 +198,8 @@ __global__ void __launch_bounds__(256) tconv1_edge_bwd_kernel(int N, const int* 
 __global__ void __launch_bounds__(256) tconv1_node_bwd_kernel(int N, const float* __restrict__ x, int ldx, const float* __restrict__ P,
                                                               const float4* __restrict__ ds4, float* __restrict__ dx, int lddx,
                                                               float* __restrict__ gP, int relu_mask) {
+    pdl_wait();
+    pdl_launch();
     __shared__ float s_g[T1_P];
     for (int t = threadIdx.x; t < T1_P; t += blockDim.x) s_g[t] = 0.f;
     __syncthreads();
@@ -263,9 +271,9 @@ QMP_API int qmp_tconv1_fwd(int N, const int* in_ptr, const int* in_src, const fl
     QMP_REQUIRE(ldx % 4 == 0 && ldx >= T1_D && al16(x) && al16(P) && al16(s4), "qmp_tconv1_fwd: rows must be 16-byte aligned");
     QMP_REQUIRE(!ea || (reinterpret_cast<uintptr_t>(ea) & 7) == 0, "qmp_tconv1_fwd: edge attributes must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    tconv1_node_fwd_kernel<<<t1_grid(N), 256, 0, st>>>(N, x, ldx, P, reinterpret_cast<float4*>(s4));
+    QMP_CUDA(launch_pdl(tconv1_node_fwd_kernel, dim3(t1_grid(N)), dim3(256), 0, st, N, x, ldx, P, reinterpret_cast<float4*>(s4)));
     QMP_LAUNCH_CHECK("tconv1_node_fwd_kernel");
-    tconv1_edge_fwd_kernel<false><<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, out, drop_p, seed, qmp::dropout_salt(), T1Finish{});
+    QMP_CUDA(launch_pdl(tconv1_edge_fwd_kernel<false>, dim3(cdiv(N, 256)), dim3(256), 0, st, N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, out, drop_p, seed, qmp::dropout_salt(), T1Finish{}));
     QMP_LAUNCH_CHECK("tconv1_edge_fwd_kernel");
     return 0;
 }
@@ -281,11 +289,11 @@ QMP_API int qmp_tconv1_bwd(int N, const int* in_ptr, const int* in_src, const fl
                 "qmp_tconv1_bwd: rows must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     QMP_CUDA(cudaMemsetAsync(ds4, 0, (size_t)N * 4 * sizeof(float), st));
-    tconv1_edge_bwd_kernel<false><<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, g, ds4, gP,
-                                                                drop_p, seed, qmp::dropout_salt(), T1Finish{});
+    QMP_CUDA(launch_pdl(tconv1_edge_bwd_kernel<false>, dim3(cdiv(N, 256)), dim3(256), 0, st, N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, g, ds4, gP,
+                                                                drop_p, seed, qmp::dropout_salt(), T1Finish{}));
     QMP_LAUNCH_CHECK("tconv1_edge_bwd_kernel");
-    tconv1_node_bwd_kernel<<<t1_grid(N) < 296 ? t1_grid(N) : 296, 256, 0, st>>>(N, x, ldx, P, reinterpret_cast<const float4*>(ds4), dx,
-                                                                               lddx, gP, 0);
+    QMP_CUDA(launch_pdl(tconv1_node_bwd_kernel, dim3(t1_grid(N) < 296 ? t1_grid(N) : 296), dim3(256), 0, st, N, x, ldx, P, reinterpret_cast<const float4*>(ds4), dx,
+                                                                               lddx, gP, 0));
     QMP_LAUNCH_CHECK("tconv1_node_bwd_kernel");
     return 0;
 }
@@ -302,12 +310,12 @@ QMP_API int qmp_head_tail_fwd(int N, const int* in_ptr, const int* in_src, const
     QMP_REQUIRE(ldh % 4 == 0 && ldh >= T1_D && al16(h) && al16(P) && al16(s4), "qmp_head_tail_fwd: rows must be 16-byte aligned");
     QMP_REQUIRE(!ea || (reinterpret_cast<uintptr_t>(ea) & 7) == 0, "qmp_head_tail_fwd: edge attributes must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    tconv1_node_fwd_kernel<<<t1_grid(N), 256, 0, st>>>(N, h, ldh, P, reinterpret_cast<float4*>(s4));
+    QMP_CUDA(launch_pdl(tconv1_node_fwd_kernel, dim3(t1_grid(N)), dim3(256), 0, st, N, h, ldh, P, reinterpret_cast<float4*>(s4)));
     QMP_LAUNCH_CHECK("tconv1_node_fwd_kernel");
     T1Finish fin{};
     fin.x = x; fin.F = F; fin.binary = binary; fin.drop_p = drop_out; fin.seed = seed_out; fin.out = out; fin.x_next = x_next;
-    tconv1_edge_fwd_kernel<true><<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, y, drop_attn,
-                                                               seed_attn, qmp::dropout_salt(), fin);
+    QMP_CUDA(launch_pdl(tconv1_edge_fwd_kernel<true>, dim3(cdiv(N, 256)), dim3(256), 0, st, N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, y, drop_attn,
+                                                               seed_attn, qmp::dropout_salt(), fin));
     QMP_LAUNCH_CHECK("tconv1_edge_fwd_kernel");
     return 0;
 }
@@ -329,11 +337,11 @@ QMP_API int qmp_head_tail_bwd(int N, const int* in_ptr, const int* in_src, const
     T1Finish fin{};
     fin.x = x; fin.F = F; fin.binary = binary; fin.drop_p = drop_out; fin.seed = seed_out; fin.out = const_cast<float*>(out); fin.y = y;
     fin.d_out = d_out; fin.d_xnext = d_xnext; fin.dx = dx;
-    tconv1_edge_bwd_kernel<true><<<cdiv(N, 256), 256, 0, st>>>(N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, nullptr, ds4,
-                                                               gP, drop_attn, seed_attn, qmp::dropout_salt(), fin);
+    QMP_CUDA(launch_pdl(tconv1_edge_bwd_kernel<true>, dim3(cdiv(N, 256)), dim3(256), 0, st, N, in_ptr, in_src, ea, reinterpret_cast<const float4*>(s4), P, nullptr, ds4,
+                                                               gP, drop_attn, seed_attn, qmp::dropout_salt(), fin));
     QMP_LAUNCH_CHECK("tconv1_edge_bwd_kernel");
-    tconv1_node_bwd_kernel<<<t1_grid(N) < 296 ? t1_grid(N) : 296, 256, 0, st>>>(N, h, ldh, P, reinterpret_cast<const float4*>(ds4), dh,
-                                                                               lddh, gP, relu_mask);
+    QMP_CUDA(launch_pdl(tconv1_node_bwd_kernel, dim3(t1_grid(N) < 296 ? t1_grid(N) : 296), dim3(256), 0, st, N, h, ldh, P, reinterpret_cast<const float4*>(ds4), dh,
+                                                                               lddh, gP, relu_mask));
     QMP_LAUNCH_CHECK("tconv1_node_bwd_kernel");
     return 0;
 }

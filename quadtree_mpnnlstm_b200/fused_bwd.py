@@ -81,7 +81,9 @@ def fused_group_backward(ctx, *grads):
     dCprev = dparams = dconcat = None
     need_dxa = GA > 0 and ctx.needs_input_grad[0]
     need_dxb = ctx.needs_input_grad[2]
-    cell = (_fz.CELL_BWD and _fz.TC_BWD and usave is not None and need_dxa and need_dxb
+    # (the kernel always writes both input gradients: a frame whose x or H needs none -- the first forecast step, whose
+    # x is an input frame -- hands it a scratch row buffer instead of falling back to the per-conv kernels)
+    cell = (_fz.CELL_BWD and _fz.TC_BWD and usave is not None and (need_dxa or need_dxb)
             and _fz.is_decoder_cell(DA, GA, DB, GB, sharedB, mode, C, xa, xb))
     gate_args = None
     if mode == 1:
@@ -122,8 +124,8 @@ def fused_group_backward(ctx, *grads):
     from . import fused as _f
     tcb = _f.TC_BWD
     onepass = tcb and _f.ONEPASS_BWD and not cell and (need_dxa or need_dxb)
-    dxa = torch.empty_like(xa) if need_dxa else None
-    dxb = torch.empty_like(xb) if need_dxb else None
+    dxa = torch.empty_like(xa) if (need_dxa or (cell and GA)) else None
+    dxb = torch.empty_like(xb) if (need_dxb or cell) else None
     lda = xa.shape[1] if xa is not None else 0
     ldb = xb.shape[1]
     if cell:        # target and source side of every edge in one persistent launch (csrc/fused_cell_bwd.cu)
@@ -174,5 +176,5 @@ def fused_group_backward(ctx, *grads):
         if GA:
             _weight_grads(gwa, DAC, DA, GA, xa, lda, True, ZsA, dUsA, GA * (DAC + 4), dP, lddp, 0, C, C, N)
         _weight_grads(gwb, DBC, DB, GB, xb, ldb, sharedB, ZsB, dUsB, GB * (DBC + 4), dP, lddp, GA * C, C, C, N)
-    return (dxa, hand_over(ha, gwa) if GA else None, dxb, hand_over(hb, gwb), dCprev,
+    return (dxa if need_dxa else None, hand_over(ha, gwa) if GA else None, dxb if need_dxb else None, hand_over(hb, gwb), dCprev,
             hand_over(hp, dparams) if dparams is not None else None, dconcat, None, None)

@@ -28,7 +28,7 @@ def test_ctypes_signatures_match_sources():
     sys.path.insert(0, os.path.join(ROOT, "quadtree_mpnnlstm_b200", "csrc"))
     import gen_abi
     from quadtree_mpnnlstm_b200 import _lib
-    protos = {name: "".join(gen_abi.code_of(t) for t, _ in args) for _, name, ret, args in gen_abi.prototypes() if ret == "int" and name not in ("qmp_version", "qmp_set_tensor_cores", "qmp_set_fused_paired", "qmp_set_dropout_salt")}
+    protos = {name: "".join(gen_abi.code_of(t) for t, _ in args) for _, name, ret, args in gen_abi.prototypes() if ret == "int" and name not in ("qmp_version", "qmp_set_tensor_cores", "qmp_set_fused_paired", "qmp_set_dropout_salt", "qmp_set_pdl")}
     assert protos == _lib.SIGNATURES
 
 
