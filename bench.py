@@ -404,27 +404,32 @@ def inference_setup(dev, mask, static_mesh=True):
     return model, gs
 
 
-def extra_inference(dev, mask, cube, clim, n_dates=12):
+def extra_inference(dev, mask, cube, clim, n_dates=16):
     """configs[4] (ice_inf.py:60): rollout inference on the static heterogeneous mesh (max cell 4), 10 + 90 frames per launch
-    date, no_grad, the whole rollout one CUDA-graph replay per launch date (infer.Rollout)."""
-    from quadtree_mpnnlstm_b200.infer import Rollout
+    date, no_grad, the whole rollout one CUDA-graph replay per launch date; independent launch dates replayed concurrently on
+    infer.RolloutPool's lanes (a rollout's persistent kernels are 32 CTAs on this mesh), next to one lane alone."""
+    from quadtree_mpnnlstm_b200.infer import RolloutPool
     model, gs = inference_setup(dev, mask)
-    ro = Rollout(model, mask, graph_structure=gs, use_cuda_graph=True)
     xs = [[torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in sample(cube, clim, d % 4)] for d in range(4)]
-    for d in range(4):                  # 2 eager warm-ups, the capture, one replay
-        ro(xs[d][0], xs[d][2])
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for d in range(n_dates):
-        out = ro(xs[d % 4][0], xs[d % 4][2])
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n_dates
+    res = {}
+    for label, lanes in (("one_lane", 1), ("pool", None)):
+        pool = RolloutPool(model, mask, graph_structure=gs, lanes=lanes)
+        pool.warm(xs[0][0], xs[0][2])
+        xl, cl = [xs[d % 4][0] for d in range(n_dates)], [xs[d % 4][2] for d in range(n_dates)]
+        pool.predict_many(xl, cl)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = pool.predict_many(xl, cl)
+        e1.record()
+        torch.cuda.synchronize()
+        res[label] = (e0.elapsed_time(e1) / n_dates, len(pool.lanes), pool.launches_per_replay)
+    ms, lanes, launches = res["pool"]
     return {"workload": "configs[4]: static heterogeneous mesh max cell 4 (N=%d, E=%d), 10+90 frames per launch date, no_grad, "
-                        "one CUDA-graph replay per date" % (int(gs["mapping"].n_nodes), int(gs["edge_index"].shape[1])),
-            "launch_dates_per_s": 1e3 / ms, "graph_frames_per_s": FRAMES * 1e3 / ms, "ms_per_launch_date": ms,
-            "qmp_launches_per_date": ro.launches_per_replay}
+                        "one CUDA-graph replay per date, %d dates in flight on their own streams"
+                        % (int(gs["mapping"].n_nodes), int(gs["edge_index"].shape[1]), lanes),
+            "launch_dates_per_s": 1e3 / ms, "graph_frames_per_s": FRAMES * 1e3 / ms, "ms_per_launch_date": ms, "lanes": lanes,
+            "one_lane_launch_dates_per_s": 1e3 / res["one_lane"][0], "qmp_launches_per_date": launches}
 
 
 _OUT = None
@@ -605,7 +610,7 @@ def run_infer(args):
     collective, one all_gather of the forecasts at the end), every rank replaying its captured rollout per date."""
     import torch.distributed as dist
     from quadtree_mpnnlstm_b200 import _lib
-    from quadtree_mpnnlstm_b200.infer import Rollout, predict_sharded
+    from quadtree_mpnnlstm_b200.infer import Rollout, RolloutPool, predict_sharded
     rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
@@ -617,15 +622,22 @@ def run_infer(args):
     cube = synthetic_cube(FRAMES + 8)
     clim = np.ascontiguousarray(cube[..., :1].mean(0, keepdims=True).repeat(366, 0))
     model, gs = inference_setup(dev, mask, static_mesh=not args.pixel_mesh)
-    ro = Rollout(model, mask, graph_structure=gs, use_cuda_graph=not args.no_graph)
+    if args.no_graph:
+        ro = Rollout(model, mask, graph_structure=gs, use_cuda_graph=False)
+    else:       # independent launch dates in flight on their own streams (one lane on the pixel-wise mesh: it fills the GPU)
+        ro = RolloutPool(model, mask, graph_structure=gs, lanes=args.lanes or None)
     pinned = [[torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in sample(cube, clim, d)] for d in range(4)]
 
     def load(d):                # host -> device inside the timed region (e2e: inputs start in pinned host memory)
         x, _, cl = pinned[d % 4]
         return x.to(dev, non_blocking=True), cl.to(dev, non_blocking=True)
 
-    for _ in range(max(args.warmup, 4)):        # eager warm-ups, the capture, a replay
-        ro(*load(0))
+    if isinstance(ro, RolloutPool):
+        ro.warm(*load(0))
+        ro.predict_many(*zip(*[load(d) for d in range(2 * len(ro.lanes))]))
+    else:
+        for _ in range(max(args.warmup, 4)):        # eager warm-ups
+            ro(*load(0))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -653,7 +665,8 @@ def run_infer(args):
                 "dtype": "f32", "data": "synthetic", "mode": "infer",
                 "config": {"workload": f"ice_inf (configs[4]): 229x361, {mesh} N={N}, TransformerConv hidden 32, 10+90 frames per "
                                        f"launch date, no_grad, {per_rank} launch dates per GPU, forecasts gathered + copied to the host",
-                           "cuda_graph": ro.graph is not None, "parallelism": f"dates/{world}"},
+                           "cuda_graph": ro.graph is not None, "parallelism": f"dates/{world}",
+                           "lanes": len(ro.lanes) if isinstance(ro, RolloutPool) else 1},
                 "e2e": {"value": n_dates / sec, "unit": "launch-dates/s",
                         "h2d_bytes_per_step": sum(t.numel() * 4 for t in (pinned[0][0], pinned[0][2])),
                         "d2h_bytes_per_step": int(host[0].numel() * 4)},
@@ -673,8 +686,9 @@ def main():
                     "TransformerConv attention dropout is 0.1 in train mode regardless, as in the reference")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip extra.dynamic_quadtree / extra.inference")
-    ap.add_argument("--pdl", type=int, default=1, help="programmatic dependent launch of the hot kernels (qmp_set_pdl); 0 = plain stream order")
+    ap.add_argument("--pdl", type=int, default=0, help="programmatic dependent launch of the hot kernels (qmp_set_pdl); 0 = plain stream order")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
+    ap.add_argument("--lanes", type=int, default=0, help="--mode infer: launch dates in flight per GPU (0 = by mesh size)")
     ap.add_argument("--pixel-mesh", action="store_true", help="--mode infer on the pixel-wise mesh (N = 47 200) instead of configs[4]'s")
     args = ap.parse_args()
     _claim_stdout()

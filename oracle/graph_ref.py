@@ -142,12 +142,52 @@ class LabelMap:
         return m
 
 
+def lane_tree_segment_sum(x, ptr):
+    """Segment sums of ``x`` [B, K, C] (segment v = rows ptr[v]:ptr[v+1]) in a DEFINED floating-point order, the one the
+    device kernel uses (csrc/pool.cu segment_sum_kernel): 32 partial sums per segment -- partial l adds the segment's rows
+    l, l + 32, l + 64, ... one after the other starting from 0 -- then the butterfly partial[l] += partial[l ^ off] for
+    off = 16, 8, 4, 2, 1; the result is partial[0].  (The reference sums through a dense GEMM whose order is unspecified.)"""
+    ptr = torch.as_tensor(ptr).long()
+    B, K, C = x.shape
+    N = ptr.numel() - 1
+    cnt = ptr[1:] - ptr[:-1]
+    out = torch.zeros(B, N, C, dtype=x.dtype)
+    if N == 0 or K == 0:
+        return out
+    one = cnt == 1
+    if bool(one.any()):                                  # a single row: 0 + x, every other partial is 0
+        out[:, one] = x[:, ptr[:-1][one]] + 0.0
+    multi = torch.nonzero(cnt > 1).squeeze(1)
+    if multi.numel() == 0:
+        return out
+    slot = torch.full((N,), -1, dtype=torch.long)
+    slot[multi] = torch.arange(multi.numel())
+    seg = torch.repeat_interleave(torch.arange(N), cnt)
+    rank = torch.arange(K) - ptr[seg]
+    keep = slot[seg] >= 0
+    rows, seg_m, lane, rnd = torch.nonzero(keep).squeeze(1), slot[seg[keep]], rank[keep] % 32, rank[keep] // 32
+    part = torch.zeros(B, multi.numel(), 32, C, dtype=x.dtype)
+    order = torch.argsort(rnd, stable=True)
+    rows, seg_m, lane, rnd = rows[order], seg_m[order], lane[order], rnd[order]
+    bounds = torch.searchsorted(rnd, torch.arange(int(rnd.max()) + 2))
+    for j in range(bounds.numel() - 1):                  # round j: every (segment, lane) pair appears at most once
+        a, b = int(bounds[j]), int(bounds[j + 1])
+        if a == b:
+            continue
+        part[:, seg_m[a:b], lane[a:b]] = part[:, seg_m[a:b], lane[a:b]] + x[:, rows[a:b]]
+    lanes = torch.arange(32)
+    for off in (16, 8, 4, 2, 1):
+        part = part + part[:, :, lanes ^ off]
+    out[:, multi] = part[:, :, 0]
+    return out
+
+
 def pool(img, mapping, n_pixels_per_node, mask=None):
     """Mean-pool pixels into nodes: [n,H,W,c] -> [n,N,c] (graph_functions.py:391-419).
 
     ``mapping is None`` is the pixel-wise shortcut ``img[:, ~mask, :]`` (:383-389).
-    The reference sums through a dense GEMM (order unspecified); here the sum runs in raster
-    order per node, then divides by the pixel count like the reference does.
+    The reference sums through a dense GEMM (order unspecified); here the sum over a node's pixels (raster order) runs
+    in the defined order of :func:`lane_tree_segment_sum`, then divides by the pixel count like the reference does.
     """
     assert img.ndim == 4, f"array should be 4-dimensional (n_samples, w, h, c); got {tuple(img.shape)}"
     n, h, w, c = img.shape
@@ -158,8 +198,11 @@ def pool(img, mapping, n_pixels_per_node, mask=None):
     flat = img.reshape(n, h * w, c)
     lab = mapping.labels
     idx = torch.nonzero(lab >= 0).squeeze(1)
-    out = torch.zeros(n, mapping.n_nodes, c, dtype=img.dtype)
-    out = out.index_add(1, lab[idx], flat[:, idx])
+    order = idx[torch.argsort(lab[idx], stable=True)]      # pixels of node 0 in raster order, then node 1, ...
+    cnt = torch.bincount(lab[idx], minlength=mapping.n_nodes)
+    ptr = torch.zeros(mapping.n_nodes + 1, dtype=torch.long)
+    ptr[1:] = torch.cumsum(cnt, 0)
+    out = lane_tree_segment_sum(flat[:, order], ptr)
     return out / n_pixels_per_node.to(img.dtype)[None, :, None]
 
 

@@ -24,7 +24,7 @@ SIGNATURES = {
     "qmp_quadtree_labels": "pppiiiidppppppppp p".replace(" ", ""),
     "qmp_mesh_pixels_from_rects": "piippp ipppp p".replace(" ", ""),
     "qmp_mesh_pixelwise": "pipppppppp p".replace(" ", ""),
-    "qmp_segment_sum": "piiipppipipp",
+    "qmp_segment_sum": "piiipppipiipp",
     "qmp_gather_by_label": "piiiippifpp",
     "qmp_adjacency_quadtree": "piippppppplppppp",
     "qmp_adjacency_pixelwise": "piippppppppp",
@@ -155,21 +155,40 @@ def _ptr(t):
     if t is None:
         return None
     if isinstance(t, torch.Tensor):
-        if not on_device(t):
+        if not t.is_cuda:
             raise QmpError("qmp_b200 kernels take CUDA tensors only (no CPU fallback)")
         return t.data_ptr()
     return t
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (the raw-handle accessors cost a fraction of a
+    microsecond; torch.cuda.current_stream() builds a Stream object per call, which an eager dynamic-mesh sample pays
+    ~3 000 times)."""
+    if _raw_stream is not None and _cur_device is not None:
+        return _raw_stream(_cur_device())
     return torch.cuda.current_stream().cuda_stream
+
+
+_Tensor = torch.Tensor
 
 
 def call(name, *args):
     """Invoke ``qmp_<name>`` on the current CUDA stream (appended as the last argument)."""
-    L = lib()
+    L = _lib if _lib is not None else lib()
     fn = getattr(L, name)
-    conv = [_ptr(a) if (isinstance(a, torch.Tensor) or a is None) else a for a in args]
+    conv = []
+    for a in args:
+        if isinstance(a, _Tensor):
+            if not a.is_cuda:
+                raise QmpError("qmp_b200 kernels take CUDA tensors only (no CPU fallback)")
+            conv.append(a.data_ptr())
+        else:
+            conv.append(a)
     CALL_COUNTS[name] = CALL_COUNTS.get(name, 0) + 1
     rc = fn(*conv, stream_ptr())
     if rc != 0:
@@ -186,7 +205,7 @@ def set_dropout_salt(t):
 
 
 def set_pdl(on):
-    """Programmatic dependent launch of the hot kernels on (default) / off; returns the previous setting (csrc/core.cu)."""
+    """Programmatic dependent launch of the hot kernels on / off (default off); returns the previous setting (csrc/core.cu)."""
     return bool(lib().qmp_set_pdl(1 if on else 0))
 
 

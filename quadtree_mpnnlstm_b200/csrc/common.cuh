@@ -62,7 +62,8 @@ __device__ __forceinline__ unsigned long long salted_seed(unsigned long long see
 //   * pdl_launch() (griddepcontrol.launch_dependents) comes AFTER the kernel's own pdl_wait(), so when a dependent starts, the
 //     kernel before its predecessor is complete: a prologue may read data that is two or more launches old (weight images,
 //     packed parameters, the dropout salt).
-// qmp_set_pdl(0) (or QMP_PDL=0) turns the launch attribute off: the same kernels then run fully serialised.
+// qmp_set_pdl(1) (or QMP_PDL=1) turns the launch attribute on; the default is off (core.cu: the captured training step
+// measured 1 % slower with it, a chain of one kernel 2.5 % faster): the same kernels then run in plain stream order.
 // The kernels that BUILD those step constants (weight packs and images) call after_producer(): the next launch_pdl() of the
 // process is then an ordinary stream-ordered launch, so a prologue never reads an image its direct predecessor wrote.
 bool pdl_enabled();

@@ -17,11 +17,11 @@ void set_error(const char* fmt, ...) {
 static const unsigned long long* g_salt = nullptr;
 const unsigned long long* dropout_salt() { return g_salt; }
 
-static int g_pdl = -1;      // -1: not decided yet (QMP_PDL, default on)
+static int g_pdl = -1;      // -1: not decided yet (QMP_PDL; default OFF: measured below)
 bool pdl_enabled() {
     if (g_pdl < 0) {
         const char* e = getenv("QMP_PDL");
-        g_pdl = e ? (atoi(e) != 0) : 1;
+        g_pdl = e ? (atoi(e) != 0) : 0;
     }
     return g_pdl != 0;
 }
@@ -127,8 +127,10 @@ QMP_API int qmp_exclusive_scan_i32(const int* in, int* out, int n, int* total, i
 // a captured CUDA graph (whose kernel arguments are frozen) resample its dropout masks every replay (the reference resamples
 // per call: torch.nn.functional.dropout in PyG TransformerConv.message, nn.Dropout in model/seq2seq.py:169).  Process-wide
 // host state, read at launch time; returns 0.
-// Programmatic dependent launch of the hot kernels (common.cuh, launch_pdl): on = 1 (default; the prologue of a kernel overlaps
-// the tail of its predecessor in the stream / captured graph), off = 0 (plain stream order; what per-kernel timing wants).
+// Programmatic dependent launch of the hot kernels (common.cuh, launch_pdl): on = 1 (the prologue of a kernel overlaps the tail
+// of its predecessor in the stream / captured graph), off = 0 (default: plain stream order).  Measured on B200
+// (profiles/r03_pdl.txt): a captured chain of decoder-cell forward launches runs 51.2 -> 49.9 us per launch with it, the
+// whole 10 + 90-frame training step 40.0 -> 40.5 ms (two A/B runs, either order): the default stays off.
 // Process-wide host state, read at launch time; returns the previous setting.
 QMP_API int qmp_set_pdl(int on) {
     const int prev = qmp::pdl_enabled() ? 1 : 0;

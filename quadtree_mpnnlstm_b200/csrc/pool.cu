@@ -7,8 +7,8 @@
 //   pool   : out[b, v, c] = (sum over the node's pixels in raster order of img[b, p, c]) / npix[v]
 //   unpool : img[b, p, c] = labels[p] >= 0 ? data[b, labels[p], c] : fill
 // The backward of one is the other (with / without the division), so two kernels serve all four.
-// The raster-order sequential sum matches oracle/graph_ref.py:pool bit for bit, which keeps the
-// node positions -- and therefore the atan2 branch of the edge angle -- identical.
+// The summation order of the pool is DEFINED (segment_sum_kernel below) and oracle/graph_ref.py:pool follows it bit for bit,
+// which keeps the node positions -- and therefore the atan2 branch of the edge angle -- identical.
 #include "common.cuh"
 
 namespace qmp {
@@ -58,10 +58,57 @@ __global__ void pixelwise_fill_kernel(const int* __restrict__ keep, const int* _
     }
 }
 
-// out[b, v, c] over B x N x C threads; N read from device when n_nodes_dev != nullptr (capacity launch)
-__global__ void segment_sum_kernel(const float* __restrict__ img, int B, int P, int C, const int* __restrict__ pix_ptr,
-                                   const int* __restrict__ pix_idx, const float* __restrict__ npix, int n_cap,
-                                   const int* __restrict__ n_nodes_dev, int divide, float* __restrict__ out) {
+// out[b, v, c] = sum of img[b, p, c] over the node's pixels (/ npix when divide).  N is read from the device when
+// n_nodes_dev != nullptr (capacity launch of the graph build).
+//
+// Summation order (the definition oracle/graph_ref.py:lane_tree_segment_sum restates, so that node positions -- and with
+// them the edge attributes -- stay bit-identical): 32 partial sums, partial l = the node's pixels l, l + 32, l + 64, ...
+// (raster order) added one after the other starting from 0; then the butterfly partial[l] += partial[l ^ off] for
+// off = 16, 8, 4, 2, 1.  One warp per (frame, node): a 64 x 64 leaf is 128 rounds of coalesced loads instead of 4096
+// dependent additions by one thread (693 us of the 977 us a mesh build at the ice grid took with a thread per output).
+constexpr int SEG_CH = 8;          // channels per pass
+__global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restrict__ img, int B, int P, int C,
+                                                          const int* __restrict__ pix_ptr, const int* __restrict__ pix_idx,
+                                                          const float* __restrict__ npix, int n_cap,
+                                                          const int* __restrict__ n_nodes_dev, int divide,
+                                                          float* __restrict__ out) {
+    const int n_nodes = n_nodes_dev ? min(*n_nodes_dev, n_cap) : n_cap;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = warp; w < (long long)B * n_nodes; w += nwarps) {
+        const int b = (int)(w / n_nodes), v = (int)(w - (long long)b * n_nodes);
+        const int a0 = pix_ptr[v], a1 = pix_ptr[v + 1];
+        const float* src = img + (size_t)b * P * C;
+        for (int c0 = 0; c0 < C; c0 += SEG_CH) {
+            const int cw = C - c0 < SEG_CH ? C - c0 : SEG_CH;
+            float acc[SEG_CH];
+#pragma unroll
+            for (int c = 0; c < SEG_CH; ++c) acc[c] = 0.f;
+            for (int k = a0 + lane; k < a1; k += 32) {
+                const float* px = src + (size_t)pix_idx[k] * C + c0;
+#pragma unroll
+                for (int c = 0; c < SEG_CH; ++c)
+                    if (c < cw) acc[c] += px[c];
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+                for (int c = 0; c < SEG_CH; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], off);
+            }
+            float mine = 0.f;
+#pragma unroll
+            for (int c = 0; c < SEG_CH; ++c)
+                if (lane == c) mine = acc[c];
+            if (lane < cw) out[((size_t)b * n_cap + v) * C + c0 + lane] = divide ? mine / npix[v] : mine;
+        }
+    }
+}
+
+// The same for a mesh whose nodes all own exactly ONE pixel (every pixel-wise mesh): 0 + x and 31 zero partials give x, so a
+// thread per output computes the identical value.
+__global__ void segment_single_kernel(const float* __restrict__ img, int B, int P, int C, const int* __restrict__ pix_ptr,
+                                      const int* __restrict__ pix_idx, const float* __restrict__ npix, int n_cap,
+                                      const int* __restrict__ n_nodes_dev, int divide, float* __restrict__ out) {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int n_nodes = n_nodes_dev ? *n_nodes_dev : n_cap;
     if (t >= (long long)B * n_cap * C) return;
@@ -69,10 +116,7 @@ __global__ void segment_sum_kernel(const float* __restrict__ img, int B, int P, 
     const int v = (int)((t / C) % n_cap);
     const int b = (int)(t / ((long long)C * n_cap));
     if (v >= n_nodes) return;
-    const float* src = img + (size_t)b * P * C + c;
-    float s = 0.f;
-    const int k1 = pix_ptr[v + 1];
-    for (int k = pix_ptr[v]; k < k1; ++k) s += src[(size_t)pix_idx[k] * C];
+    const float s = 0.f + img[((size_t)b * P + pix_idx[pix_ptr[v]]) * C + c];
     out[((size_t)b * n_cap + v) * C + c] = divide ? s / npix[v] : s;
 }
 
@@ -127,13 +171,21 @@ QMP_API int qmp_mesh_pixelwise(const uint8_t* mask, int P, int* labels, int* pix
     return 0;
 }
 
-// pool forward (divide=1) / unpool backward (divide=0).  img [B,P,C] -> out [B,n_cap,C].
+// pool forward (divide=1) / unpool backward (divide=0).  img [B,P,C] -> out [B,n_cap,C].  single = 1: the caller guarantees
+// that every node owns exactly one pixel (a pixel-wise mesh) -- same values, a thread per output instead of a warp per node.
 QMP_API int qmp_segment_sum(const float* img, int B, int P, int C, const int* pix_ptr, const int* pix_idx,
-                            const float* npix, int n_cap, const int* n_nodes_dev, int divide, float* out, void* stream) {
+                            const float* npix, int n_cap, const int* n_nodes_dev, int divide, int single, float* out, void* stream) {
     const long long tot = (long long)B * n_cap * C;
     if (tot == 0) return 0;
-    segment_sum_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(img, B, P, C, pix_ptr, pix_idx, npix, n_cap,
-                                                                         n_nodes_dev, divide, out);
+    if (single) {
+        segment_single_kernel<<<cdiv(tot, 256), 256, 0, (cudaStream_t)stream>>>(img, B, P, C, pix_ptr, pix_idx, npix, n_cap,
+                                                                                n_nodes_dev, divide, out);
+    } else {
+        // one warp per (frame, node), grid-stride (the node count of a capacity launch lives on the device)
+        const long long items = (long long)B * n_cap;
+        const int grid = (int)(items < 148 * 16 * 8 ? (items + 7) / 8 : 148 * 16);
+        segment_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, B, P, C, pix_ptr, pix_idx, npix, n_cap, n_nodes_dev, divide, out);
+    }
     QMP_LAUNCH_CHECK("qmp_segment_sum");
     return 0;
 }

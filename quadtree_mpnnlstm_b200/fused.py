@@ -261,6 +261,11 @@ class _GradAccum(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad):
         h = ctx.holder
+        if h.handed and grad.data_ptr() != h.acc.data_ptr():
+            # the consumers kept adding into h.acc after the first one handed it over: that is only the complete sum while
+            # autograd passes the handed tensor through by reference (no copy, no second non-None gradient for the pack)
+            raise RuntimeError("fused._GradAccum: autograd handed over a copy of the shared accumulator; the in-place "
+                               "accumulation of the pack gradients is not valid with this PyTorch build")
         out = grad.clone()
         h.acc.zero_()                 # ready for another backward pass over the same graph
         h.handed = False

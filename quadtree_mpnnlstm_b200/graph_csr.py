@@ -73,7 +73,9 @@ def get_csr(edge_index, edge_attr, n_nodes, validate=True):
     if hit is not None and hit._keepalive[0] is edge_index and hit._keepalive[1] is edge_attr:
         _cache.move_to_end(key)
         return hit
-    csr = GraphCSR(edge_index, edge_attr, n_nodes, validate=validate)
+    # an edge_index this package's own graph build emitted needs no bounds check (a host read-back per mesh: with a mesh per
+    # forecast step that is one pipeline drain per frame)
+    csr = GraphCSR(edge_index, edge_attr, n_nodes, validate=validate and not getattr(edge_index, "_qmp_trusted", False))
     _cache[key] = csr                    # a stale entry under the same key (same storage, new tensor object) is replaced
     _cache.move_to_end(key)
     while len(_cache) > _MAX:

@@ -168,7 +168,7 @@ class _Pool(torch.autograd.Function):
         B, H, W, C = img.shape
         img = img.contiguous()
         out = torch.empty(B, mesh.n_nodes, C, dtype=torch.float32, device=img.device)
-        _lib.call("qmp_segment_sum", img, B, H * W, C, mesh.pix_ptr, mesh.pix_idx, mesh.npix, mesh.n_nodes, None, 1, out)
+        _lib.call("qmp_segment_sum", img, B, H * W, C, mesh.pix_ptr, mesh.pix_idx, mesh.npix, mesh.n_nodes, None, 1, int(mesh.kind == "pixelwise"), out)
         ctx.mesh, ctx.shape = mesh, (B, H, W, C)
         return out
 
@@ -200,7 +200,7 @@ class _Unpool(torch.autograd.Function):
         H, W = mesh.image_shape
         g = g.contiguous()
         dd = torch.empty(B, N, C, dtype=torch.float32, device=g.device)
-        _lib.call("qmp_segment_sum", g, B, H * W, C, mesh.pix_ptr, mesh.pix_idx, mesh.npix, N, None, 0, dd)
+        _lib.call("qmp_segment_sum", g, B, H * W, C, mesh.pix_ptr, mesh.pix_idx, mesh.npix, N, None, 0, int(mesh.kind == "pixelwise"), dd)
         return dd, None, None
 
 
@@ -370,7 +370,7 @@ def image_to_graph(img, thresh=0.05, max_grid_size=64, mask=None, high_interest_
 
     # pooled node features with node capacity P (true N still on the device)
     data_cap = torch.empty(n, P, c, **f32)
-    _lib.call("qmp_segment_sum", img.detach(), n, P, c, pix_ptr, pix_idx, npix, P, counts[0:], 1, data_cap)
+    _lib.call("qmp_segment_sum", img.detach(), n, P, c, pix_ptr, pix_idx, npix, P, counts[0:], 1, 0, data_cap)
 
     e_cap = 4 * P
     ei, s32, d32 = _edge_buffers(e_cap, dev)
@@ -395,7 +395,9 @@ def image_to_graph(img, thresh=0.05, max_grid_size=64, mask=None, high_interest_
         data = data_cap[:, :N] if n == 1 else data_cap[:, :N].contiguous()
     cell_sizes = (mesh.npix / ((max_grid_size / 2) ** 2)).reshape(1, N, 1).expand(n, N, 1)   # :665-666
     data = torch.cat([data, cell_sizes], -1)
-    return dict(edge_index=ei[:, :E].contiguous(), edge_attrs=edge_attrs[:E].contiguous(), data=data,
+    edge_index = ei[:, :E].contiguous()
+    edge_index._qmp_trusted = True          # emitted by qmp_adjacency_quadtree: endpoints are in [0, N) by construction
+    return dict(edge_index=edge_index, edge_attrs=edge_attrs[:E].contiguous(), data=data,
                 graph_nodes=np.arange(N), mapping=mesh, n_pixels_per_node=mesh.npix, labels=labels.view(h, w))
 
 

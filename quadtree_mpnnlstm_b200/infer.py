@@ -7,7 +7,10 @@ ice_inf.py:60-130: per launch date forward -> unflatten -> stack to [n_dates, T_
   an eager Python loop is pure launch latency.  Dynamic-quadtree rollouts (data-dependent N, E) stay eager.
 * ``predict_sharded``: launch dates are independent, so they are dealt round-robin to the ranks (one process per GPU) with NO
   collective on the data path; short ranks are padded so that every rank joins the single ``all_gather`` at the end, and the
-  padding is trimmed afterwards -- every date is forecast."""
+  padding is trimmed afterwards -- every date is forecast.
+* ``RolloutPool``: several ``Rollout`` lanes (own captured graph, static buffers and stream each) replayed CONCURRENTLY.  On
+  the ice_inf.py mesh (N = 4 066) a rollout's persistent kernels are 32 CTAs on a 148-SM part and every launch is latency-
+  bound; independent launch dates on different streams fill the other SMs."""
 from __future__ import annotations
 
 import torch
@@ -84,13 +87,84 @@ class Rollout:
         return self.out
 
 
+def default_lanes(n_nodes, n_sm=148, most=4):
+    """How many rollouts fit side by side: the persistent kernels run one CTA per 128-node tile and SM."""
+    tiles = max(1, -(-int(n_nodes) // 128))
+    return max(1, min(most, n_sm // tiles))
+
+
+class RolloutPool:
+    """``lanes`` captured rollouts of one model replayed on ``lanes`` streams: launch date i runs on lane i % lanes.  Every
+    lane owns its graph, its static input / output buffers and its dropout salt (offset per lane, so that two lanes never
+    draw the same attention-dropout masks); the lanes share the model's parameters, the mesh and its CSR, which a replay
+    only reads."""
+
+    def __init__(self, model, mask, graph_structure=None, high_interest_region=None, remesh_every=1, lanes=None, warmup_eager=2):
+        if not _static_mesh(model, graph_structure):
+            raise ValueError("RolloutPool needs a static mesh (thresh = -inf or a preset graph_structure): a dynamic-quadtree "
+                             "rollout cannot be captured")
+        if lanes is None:
+            lanes = default_lanes(graph_structure["mapping"].n_nodes) if graph_structure is not None else 1
+        self.lanes = [Rollout(model, mask, graph_structure, high_interest_region, remesh_every, True, warmup_eager)
+                      for _ in range(max(1, int(lanes)))]
+        for k, ro in enumerate(self.lanes):
+            if ro.salt is not None:
+                ro.salt.fill_(k << 32)
+        self.streams = None
+
+    @property
+    def graph(self):
+        return self.lanes[0].graph
+
+    @property
+    def launches_per_replay(self):
+        return self.lanes[0].launches_per_replay
+
+    def warm(self, x, cl):
+        """Eager warm-ups and the capture of every lane (one after the other, on the calling stream)."""
+        for ro in self.lanes:
+            while ro.graph is None:
+                ro(x, cl)
+        torch.cuda.current_stream().synchronize()
+
+    @torch.no_grad()
+    def predict_many(self, xs, concat_layers, out=None):
+        if self.streams is None:
+            self.streams = [torch.cuda.Stream() for _ in self.lanes]
+        main = torch.cuda.current_stream()
+        for i, (x, cl) in enumerate(zip(xs, concat_layers)):
+            k = i % len(self.lanes)
+            ro, st = self.lanes[k], self.streams[k]
+            if ro.graph is None:                    # still warming up / capturing: on the calling stream, nothing in flight
+                for s2 in self.streams:
+                    main.wait_stream(s2)
+                y = ro(x, cl)
+                if out is None:
+                    out = torch.empty((len(xs),) + tuple(y.shape), dtype=y.dtype, device=y.device)
+                out[i].copy_(y)
+                continue
+            if out is None:
+                out = torch.empty((len(xs),) + tuple(ro.out.shape), dtype=ro.out.dtype, device=ro.out.device)
+            st.wait_stream(main)                    # x, cl (and `out`) were produced on the calling stream
+            with torch.cuda.stream(st):
+                y = ro(x, cl)                       # static-buffer copies + the replay, in this lane's stream order
+                out[i].copy_(y, non_blocking=True)
+            x.record_stream(st)
+            cl.record_stream(st)
+        for st in self.streams:
+            main.wait_stream(st)
+        return out
+
+
 @torch.no_grad()
 def predict(model, xs, concat_layers, mask, graph_structure=None, high_interest_region=None, remesh_every=1,
             use_cuda_graph=False, rollout=None):
     """xs: list of [T_in, H, W, c] device tensors (one per launch date), concat_layers: matching list of
-    [T_out, H, W, 1].  Returns [n, T_out, H, W, 1] on the device."""
+    [T_out, H, W, 1].  Returns [n, T_out, H, W, 1] on the device.  ``rollout``: a Rollout or a RolloutPool to reuse."""
     if not xs:
         return None
+    if isinstance(rollout, RolloutPool):
+        return rollout.predict_many(xs, concat_layers)
     ro = rollout or Rollout(model, mask, graph_structure, high_interest_region, remesh_every, use_cuda_graph)
     out = None
     for i, (x, cl) in enumerate(zip(xs, concat_layers)):

@@ -100,13 +100,13 @@ def qmp_mesh_pixelwise(mask, P, labels, pix_ptr, pix_idx, npix, n_nodes, keep, r
     flat(npix, N).fill_(1.0)
 
 
-def qmp_segment_sum(img, B, P, C, pix_ptr, pix_idx, npix, n_cap, n_nodes_dev, divide, out):
+def qmp_segment_sum(img, B, P, C, pix_ptr, pix_idx, npix, n_cap, n_nodes_dev, divide, single, out):
+    from oracle.graph_ref import lane_tree_segment_sum
     N = int(flat(n_nodes_dev, 1)[0]) if n_nodes_dev is not None else n_cap
     im = flat(img, B * P * C).view(B, P, C)
     ptr = flat(pix_ptr, N + 1).long()
     idx = flat(pix_idx, int(ptr[N])).long()
-    seg = torch.repeat_interleave(torch.arange(N), ptr[1:] - ptr[:-1])
-    res = torch.zeros(B, N, C).index_add(1, seg, im[:, idx])
+    res = lane_tree_segment_sum(im[:, idx], ptr)          # the defined summation order of csrc/pool.cu
     if divide:
         res = res / flat(npix, N)[None, :, None]
     flat(out, B * n_cap * C).view(B, n_cap, C)[:, :N] = res
