@@ -25,6 +25,8 @@ SIGNATURES = {
     "qmp_mesh_pixels_from_rects": "piippp ipppp p".replace(" ", ""),
     "qmp_mesh_pixelwise": "pipppppppp p".replace(" ", ""),
     "qmp_segment_sum": "piiipppipiipp",
+    "qmp_quadtree_graph": "piiiipppiidfippp",
+    "qmp_quadtree_graph_export": "piiiiiiiipppp",
     "qmp_gather_by_label": "piiiippifpp",
     "qmp_adjacency_quadtree": "piippppppplppppp",
     "qmp_adjacency_pixelwise": "piippppppppp",
@@ -81,7 +83,7 @@ SIGNATURES = {
 # kernels launched by one call of each entry point (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {
     "qmp_exclusive_scan_i32": 3, "qmp_frame_max_pad": 1, "qmp_quadtree_labels": 3, "qmp_mesh_pixels_from_rects": 5,
-    "qmp_mesh_pixelwise": 5, "qmp_segment_sum": 1, "qmp_gather_by_label": 1, "qmp_adjacency_quadtree": 8,
+    "qmp_mesh_pixelwise": 5, "qmp_segment_sum": 1, "qmp_quadtree_graph": 1, "qmp_quadtree_graph_export": 1, "qmp_gather_by_label": 1, "qmp_adjacency_quadtree": 8,
     "qmp_adjacency_pixelwise": 5, "qmp_edge_attrs": 1, "qmp_add_positional_encoding": 1,
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,
@@ -117,6 +119,8 @@ def lib():
         L.qmp_version.restype = _I
         L.qmp_quadtree_pyramid_cells.restype = _L
         L.qmp_quadtree_pyramid_cells.argtypes = [_I, _I, _I]
+        L.qmp_quadtree_graph_scratch_bytes.restype = _L
+        L.qmp_quadtree_graph_scratch_bytes.argtypes = [_I, _I, _I, _I, _I]
         L.qmp_set_tensor_cores.restype = _I
         L.qmp_set_tensor_cores.argtypes = [_I]
         L.qmp_set_fused_paired.restype = _I
@@ -210,4 +214,4 @@ def set_pdl(on):
 
 
 def exported_symbols():
-    return ["qmp_set_dropout_salt", "qmp_set_pdl", "qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes", "qmp_head_bwd_image_bytes"] + list(SIGNATURES)
+    return ["qmp_set_dropout_salt", "qmp_set_pdl", "qmp_last_error", "qmp_version", "qmp_quadtree_pyramid_cells", "qmp_quadtree_graph_scratch_bytes", "qmp_set_tensor_cores", "qmp_fused_tc_image_bytes", "qmp_set_fused_paired", "qmp_fused_cell_image_bytes", "qmp_fused_cell_bwd_image_bytes", "qmp_head_bwd_image_bytes"] + list(SIGNATURES)

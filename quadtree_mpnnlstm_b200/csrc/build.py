@@ -27,6 +27,9 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_frame_max_pad": "model/graph_functions.py:632 (max over frames of channel 0) and :190 (edge pad)",
     "qmp_quadtree_labels": "model/graph_functions.py:145-259 quadtree_decompose",
     "qmp_quadtree_pyramid_cells": "(scratch sizing for qmp_quadtree_labels)",
+    "qmp_quadtree_graph": "model/graph_functions.py:590-681 image_to_graph (quadtree_decompose :145-259, get_mapping :555-587, flatten :391-419, get_adj :261-345, dist_angle :358-370) + PyG's per-edge scatter (the CSR) -- one cooperative launch",
+    "qmp_quadtree_graph_export": "(copies the compacted result of qmp_quadtree_graph out of its arena into exact-size buffers)",
+    "qmp_quadtree_graph_scratch_bytes": "(arena sizing for qmp_quadtree_graph)",
     "qmp_mesh_pixels_from_rects": "model/graph_functions.py:555-587 get_mapping (+ :649 to_dense)",
     "qmp_mesh_pixelwise": "model/graph_functions.py:511-525 pixel-wise labels / graph_nodes / n_pixels_per_node",
     "qmp_segment_sum": "model/graph_functions.py:391-419 flatten (and the backward of unflatten)",

@@ -44,6 +44,20 @@ class GraphCSR:
         self._norm = {}
         self._keepalive = (edge_index, edge_attr)
 
+    @classmethod
+    def from_parts(cls, edge_index, edge_attr, n_nodes, src, dst, in_ptr, in_src, in_eid, out_ptr, out_dst, out_kin, edge_attr_in):
+        """A CSR the graph build already produced on the device (qmp_quadtree_graph): no kernels, no validation read-back."""
+        self = cls.__new__(cls)
+        self.n_nodes, self.n_edges, self.device = int(n_nodes), int(edge_index.shape[1]), edge_index.device
+        self.src, self.dst = src, dst
+        self.in_ptr, self.in_src, self.in_eid = in_ptr, in_src, in_eid
+        self.out_ptr, self.out_dst, self.out_kin = out_ptr, out_dst, out_kin
+        self.edge_attr_in = edge_attr_in
+        self.edge_dim = 0 if edge_attr is None else (1 if edge_attr.dim() == 1 else edge_attr.shape[1])
+        self._norm = {}
+        self._keepalive = (edge_index, edge_attr)
+        return self
+
     def norm(self, mode):
         """Per-edge normalisation (in-CSR order) for 'gcn' (mode 0) or 'cheb' (mode 1); cached per graph."""
         val = self._norm.get(mode)
@@ -64,11 +78,26 @@ _cache = collections.OrderedDict()       # least recently used first
 _MAX = 32
 
 
+def _key(edge_index, edge_attr, n_nodes):
+    return (edge_index.data_ptr(), tuple(edge_index.shape), int(n_nodes), edge_index._version,
+            None if edge_attr is None else (edge_attr.data_ptr(), tuple(edge_attr.shape), edge_attr._version))
+
+
+def register(csr):
+    """Put a prebuilt GraphCSR where get_csr() finds it for its (edge_index, edge_attr) tensors."""
+    ei, ea = csr._keepalive
+    key = _key(ei, ea, csr.n_nodes)
+    _cache[key] = csr
+    _cache.move_to_end(key)
+    while len(_cache) > _MAX:
+        _cache.popitem(last=False)
+    return csr
+
+
 def get_csr(edge_index, edge_attr, n_nodes, validate=True):
     if isinstance(edge_index, GraphCSR):
         return edge_index
-    key = (edge_index.data_ptr(), tuple(edge_index.shape), int(n_nodes), edge_index._version,
-           None if edge_attr is None else (edge_attr.data_ptr(), tuple(edge_attr.shape), edge_attr._version))
+    key = _key(edge_index, edge_attr, n_nodes)
     hit = _cache.get(key)
     if hit is not None and hit._keepalive[0] is edge_index and hit._keepalive[1] is edge_attr:
         _cache.move_to_end(key)

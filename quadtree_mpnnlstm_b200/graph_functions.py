@@ -10,6 +10,8 @@ accepted and converted once.  There is no CPU path: every function here needs a 
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -324,6 +326,71 @@ def image_to_graph_pixelwise(img, mask=None, use_edge_attrs=True, resolution=0.2
                 mapping=None, n_pixels_per_node=mesh.npix, labels=mesh.labels.view(h, w), mesh=mesh)
 
 
+ONE_LAUNCH_BUILD = os.environ.get("QMP_ONE_LAUNCH_BUILD", "1") != "0"     # 0: the per-kernel entry points (cross-check path)
+_gb_arenas = {}
+
+
+def _gb_arena(h, w, S, T, C, dev):
+    """Arena of qmp_quadtree_graph (scratch + the results at capacity) and its pinned count buffer, reused per shape and stream."""
+    key = (h, w, S, T, C, dev.index, _lib.stream_ptr())
+    hit = _gb_arenas.get(key)
+    if hit is None:
+        nbytes = int(_lib.lib().qmp_quadtree_graph_scratch_bytes(h, w, S, T, C))
+        if len(_gb_arenas) > 8:
+            _gb_arenas.clear()
+        host = torch.zeros(4, dtype=torch.int32)
+        hit = (torch.empty(nbytes, dtype=torch.uint8, device=dev), host.pin_memory() if torch.cuda.is_available() else host)
+        _gb_arenas[key] = hit
+    return hit
+
+
+def _quadtree_graph_one_launch(img, crit, m8, h8, S, cond, thresh, use_edge_attrs, resolution, max_grid_size):
+    """image_to_graph's quadtree branch on csrc/graph_build.cu: one cooperative launch builds labels, pixel lists, pooled node
+    features, edges, edge attributes and both CSRs inside an arena; one read-back of (N, E, NaN count); one launch copies the
+    compacted result into exact-size buffers.  The CSR is registered with graph_csr, so the conv modules never rebuild it."""
+    from . import graph_csr
+    n, h, w, c = img.shape
+    dev = img.device
+    P = h * w
+    two = 1 if use_edge_attrs else 0
+    arena, counts_host = _gb_arena(h, w, S, n, c, dev)
+    _lib.call("qmp_quadtree_graph", img.detach(), n, h, w, c, crit, m8, h8, S, cond, float(thresh), float(resolution), two,
+              counts_host.data_ptr(), arena)
+    N, E, nans = counts_host.tolist()[:3]
+    if nans:
+        raise ValueError(f'Found NaNs in image data {nans} / {img.numel()}')
+    r4 = lambda v: (v + 3) & ~3
+    wd = 2 if two else 1
+    isz = (P, N + 1, P, E, E, N + 1, E, E, N + 1, E, E)
+    fsz = (N, n * N * (c + 1), E * wd, E * wd)
+    ipack = torch.empty(sum(r4(v) for v in isz), dtype=torch.int32, device=dev)
+    fpack = torch.empty(sum(r4(v) for v in fsz), dtype=torch.float32, device=dev)
+    edge_index = torch.empty(2, E, dtype=torch.int64, device=dev)
+    _lib.call("qmp_quadtree_graph_export", arena, h, w, S, n, c, two, N, E, ipack, fpack, edge_index)
+    iv, off = [], 0
+    for v in isz:
+        iv.append(ipack[off:off + v])
+        off += r4(v)
+    labels, pix_ptr, pix_idx, src32, dst32, in_ptr, in_src, in_eid, out_ptr, out_dst, out_kin = iv
+    fv, off = [], 0
+    for v in fsz:
+        fv.append(fpack[off:off + v])
+        off += r4(v)
+    npix, data, edge_attrs, edge_attr_in = fv
+    data = data.view(n, N, c + 1)
+    if two:
+        edge_attrs, edge_attr_in = edge_attrs.view(E, 2), edge_attr_in.view(E, 2)
+    mesh = Mesh(labels, N, npix, pix_ptr, pix_idx, (h, w), "quadtree")
+    if img.requires_grad:            # differentiable pooling (seq2seq.py:440-476 regrids state)
+        cell_sizes = (npix / ((max_grid_size / 2) ** 2)).reshape(1, N, 1).expand(n, N, 1)   # :665-666
+        data = torch.cat([_Pool.apply(img, mesh), cell_sizes], -1)
+    edge_index._qmp_trusted = True
+    graph_csr.register(graph_csr.GraphCSR.from_parts(edge_index, edge_attrs, N, src32, dst32, in_ptr, in_src, in_eid, out_ptr, out_dst,
+                                                     out_kin, edge_attr_in))
+    return dict(edge_index=edge_index, edge_attrs=edge_attrs, data=data, graph_nodes=np.arange(N), mapping=mesh,
+                n_pixels_per_node=npix, labels=labels.view(h, w))
+
+
 def image_to_graph(img, thresh=0.05, max_grid_size=64, mask=None, high_interest_region=None, transform_func=None,
                    condition='max_larger_than', use_edge_attrs=True, resolution=0.25):
     """Convert an image (n_samples, height, width, channels) to its graph representation using quadtree
@@ -355,6 +422,9 @@ def image_to_graph(img, thresh=0.05, max_grid_size=64, mask=None, high_interest_
     crit = _apply_transform(transform_func, crit)
 
     m8, h8 = _mask_u8(mask, dev), _mask_u8(high_interest_region, dev)
+    if S <= 64 and c >= 2 and ONE_LAUNCH_BUILD:
+        return _quadtree_graph_one_launch(img, crit, m8, h8, S, CONDITIONS.index(condition), thresh, use_edge_attrs, resolution,
+                                          max_grid_size)
     cells = _lib.lib().qmp_quadtree_pyramid_cells(h, w, S)
     labels, rect, npix = torch.empty(P, **i32), torch.empty(P, 4, **i32), torch.empty(P, **f32)
     counts = torch.zeros(2, **i32)                       # [n_nodes, n_edges]

@@ -87,10 +87,12 @@ class Rollout:
         return self.out
 
 
-def default_lanes(n_nodes, n_sm=148, most=4):
-    """How many rollouts fit side by side: the persistent kernels run one CTA per 128-node tile and SM."""
+def default_lanes(n_nodes, n_sm=148, most=8):
+    """How many rollouts to keep in flight: the persistent kernels run one CTA per 128-node tile and SM, and a second set of
+    lanes fills the launch gaps and tails of the first (measured on the N = 4 066 mesh, end to end: 2 lanes 203, 4 lanes 324,
+    8 lanes 442, 12 lanes 453 launch dates/s; one lane 46)."""
     tiles = max(1, -(-int(n_nodes) // 128))
-    return max(1, min(most, n_sm // tiles))
+    return max(1, min(most, 2 * n_sm // tiles))
 
 
 class RolloutPool:

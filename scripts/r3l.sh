@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_parity_graph.py tests/test_golden.py tests/test_rollout_pool.py -q -m gpu -p no:cacheprovider --tb=short -x > gpurun_out/r3l_pytest.log 2>&1; echo "pytest rc=$?"; tail -25 gpurun_out/r3l_pytest.log
+timeout 250 python scripts/build_profile.py > gpurun_out/r3l_build_profile.log 2>&1; head -4 gpurun_out/r3l_build_profile.log

@@ -174,6 +174,53 @@ def qmp_csr_from_edge_index(ei, E, N, src32, dst32, in_ptr, in_src, in_eid, out_
     flat(out_kin, E).copy_(kin[order_out].int())
 
 
+_GB = {}      # arena pointer -> the compacted result of the last emulated qmp_quadtree_graph
+
+
+def qmp_quadtree_graph(img, T, n, m, C, crit, mask, hir, S, cond, thresh, resolution, two_cols, counts_host, arena):
+    """csrc/graph_build.cu: the phases of the one-launch build, composed from the per-kernel emulations above."""
+    import ctypes
+    P = n * m
+    i32 = lambda k: torch.zeros(k, dtype=torch.int32)
+    labels, rect, npix, nn = i32(P), i32(4 * P), torch.zeros(P), i32(1)
+    qmp_quadtree_labels(crit, mask, hir, n, m, S, cond, thresh, labels, rect, npix, nn, None, None, None, None, None)
+    N = int(nn[0])
+    pix_ptr, pix_idx = i32(P + 1), i32(P)
+    qmp_mesh_pixels_from_rects(labels, n, m, rect, npix, nn, P, pix_ptr, pix_idx, None, None)
+    data_cap = torch.zeros(T, P, C)
+    qmp_segment_sum(img, T, P, C, pix_ptr, pix_idx, npix, P, nn, 1, 0, data_cap)
+    e_cap = 4 * P
+    ei, s32, d32, ne = torch.zeros(2, e_cap, dtype=torch.int64), i32(e_cap), i32(e_cap), i32(1)
+    qmp_adjacency_quadtree(labels, n, m, ei[0], ei[1], s32, d32, ne, None, None, 0, None, None, None, None)
+    E = int(ne[0])
+    attrs = torch.zeros(e_cap, 2) if two_cols else torch.zeros(e_cap)
+    qmp_edge_attrs(s32, d32, e_cap, ne, data_cap[0, :, C - 2:], data_cap[0, :, C - 1:], C, m, n, resolution, two_cols, attrs)
+    edge_index = ei[:, :E].contiguous()
+    in_ptr, out_ptr = i32(N + 1), i32(N + 1)
+    in_src, in_eid, out_dst, out_kin = i32(E), i32(E), i32(E), i32(E)
+    qmp_csr_from_edge_index(edge_index, E, N, i32(E), i32(E), in_ptr, in_src, in_eid, out_ptr, out_dst, out_kin, None, None, None, None,
+                            None)
+    attrs = attrs[:E].contiguous()
+    data = torch.cat([data_cap[:, :N], (npix[:N] / ((S / 2) ** 2)).reshape(1, N, 1).expand(T, N, 1)], -1).contiguous()
+    im = flat(img, T * P * C)
+    _GB[arena.data_ptr()] = dict(
+        ints=[labels, pix_ptr[:N + 1], pix_idx, s32[:E], d32[:E], in_ptr, in_src, in_eid, out_ptr, out_dst, out_kin],
+        floats=[npix[:N], data.reshape(-1), attrs.reshape(-1), attrs[in_eid.long()].reshape(-1)], edge_index=edge_index)
+    host = (ctypes.c_int * 4).from_address(int(counts_host))
+    host[0], host[1], host[2], host[3] = N, E, int(torch.isnan(im).sum()), 0
+
+
+def qmp_quadtree_graph_export(arena, n, m, S, T, C, two_cols, N, E, ipack, fpack, edge_index):
+    res = _GB[arena.data_ptr()]
+    r4 = lambda v: (v + 3) & ~3
+    for pack, segs in ((ipack, res["ints"]), (fpack, res["floats"])):
+        off = 0
+        for seg in segs:
+            flat(pack)[off:off + seg.numel()].copy_(seg)
+            off += r4(seg.numel())
+    flat(edge_index, 2 * E).copy_(res["edge_index"].reshape(-1))
+
+
 def qmp_gather_rows(inp, idx, n, width, out):
     flat(out, n * width).view(n, width).copy_(flat(inp, n * width).view(n, width)[flat(idx, n).long()])
 
@@ -982,6 +1029,8 @@ class Emulated:
         from quadtree_mpnnlstm_b200 import _lib, graph_functions as gf
         self._lib, self._gf = _lib, gf
         self._saved = (_lib.call, gf._device, _lib.lib)
+        self._stream_ptr = _lib.stream_ptr
+        _lib.stream_ptr = lambda: 0
         table = globals()
 
         def call(name, *args):
@@ -992,6 +1041,10 @@ class Emulated:
             @staticmethod
             def qmp_quadtree_pyramid_cells(n, m, s):
                 return 1
+
+            @staticmethod
+            def qmp_quadtree_graph_scratch_bytes(n, m, s, t, c):
+                return 16
 
             @staticmethod
             def qmp_fused_cell_image_bytes():
@@ -1014,5 +1067,6 @@ class Emulated:
 
     def __exit__(self, *exc):
         self._lib.call, self._gf._device, self._lib.lib = self._saved
+        self._lib.stream_ptr = self._stream_ptr
         torch.Tensor.is_cuda = self._is_cuda
         return False

@@ -152,3 +152,39 @@ def test_scan_kernel(be):
         ref = torch.cumsum(v.long(), 0) - v.long()
         assert torch.equal(out.long(), ref), n
         assert int(tot) == int(v.sum())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", [0, 1, 3, 4, 7, 8])
+def test_one_launch_build_matches_the_per_kernel_path(idx):
+    """csrc/graph_build.cu (one cooperative launch: mesh + pooled features + edges + both CSRs) against the per-kernel entry
+    points it replaces (quadtree.cu / pool.cu / edges.cu, then csr.cu from the emitted edge_index): every output bit for bit,
+    pixel lists and CSR arrays included."""
+    import quadtree_mpnnlstm_b200 as q
+    from quadtree_mpnnlstm_b200 import graph_csr, graph_functions as gf
+    case = CASES[idx]
+    H, W, S, thresh, cond, *_ = case
+    x, mask, hir, tf = _inputs(case, 300 + idx)
+    xg = q.add_positional_encoding(torch.from_numpy(x).cuda())
+    kw = dict(thresh=thresh, max_grid_size=S, mask=mask, high_interest_region=hir, transform_func=tf, condition=cond, use_edge_attrs=True)
+    assert gf.ONE_LAUNCH_BUILD
+    a = q.image_to_graph(xg, **kw)
+    csr_a = graph_csr.get_csr(a["edge_index"], a["edge_attrs"], a["data"].shape[1])
+    assert csr_a._keepalive[0] is a["edge_index"], "the build must have registered its CSR"
+    gf.ONE_LAUNCH_BUILD = False
+    try:
+        b = q.image_to_graph(xg, **kw)
+    finally:
+        gf.ONE_LAUNCH_BUILD = True
+    csr_b = graph_csr.GraphCSR(b["edge_index"], b["edge_attrs"], b["data"].shape[1])
+    for k in ("edge_index", "edge_attrs", "data", "n_pixels_per_node", "labels"):
+        assert torch.equal(a[k], b[k]), k
+    ma, mb = a["mapping"], b["mapping"]
+    assert ma.n_nodes == mb.n_nodes and torch.equal(ma.pix_ptr, mb.pix_ptr)
+    nv = int(ma.pix_ptr[-1])
+    assert torch.equal(ma.pix_idx[:nv], mb.pix_idx[:nv])
+    for k in ("src", "dst", "in_ptr", "in_src", "in_eid", "out_ptr", "out_dst", "out_kin", "edge_attr_in"):
+        assert torch.equal(getattr(csr_a, k), getattr(csr_b, k)), k
+    # a second build on the same arena must not disturb the first result
+    c = q.image_to_graph(xg.flip(0), **kw)
+    assert torch.equal(a["edge_index"], b["edge_index"]) and torch.equal(csr_a.in_src, csr_b.in_src) and c["data"].shape[0] == xg.shape[0]

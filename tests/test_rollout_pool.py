@@ -57,4 +57,4 @@ def test_pool_lanes_match_sequential_eager_rollouts(static_mesh):
 
 def test_default_lanes():
     from quadtree_mpnnlstm_b200.infer import default_lanes
-    assert default_lanes(4066) == 4 and default_lanes(47200) == 1 and default_lanes(100) == 4 and default_lanes(9000) == 2
+    assert default_lanes(4066) == 8 and default_lanes(47200) == 1 and default_lanes(100) == 8 and default_lanes(9000) == 4
