@@ -46,7 +46,7 @@ struct GbArgs {
     unsigned long long* keys; int* vals; unsigned cap_mask; long long table_cap;
     uint8_t* emit; int* count;
     int* part_a; int* part_b;                              // per-CTA partial sums of the grid-wide scans [gridDim]
-    int* cnt_in; int* cnt_out; int* cur_in; int* cur_out; int* eid_out; int* kin_of_edge;
+    int* cnt_in; int* cnt_out; int* cur_in; int* cur_out; int* eid_out; int* kin_of_edge; int* tmp_in; int* tmp_out;
 };
 
 __device__ __forceinline__ long long gb_level_off(int n_pad, int m_pad, int lvl) {
@@ -146,8 +146,19 @@ __device__ __forceinline__ unsigned long long gb_mix64(unsigned long long k) {
     return k;
 }
 
+// phase timeline: CTA 0 stamps the global timer (ns) after every grid-wide barrier into the arena's first 256 bytes, behind the
+// four counts (bytes 64 ..: read by scripts/build_phases.py; 16 stores per launch)
+__device__ __forceinline__ void gb_mark(const GbArgs& a, int k) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        reinterpret_cast<unsigned long long*>(a.counts)[8 + k] = t;
+    }
+}
+
 __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbArgs a) {
     cg::grid_group grid = cg::this_grid();
+    gb_mark(a, 0);
     __shared__ __align__(128) float s_e0[GB_TS * GB_TS];   // staged level-0 tile (bulk copies)
     __shared__ __align__(128) int s_k0[GB_TS * GB_TS];
     __shared__ float s_ext[1024 + 256];                    // levels >= 1: ping (1024) / pong (256)
@@ -199,6 +210,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         tc::fence_mbar_init();
     }
     grid.sync();
+    gb_mark(a, 1);
 
     // ---------------------------------------------------------------- phase 1: split pyramid per 64 x 64 tile
     {
@@ -279,6 +291,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         }
     }
     grid.sync();
+    gb_mark(a, 2);
 
     // ---------------------------------------------------------------- phase 2: leaves before each base cell (reverse raster)
     if (blockIdx.x == 0) {
@@ -303,6 +316,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         if (tid == 0) a.counts[0] = total;
     }
     grid.sync();
+    gb_mark(a, 3);
     const int N = a.counts[0];
 
     // ---------------------------------------------------------------- phase 3: label of every pixel, leaf rectangles
@@ -348,6 +362,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         }
     }
     grid.sync();
+    gb_mark(a, 4);
 
     // ---------------------------------------------------------------- phase 4a: pixel-list scan (pass 1), adjacency inserts
     {
@@ -380,6 +395,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         }
     }
     grid.sync();
+    gb_mark(a, 5);
 
     // ---------------------------------------------------------------- phase 4b: pix_ptr; first-occurrence flags + edge scan (pass 1)
     {
@@ -425,6 +441,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         if (tid == 0) a.part_b[blockIdx.x] = s;
     }
     grid.sync();
+    gb_mark(a, 6);
 
     // ---------------------------------------------------------------- phase 5: pixel lists; edge offsets + emission
     for (long long p = gtid; p < P; p += gthreads) {
@@ -461,6 +478,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         if (blockIdx.x == gridDim.x - 1 && tid == 0) a.counts[1] = carry;
     }
     grid.sync();
+    gb_mark(a, 7);
     const int E = a.counts[1];
     const int Cd = a.C + 1;                                 // data row: pooled channels | cell size
 
@@ -470,7 +488,11 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         const long long warp = gtid >> 5, nwarps = gthreads >> 5;
         for (long long w = warp; w < (long long)a.T * N; w += nwarps) {
             const int b = (int)(w / N), v = (int)(w - (long long)b * N);
-            const int a0 = a.pix_ptr[v], a1 = a.pix_ptr[v + 1];
+            // the pixels of a leaf in raster order come straight from its rectangle (no pixel-list indirection: every load
+            // address is known up front, so the loads of several rounds are in flight together; the additions stay in the
+            // defined order)
+            const int4 rc = a.rect[v];
+            const int cnt = rc.z * rc.w;
             const float* src = a.img + (size_t)b * P * a.C;
             const float np = a.npix[v];
             float* orow = a.data + ((size_t)b * N + v) * Cd;
@@ -479,11 +501,23 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
                 float acc[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) acc[c] = 0.f;
-                for (int k = a0 + lane; k < a1; k += 32) {
-                    const float* px = src + (size_t)a.pix_idx[k] * a.C + c0;
+                for (int k0 = lane; k0 < cnt; k0 += 128) {
+                    float x[4][8];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c)
-                        if (c < cw) acc[c] += px[c];
+                    for (int u = 0; u < 4; ++u) {
+                        const int k = k0 + 32 * u;
+                        const bool ok = k < cnt;
+                        const int rr = ok ? k / rc.w : 0;
+                        const float* px = src + ((size_t)(rc.x + rr) * a.m + rc.y + (ok ? k - rr * rc.w : 0)) * a.C + c0;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) x[u][c] = (ok && c < cw) ? px[c] : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (k0 + 32 * u < cnt) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) acc[c] += x[u][c];
+                        }
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
@@ -507,6 +541,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         atomicAdd(&a.cnt_out[s], 1);
     }
     grid.sync();
+    gb_mark(a, 8);
 
     // ---------------------------------------------------------------- phase 7: edge attributes; CSR row-pointer scans (pass 1)
     for (long long e = gtid; e < E; e += gthreads) {
@@ -544,6 +579,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         }
     }
     grid.sync();
+    gb_mark(a, 9);
 
     // ---------------------------------------------------------------- phase 8: in_ptr / out_ptr (+ cursors)
     {
@@ -567,31 +603,37 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         }
     }
     grid.sync();
+    gb_mark(a, 10);
 
     // ---------------------------------------------------------------- phase 9: rows filled in arrival order ...
     for (long long e = gtid; e < E; e += gthreads) {
-        a.in_eid[atomicAdd(&a.cur_in[a.dst32[e]], 1)] = (int)e;
-        a.eid_out[atomicAdd(&a.cur_out[a.src32[e]], 1)] = (int)e;
+        a.tmp_in[atomicAdd(&a.cur_in[a.dst32[e]], 1)] = (int)e;
+        a.tmp_out[atomicAdd(&a.cur_out[a.src32[e]], 1)] = (int)e;
     }
     grid.sync();
+    gb_mark(a, 11);
 
-    // ---------------------------------------------------------------- phase 10: ... then sorted by edge id (fixed summation order)
-    for (long long t = gtid; t < 2ll * N; t += gthreads) {
-        const int v = (int)(t >> 1);
-        const int* ptr = (t & 1) ? a.out_ptr : a.in_ptr;
-        int* eid = (t & 1) ? a.eid_out : a.in_eid;
-        const int lo = ptr[v], hi = ptr[v + 1];
-        for (int x = lo + 1; x < hi; ++x) {
-            const int val = eid[x];
-            int y = x - 1;
-            while (y >= lo && eid[y] > val) {
-                eid[y + 1] = eid[y];
-                --y;
+    // ---------------------------------------------------------------- phase 10: ... then ordered by edge id (fixed summation order):
+    // a warp per row, every element's rank = the number of smaller ids in its row (rows are short: a leaf's perimeter)
+    {
+        const int lane = tid & 31;
+        const long long warp = gtid >> 5, nwarps = gthreads >> 5;
+        for (long long t = warp; t < 2ll * N; t += nwarps) {
+            const int v = (int)(t >> 1);
+            const int* ptr = (t & 1) ? a.out_ptr : a.in_ptr;
+            const int* tmp = (t & 1) ? a.tmp_out : a.tmp_in;
+            int* eid = (t & 1) ? a.eid_out : a.in_eid;
+            const int lo = ptr[v], r = ptr[v + 1] - lo;
+            for (int i = lane; i < r; i += 32) {
+                const int x = tmp[lo + i];
+                int rank = 0;
+                for (int j = 0; j < r; ++j) rank += (tmp[lo + j] < x);
+                eid[lo + rank] = x;
             }
-            eid[y + 1] = val;
         }
     }
     grid.sync();
+    gb_mark(a, 12);
 
     // ---------------------------------------------------------------- phase 11: in-CSR payload
     {
@@ -604,6 +646,7 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         }
     }
     grid.sync();
+    gb_mark(a, 13);
 
     // ---------------------------------------------------------------- phase 12: out-CSR payload
     for (long long k = gtid; k < E; k += gthreads) {
@@ -611,11 +654,12 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
         a.out_dst[k] = a.dst32[e];
         a.out_kin[k] = a.kin_of_edge[e];
     }
+    gb_mark(a, 14);
 }
 
 struct GbScratch {
     size_t e0, ka0, cnt, split, base_off, rect, keys, vals, emit, count, part_a, part_b, cnt_in, cnt_out, cur_in, cur_out, eid_out,
-        kin_of_edge, counts;
+        kin_of_edge, tmp_in, tmp_out, counts;
     // results at capacity (P pixels, e_cap = 4 P edges); qmp_quadtree_graph_export copies their prefixes out
     size_t labels, npix, pix_ptr, pix_idx, data, ei64, src32, dst32, edge_attrs, in_ptr, in_src, in_eid, out_ptr, out_dst, out_kin,
         edge_attr_in;
@@ -643,7 +687,7 @@ static GbScratch gb_layout(int n, int m, int max_size, int T, int C) {
         off += (bytes + 255) & ~(size_t)255;
         return at;
     };
-    s.counts = take(16);
+    s.counts = take(256);                                   // 4 counts | phase timeline (gb_mark)
     s.e0 = take(4 * np);
     s.ka0 = take(4 * np);
     s.cnt = take(4 * cells);
@@ -662,6 +706,8 @@ static GbScratch gb_layout(int n, int m, int max_size, int T, int C) {
     s.cur_out = take(4 * (P + 2));
     s.eid_out = take(4 * e_cap);
     s.kin_of_edge = take(4 * e_cap);
+    s.tmp_in = take(4 * e_cap);
+    s.tmp_out = take(4 * e_cap);
     s.labels = take(4 * P);
     s.npix = take(4 * P);
     s.pix_ptr = take(4 * (P + 1));
@@ -748,6 +794,7 @@ QMP_API int qmp_quadtree_graph(const float* img, int T, int n, int m, int C, con
     a.emit = GB_AT(uint8_t, emit); a.count = GB_AT(int, count); a.part_a = GB_AT(int, part_a); a.part_b = GB_AT(int, part_b);
     a.cnt_in = GB_AT(int, cnt_in); a.cnt_out = GB_AT(int, cnt_out); a.cur_in = GB_AT(int, cur_in); a.cur_out = GB_AT(int, cur_out);
     a.eid_out = GB_AT(int, eid_out); a.kin_of_edge = GB_AT(int, kin_of_edge);
+    a.tmp_in = GB_AT(int, tmp_in); a.tmp_out = GB_AT(int, tmp_out);
 
     static int grid = 0;
     if (grid == 0) {

@@ -84,11 +84,24 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const float* __restric
             float acc[SEG_CH];
 #pragma unroll
             for (int c = 0; c < SEG_CH; ++c) acc[c] = 0.f;
-            for (int k = a0 + lane; k < a1; k += 32) {
-                const float* px = src + (size_t)pix_idx[k] * C + c0;
+            // four rounds of loads in flight (pixel ids first, then the rows); the additions keep the defined order
+            for (int k0 = a0 + lane; k0 < a1; k0 += 128) {
+                int pid[4];
 #pragma unroll
-                for (int c = 0; c < SEG_CH; ++c)
-                    if (c < cw) acc[c] += px[c];
+                for (int u = 0; u < 4; ++u) pid[u] = (k0 + 32 * u < a1) ? pix_idx[k0 + 32 * u] : -1;
+                float x[4][SEG_CH];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float* px = src + (size_t)(pid[u] < 0 ? 0 : pid[u]) * C + c0;
+#pragma unroll
+                    for (int c = 0; c < SEG_CH; ++c) x[u][c] = (pid[u] >= 0 && c < cw) ? px[c] : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (pid[u] >= 0) {
+#pragma unroll
+                        for (int c = 0; c < SEG_CH; ++c) acc[c] += x[u][c];
+                    }
             }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {

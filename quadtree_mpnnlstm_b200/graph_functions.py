@@ -403,11 +403,12 @@ def image_to_graph(img, thresh=0.05, max_grid_size=64, mask=None, high_interest_
     if not _lib.on_device(img):
         raise _lib.QmpError("image_to_graph: CUDA tensor required (no CPU fallback)")
     img = img.float().contiguous()
-    nan_flag = torch.isnan(img.detach()).sum()
     if thresh == -np.inf:
         # (a CUDA-graph capture cannot read back; the eager warm-up steps before a capture do check)
-        if not _lib.capturing() and int(nan_flag.item()):
-            raise ValueError(f'Found NaNs in image data {int(nan_flag.item())} / {img.numel()}')
+        if not _lib.capturing():
+            nans = int(torch.isnan(img.detach()).sum().item())
+            if nans:
+                raise ValueError(f'Found NaNs in image data {nans} / {img.numel()}')
         return image_to_graph_pixelwise(img, mask, use_edge_attrs=use_edge_attrs, resolution=resolution)
 
     n, h, w, c = img.shape
@@ -425,6 +426,7 @@ def image_to_graph(img, thresh=0.05, max_grid_size=64, mask=None, high_interest_
     if S <= 64 and c >= 2 and ONE_LAUNCH_BUILD:
         return _quadtree_graph_one_launch(img, crit, m8, h8, S, CONDITIONS.index(condition), thresh, use_edge_attrs, resolution,
                                           max_grid_size)
+    nan_flag = torch.isnan(img.detach()).sum()              # (the one-launch build counts NaNs itself)
     cells = _lib.lib().qmp_quadtree_pyramid_cells(h, w, S)
     labels, rect, npix = torch.empty(P, **i32), torch.empty(P, 4, **i32), torch.empty(P, **f32)
     counts = torch.zeros(2, **i32)                       # [n_nodes, n_edges]
