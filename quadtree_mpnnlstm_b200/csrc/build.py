@@ -34,6 +34,7 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_mesh_pixelwise": "model/graph_functions.py:511-525 pixel-wise labels / graph_nodes / n_pixels_per_node",
     "qmp_segment_sum": "model/graph_functions.py:391-419 flatten (and the backward of unflatten)",
     "qmp_gather_by_label": "model/graph_functions.py:451-468 unflatten (and the backward of flatten)",
+    "qmp_regrid": "model/seq2seq.py:434-491 do_remesh: unflatten (graph_functions.py:451-468) + flatten (:391-419) of a recurrent state as one pass, and their backward",
     "qmp_adjacency_quadtree": "model/graph_functions.py:261-345 get_adj",
     "qmp_adjacency_pixelwise": "model/graph_functions.py:471-493 get_adj_pixelwise",
     "qmp_edge_attrs": "model/graph_functions.py:358-370 dist / dist_angle (+ :347-353, :657)",

@@ -206,6 +206,62 @@ class _Unpool(torch.autograd.Function):
         return dd, None, None
 
 
+class _Regrid(torch.autograd.Function):
+    """``flatten(unflatten(a, mesh_s), mesh_d)`` for up to two node tensors [B, N_s, C] (hidden and cell state) as ONE launch each
+    way (csrc/pool.cu regrid_kernel) -- the [B, H, W, C] images of model/seq2seq.py:440-476 are never materialised.  Values and
+    gradients are bit-identical to the two-step path (same gather, same defined summation order)."""
+
+    @staticmethod
+    def forward(ctx, mesh_s, mesh_d, a, b):
+        B, Ns, C = a.shape
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+        H, W = mesh_s.image_shape
+        Nd = mesh_d.n_nodes
+        out_a = torch.empty(B, Nd, C, dtype=torch.float32, device=a.device)
+        out_b = torch.empty(B, Nd, C, dtype=torch.float32, device=a.device) if b is not None else None
+        _lib.call("qmp_regrid", a, b, B, H * W, C, Ns, mesh_s.labels, mesh_s.npix, 0, 0.0, mesh_d.pix_ptr, mesh_d.pix_idx,
+                  mesh_d.npix, Nd, 1, out_a, out_b)
+        ctx.meshes, ctx.shape, ctx.two = (mesh_s, mesh_d), (B, Ns, C), b is not None
+        if b is None:
+            return out_a
+        return out_a, out_b
+
+    @staticmethod
+    def backward(ctx, ga, gb=None):
+        mesh_s, mesh_d = ctx.meshes
+        B, Ns, C = ctx.shape
+        H, W = mesh_s.image_shape
+        Nd = mesh_d.n_nodes
+        if ga is None and gb is None:
+            return None, None, None, None
+        zero = lambda: torch.zeros(B, Nd, C, dtype=torch.float32, device=mesh_s.labels.device)
+        ga = ga.contiguous() if ga is not None else zero()
+        if ctx.two:
+            gb = gb.contiguous() if gb is not None else zero()
+        da = torch.empty(B, Ns, C, dtype=torch.float32, device=ga.device)
+        db = torch.empty(B, Ns, C, dtype=torch.float32, device=ga.device) if ctx.two else None
+        # pool backward (gather by D's labels with the division) + unpool backward (sum over S's pixel lists)
+        _lib.call("qmp_regrid", ga, gb if ctx.two else None, B, H * W, C, Nd, mesh_d.labels, mesh_d.npix, 1, 0.0, mesh_s.pix_ptr,
+                  mesh_s.pix_idx, mesh_s.npix, Ns, 0, da, db)
+        return None, None, da, db
+
+
+def regrid(mesh_s, mesh_d, a, b=None, image_shape=None, n_pixels_per_node=None):
+    """Move node tensors ``a`` (and ``b``) [..., N_s, C] from mesh ``mesh_s`` onto mesh ``mesh_d``: the reference's
+    unflatten -> flatten pair of do_remesh (model/seq2seq.py:440-476) in one pass.  Returns tensors [..., N_d, C]."""
+    C = a.shape[-1]
+    if not (isinstance(mesh_s, Mesh) and isinstance(mesh_d, Mesh)) or (b is not None and b.shape != a.shape):
+        f = lambda t: flatten(unflatten(t, mesh_s, image_shape), mesh_d, n_pixels_per_node)      # dense mappings
+        return f(a) if b is None else (f(a), f(b))
+    lead = a.shape[:-2]
+    a3 = a.float().reshape(-1, a.shape[-2], C)
+    if b is None:
+        return _Regrid.apply(mesh_s, mesh_d, a3, None).reshape(*lead, mesh_d.n_nodes, C)
+    oa, ob = _Regrid.apply(mesh_s, mesh_d, a3, b.float().reshape(-1, b.shape[-2], C))
+    return oa.reshape(*lead, mesh_d.n_nodes, C), ob.reshape(*lead, mesh_d.n_nodes, C)
+
+
 def _as_mesh(mapping, image_shape, mask, device):
     if isinstance(mapping, Mesh):
         return mapping

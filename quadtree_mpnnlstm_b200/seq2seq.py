@@ -19,7 +19,7 @@ import torch.nn as nn
 from . import _lib
 from . import fused as _fused
 from .graph_csr import get_csr
-from .graph_functions import Graph, Mesh, flatten, image_to_graph, unflatten
+from .graph_functions import Graph, Mesh, flatten, image_to_graph, regrid, unflatten
 from .model import CONVOLUTION_KWARGS, CONVOLUTIONS, GConvLSTM, new_epoch
 from .ops import HeadFinishFn, NodeLinearFn, SpmmFn, TConvFn, next_seed
 from .convs import cheb_basis, pack_tconv
@@ -365,15 +365,13 @@ class Seq2Seq(torch.nn.Module):
         g = self.graph
         image_shape = g.image_shape
         data_img = unflatten(data, g.mapping, image_shape)
-        hidden_img = unflatten(hidden, g.mapping, image_shape)
-        cell_img = unflatten(cell, g.mapping, image_shape)
         if teacher_force:
             gs = self._image_to_graph(add_positional_encoding(teacher_input.float()), mask, high_interest_region)
         else:
             gs = self._image_to_graph(add_positional_encoding(data_img.unsqueeze(0)), mask, high_interest_region)
         # flatten(swapaxes(img, 0, -1)) and swap back (seq2seq.py:474-477) == pooling every [H, W] plane
-        g.hidden = flatten(hidden_img, gs['mapping'], gs['n_pixels_per_node'])
-        g.cell = flatten(cell_img, gs['mapping'], gs['n_pixels_per_node'])
+        # -- hidden and cell state go old nodes -> pixels -> new nodes in one launch, no [H, W, C] images (graph_functions.regrid)
+        g.hidden, g.cell = regrid(g.mapping, gs['mapping'], hidden, cell, image_shape, gs['n_pixels_per_node'])
         g.pyg.edge_index = gs['edge_index']
         g.pyg.edge_attr = gs['edge_attrs']
         g.pyg.x = gs['data'].squeeze(0)

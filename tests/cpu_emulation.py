@@ -122,6 +122,19 @@ def qmp_gather_by_label(data, B, P, C, n_stride, labels, npix, divide, fill, img
     flat(img, B * P * C).view(B, P, C).copy_(res)
 
 
+def qmp_regrid(src0, src1, B, P, C, n_src, lab_s, npix_s, src_divide, fill, pix_ptr, pix_idx, npix_d, n_dst, dst_divide, out0, out1):
+    """csrc/pool.cu regrid_kernel: gather by the source labels, then the defined segment sum over the destination pixel lists."""
+    for src, out in ((src0, out0), (src1, out1)):
+        if src is None or out is None:
+            continue
+        if lab_s is None:
+            img = src
+        else:
+            img = torch.empty(B * P * C, dtype=torch.float32)
+            qmp_gather_by_label(src, B, P, C, n_src, lab_s, npix_s, src_divide, fill, img)
+        qmp_segment_sum(img, B, P, C, pix_ptr, pix_idx, npix_d, n_dst, None, dst_divide, 0, out)
+
+
 def _emit_edges(ei, src64, dst64, src32, dst32, n_edges):
     E = ei.shape[1]
     flat(src64, E).copy_(torch.from_numpy(ei[0]))

@@ -127,6 +127,46 @@ def test_pool_unpool_forward_backward(be):
     assert torch.equal(pc.cpu(), pa.detach())
 
 
+@pytest.mark.parametrize("shape,S,C", [((48, 40), 16, 8), ((229, 361), 64, 32), ((33, 70), 4, 4), ((64, 64), 64, 3)])
+def test_regrid_is_bit_identical_to_unflatten_then_flatten(be, shape, S, C):
+    """graph_functions.regrid (csrc/pool.cu regrid_kernel; model/seq2seq.py:440-476 do_remesh) against the two-step path it
+    replaces: values AND gradients bit for bit, hidden and cell state in one launch, nodes of 1 ... S x S pixels."""
+    import quadtree_mpnnlstm_b200 as q
+    from quadtree_mpnnlstm_b200.graph_functions import regrid
+    if be.device == "cpu" and shape[0] > 100:
+        pytest.skip("full grid on the GPU only")
+    rng = np.random.default_rng(11)
+    H, W = shape
+    mask = rng.random((H, W)) > 0.9
+    meshes = []
+    for k in range(2):
+        x = blob_frames(rng, 1, H, W, c=1)
+        g = q.image_to_graph(q.add_positional_encoding(be.dev(torch.from_numpy(x))), thresh=0.3 + 0.3 * k, max_grid_size=S, mask=mask)
+        meshes.append(g)
+    ms, md = meshes[0]["mapping"], meshes[1]["mapping"]
+    L = 2
+    h0 = torch.from_numpy(rng.standard_normal((L, ms.n_nodes, C)).astype(np.float32))
+    c0 = torch.from_numpy(rng.standard_normal((L, ms.n_nodes, C)).astype(np.float32))
+    wa = be.dev(torch.from_numpy(rng.standard_normal((L, md.n_nodes, C)).astype(np.float32)))
+    wb = be.dev(torch.from_numpy(rng.standard_normal((L, md.n_nodes, C)).astype(np.float32)))
+    res = []
+    for fused in (True, False):
+        h = be.dev(h0.clone()).requires_grad_(True)
+        c = be.dev(c0.clone()).requires_grad_(True)
+        if fused:
+            oh, oc = regrid(ms, md, h, c, (H, W), meshes[1]["n_pixels_per_node"])
+        else:
+            oh = q.flatten(q.unflatten(h, ms, (H, W)), md, meshes[1]["n_pixels_per_node"])
+            oc = q.flatten(q.unflatten(c, ms, (H, W)), md, meshes[1]["n_pixels_per_node"])
+        ((oh * wa).sum() + (oc * wb).sum()).backward()
+        res.append((oh.detach().cpu(), oc.detach().cpu(), h.grad.cpu(), c.grad.cpu()))
+    for a, b, name in zip(res[0], res[1], ("hidden", "cell", "d hidden", "d cell")):
+        assert a.shape == b.shape and torch.equal(a, b), f"{name} differs: {rel_err(a, b)}"
+    # one tensor only
+    h = be.dev(h0.clone())
+    assert torch.equal(regrid(ms, md, h, None, (H, W), meshes[1]["n_pixels_per_node"]).cpu(), res[1][0])
+
+
 def test_nan_input_raises(be):
     import quadtree_mpnnlstm_b200 as q
     x = torch.zeros(1, 16, 16, 3, device=be.device)
