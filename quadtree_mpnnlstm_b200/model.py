@@ -9,6 +9,8 @@ when the encoder / decoder ask for it, the LayerNorms and the decoder-head input
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -16,8 +18,12 @@ import torch.nn.functional as F
 from .convs import (ChebConv, GATConv, GATv2Conv, GCNConv, MHTransformerConv, TransformerConv, cheb_basis,
                     pack_tconv)
 from . import fused as _fused
+from .cheb_cell import ChebCellFn, pack_linear_group
 from .graph_csr import get_csr
 from .ops import LstmGatesFn, NodeLinearFn, SpmmFn, TConvFn, next_seed
+
+CHEB_CELL_FN = os.environ.get("QMP_CHEB_CELL_FN", "1") != "0"     # ChebConv / GCNConv cells as one autograd node (cheb_cell.py); 0: the
+                                                                  # modular SpmmFn / NodeLinearFn path (the cross-check)
 
 CONVOLUTIONS = {
     'GCNConv': GCNConv,
@@ -151,6 +157,15 @@ class GConvLSTM(nn.Module):
                                    lambda: pack_tconv(self._convs("x", l) + self._convs("h", l)))
                 cur = TConvFn.apply(cur, *pka, csr, False, p, seed(), False, None)
             return cur[:, :4 * C] + cur[:, 4 * C:]
+        if kind in ('GCNConv', 'ChebConv') and CHEB_CELL_FN:
+            # one autograd node for the eight stacks (cheb_cell.py): basis blocks, grouped GEMMs and the in-place weight gradients
+            mode = "gcn" if kind == 'GCNConv' else "cheb"
+            K = 1 if kind == 'GCNConv' else self.conv_x_i.convolutions[0].K
+            pk = lambda key, convs: self._cached((mode, "cell") + key, epoch,
+                                                 lambda: _fused.shared_pack(pack_linear_group(convs(), kind)))
+            packs = [pk(("x", 0), lambda: self._convs("x", 0)), pk(("h", 0), lambda: self._convs("h", 0))]
+            packs += [pk(("all", l), lambda l=l: self._convs("x", l) + self._convs("h", l)) for l in range(1, S)]
+            return ChebCellFn.apply(X.contiguous(), H, csr, mode, K, S, C, *packs)
         if kind in ('GCNConv', 'ChebConv'):
             mode = "gcn" if kind == 'GCNConv' else "cheb"
             K = 1 if kind == 'GCNConv' else self.conv_x_i.convolutions[0].K

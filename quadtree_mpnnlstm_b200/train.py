@@ -39,7 +39,8 @@ class TrainStep:
         self.params = [p for p in model.parameters()]
         # capturable foreach Adam divides by per-parameter bias-correction TENSORS: two one-tensor kernels per parameter
         # (652 of the step's launches, 2 ms at the ice configuration); the fused implementation is a handful of launches
-        fused = bool(use_cuda_graph and self.params and all(p.is_cuda for p in self.params))
+        # (eager steps -- dynamic meshes -- are bound by the number of launches, so they take the fused implementation too)
+        fused = bool(self.params and all(p.is_cuda for p in self.params))
         self.opt = torch.optim.Adam(self.params, lr=lr, capturable=use_cuda_graph, fused=fused or None)
         self.use_cuda_graph, self.pg, self.world, self.max_norm = use_cuda_graph, process_group, world_size, max_norm
         self.graph = None

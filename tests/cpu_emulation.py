@@ -370,6 +370,24 @@ def qmp_spmm(N, width, ptr, nbr, vidx, val, x, ldx, alpha, beta, z, ldz, y, ldy)
     rows(y, N, ldy, width).copy_(out)
 
 
+def qmp_cheb_cell_fwd(N, F, C, K, S, cheb, in_ptr, in_src, val, X, H, p0, p1, p2, p3, b0, b1, b2, b3, ws, P):
+    """csrc/cheb_cell.cu issues the launch sequence that cheb_cell._fwd_py restates (on the emulated kernels here)."""
+    from quadtree_mpnnlstm_b200 import cheb_cell as CC
+    packs = [p for p in (p0, p1, p2, p3) if p is not None]
+    biases = [b for b in (b0, b1, b2, b3) if b is not None]
+    CC._fwd_py(N, F, C, K, S, bool(cheb), (in_ptr, in_src, val, None, None, None), X.reshape(-1), H.reshape(-1), packs, biases, ws,
+               P.view(-1))
+
+
+def qmp_cheb_cell_bwd(N, F, C, K, S, cheb, out_ptr, out_dst, out_kin, val, dP, p0, p1, p2, p3, a0, a1, a2, a3, ws, ws2, need_dx,
+                      need_dh, dX, dH):
+    from quadtree_mpnnlstm_b200 import cheb_cell as CC
+    packs = [p for p in (p0, p1, p2, p3) if p is not None]
+    accs = [a for a in (a0, a1, a2, a3) if a is not None]
+    CC._bwd_py(N, F, C, K, S, bool(cheb), (None, None, val, out_ptr, out_dst, out_kin), dP.reshape(-1), packs, accs, ws, ws2,
+               bool(need_dx), bool(need_dh), dX.view(-1) if dX is not None else None, dH.view(-1) if dH is not None else None)
+
+
 # ------------------------------------------------------------------------------------------ LSTM gates
 def _ln(x, gamma, beta, eps):
     mu = x.mean(-1, keepdim=True)

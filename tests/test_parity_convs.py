@@ -646,3 +646,45 @@ def test_head_bwd_kernel_matches_onepass(N, drop_p):
         assert not torch.isnan(vb).any(), f"{k}: unwritten / NaN entries"
         err = float((va - vb).abs().max()) / max(float(va.abs().max()), 1e-6)
         assert err < 5e-5, f"{k}: {err}"
+
+
+@pytest.mark.parametrize("conv,S", [("ChebConv", 1), ("ChebConv", 2), ("ChebConv", 3), ("GCNConv", 2)])
+def test_cheb_cell_c_sequence_equals_python_sequence_and_modular_path(be, conv, S, monkeypatch):
+    """cheb_cell.ChebCellFn: the launch sequence issued from C++ (qmp_cheb_cell_fwd / _bwd) against the same sequence issued from
+    Python (bit for bit: same kernels, same order) and against the modular SpmmFn / NodeLinearFn path (model/model.py:430-447),
+    over three timesteps that share the weight packs (in-place gradient accumulation)."""
+    import quadtree_mpnnlstm_b200.model as M
+    import quadtree_mpnnlstm_b200.cheb_cell as CC
+    ei, ea, n = _graph(5, use_edge_attrs=False)
+    f_in, hid = 4, 16
+    torch.manual_seed(3)
+    X = [torch.randn(n, f_in) for _ in range(3)]
+    results = {}
+    for path in ("c", "py", "modular"):
+        monkeypatch.setattr(M, "CHEB_CELL_FN", path != "modular")
+        monkeypatch.setattr(CC, "USE_C", path == "c")
+        torch.manual_seed(5)
+        cell = be.dev(M.GConvLSTM(f_in, hid, S, conv))
+        with torch.no_grad():
+            for k, p in cell.named_parameters():
+                if k.startswith(("w_c_", "b_")):
+                    p.copy_(torch.linspace(-0.5, 0.5, p.numel()).view_as(p))
+        xs = [be.dev(x.clone()).requires_grad_(True) for x in X]
+        H = C = None
+        epoch = M.new_epoch()
+        outs = []
+        for x in xs:
+            O, H, C, _ = cell.fused(x, be.dev(ei), None, H, C, epoch=epoch)
+            outs.append(O)
+        sum((o * o).sum() for o in outs).backward()
+        results[path] = ([o.detach().cpu() for o in outs], [x.grad.cpu() for x in xs],
+                         {k: p.grad.cpu() for k, p in cell.named_parameters() if p.grad is not None})
+    for a, b in zip(results["c"][0] + results["c"][1], results["py"][0] + results["py"][1]):
+        assert torch.equal(a, b), "C++ and Python launch sequences differ"
+    assert results["c"][2].keys() == results["py"][2].keys() == results["modular"][2].keys()
+    for k in results["c"][2]:
+        if k.startswith("conv_"):          # (the peephole / bias gradients of the gate kernel are atomics: order not defined)
+            assert torch.equal(results["c"][2][k], results["py"][2][k]), k
+        assert rel_err(results["c"][2][k], results["modular"][2][k]) < 1e-4, k
+    for a, b in zip(results["c"][0] + results["c"][1], results["modular"][0] + results["modular"][1]):
+        assert rel_err(a, b) < 1e-4

@@ -133,7 +133,7 @@ def test_regrid_is_bit_identical_to_unflatten_then_flatten(be, shape, S, C):
     replaces: values AND gradients bit for bit, hidden and cell state in one launch, nodes of 1 ... S x S pixels."""
     import quadtree_mpnnlstm_b200 as q
     from quadtree_mpnnlstm_b200.graph_functions import regrid
-    if be.device == "cpu" and shape[0] > 100:
+    if be.name == "cpu" and shape[0] > 100:
         pytest.skip("full grid on the GPU only")
     rng = np.random.default_rng(11)
     H, W = shape
