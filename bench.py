@@ -395,6 +395,40 @@ def extra_dynamic_quadtree(dev, mask, cube, clim, dropout, hbm):
                             "what": "image_to_graph of the 10 input frames (quadtree + pixel lists + pooling + adjacency + edge attributes), wall per call incl. its one host read-back"}}
 
 
+def extra_cheb_dynamic(dev):
+    """configs[0]-like (moving_mnist_example: 64 x 64 frames, Seq2Seq defaults = ChebConv K 3, hidden 16, 2 layers, quadtree thresh
+    0.1 rebuilt every forecast step, 10 + 10 frames): fwd + bwd + clip + Adam per sample, eager (data-dependent mesh)."""
+    import quadtree_mpnnlstm_b200 as q
+    from quadtree_mpnnlstm_b200.train import TrainStep
+    rng = np.random.default_rng(1)
+
+    def blob(T=10, size=28):          # N(0, 0.05) noise + a sparse blob translating 1 px / frame (SURVEY 8(d) C1-style sample)
+        x = rng.normal(0, 0.05, (T, 64, 64, 1)).astype(np.float32)
+        u = rng.random((size, size)).astype(np.float32)
+        b = (u > 0.6) * u
+        for t in range(T):
+            x[t, 5 + t:5 + t + size, 7 + t:7 + t + size, 0] += b
+        return x
+
+    smp = [[torch.from_numpy(a).to(dev) for a in (blob(), blob(), np.zeros((10, 64, 64, 1), np.float32))] for _ in range(7)]
+    torch.manual_seed(1)
+    model = q.Seq2Seq(hidden_size=16, dropout=0.0, thresh=0.1, input_timesteps=10, input_features=4, output_timesteps=10, n_layers=2,
+                      device=dev).to(dev).train()
+    step = TrainStep(model, np.zeros((64, 64), bool), lr=1e-4, use_cuda_graph=False)
+    for s_ in smp[:3]:
+        step(*s_)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s_ in smp[3:]:
+        step(*s_)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / len(smp[3:])
+    return {"workload": "configs[0]-like: 64x64 moving blob, Seq2Seq defaults (ChebConv K=3), hidden 16, 2 layers, dynamic quadtree "
+                        "thresh 0.1, 10+10 frames, fwd+bwd+clip+Adam, eager", "graph_frames_per_s": 20 / (ms / 1e3), "ms_per_sample": ms}
+
+
 def inference_setup(dev, mask, static_mesh=True):
     import quadtree_mpnnlstm_b200 as q
     torch.manual_seed(21)
@@ -588,6 +622,7 @@ def run_gpu(args):
         if world == 1 and not args.no_extras:
             extra = {}
             for name, fn in (("dynamic_quadtree", lambda: extra_dynamic_quadtree(dev, mask, cube, clim, args.dropout, hbm)),
+                             ("cheb_dynamic", lambda: extra_cheb_dynamic(dev)),
                              ("inference", lambda: extra_inference(dev, mask, cube, clim))):
                 try:
                     extra[name] = fn()

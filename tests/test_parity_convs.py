@@ -683,8 +683,9 @@ def test_cheb_cell_c_sequence_equals_python_sequence_and_modular_path(be, conv, 
         assert torch.equal(a, b), "C++ and Python launch sequences differ"
     assert results["c"][2].keys() == results["py"][2].keys() == results["modular"][2].keys()
     for k in results["c"][2]:
-        if k.startswith("conv_"):          # (the peephole / bias gradients of the gate kernel are atomics: order not defined)
-            assert torch.equal(results["c"][2][k], results["py"][2][k]), k
+        # (weight gradients are chunked reductions finished by atomics -- qmp_gemm_tn_acc, the gate kernel -- so their summation
+        # order is not defined: close, not bit-equal)
+        assert rel_err(results["c"][2][k], results["py"][2][k]) < 1e-5, k
         assert rel_err(results["c"][2][k], results["modular"][2][k]) < 1e-4, k
     for a, b in zip(results["c"][0] + results["c"][1], results["modular"][0] + results["modular"][1]):
         assert rel_err(a, b) < 1e-4
