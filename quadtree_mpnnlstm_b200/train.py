@@ -94,6 +94,21 @@ class TrainStep:
         self.opt.step()
         return loss.detach()
 
+    def _reserve_headroom(self, device, factor=1.25):
+        """Eager steps on data-dependent meshes: the bytes a sample keeps alive for its backward pass vary from sample to sample,
+        and every new high-water mark is a ``cudaMalloc`` -- a device-synchronising call of 2 ... 14 ms in the middle of a step
+        (profiles/r02c_dynprof_ice_after.txt).  After the second sample, grow the caching allocator's pool once to ``factor`` x
+        the peak seen so far; later samples then carve their blocks out of cached segments."""
+        peak, reserved = torch.cuda.max_memory_allocated(device), torch.cuda.memory_reserved(device)
+        free, _ = torch.cuda.mem_get_info(device)
+        want = min(max(int(factor * peak) - reserved, 256 << 20), free // 2)
+        if want > (8 << 20):
+            try:
+                del_me = torch.empty(want, dtype=torch.uint8, device=device)
+                del del_me
+            except RuntimeError:          # out of memory: keep going without the headroom
+                pass
+
     def _keep_mask(self, device):
         if getattr(self, "_keep", None) is None or self._keep.device != device:
             import numpy as np
@@ -135,7 +150,11 @@ class TrainStep:
         if ev is not None:                               # staged by stage(): wait for its copy
             torch.cuda.current_stream().wait_event(ev)
         if not self.use_cuda_graph:
-            return self._step(x, y, concat)
+            loss = self._step(x, y, concat)
+            self.eager_steps += 1
+            if self.eager_steps == 2 and x.is_cuda:
+                self._reserve_headroom(x.device)
+            return loss
         if self.graph is None:
             if self.stream is None:
                 self.stream = torch.cuda.Stream()
