@@ -486,14 +486,61 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
     {
         const int lane = tid & 31;
         const long long warp = gtid >> 5, nwarps = gthreads >> 5;
-        for (long long w = warp; w < (long long)a.T * N; w += nwarps) {
-            const int b = (int)(w / N), v = (int)(w - (long long)b * N);
+        // a warp takes 32 consecutive leaves of one frame.  Leaves of <= 4 pixels (all of a pixel-level mesh, most of any quadtree)
+        // are summed lane-serially -- lane l owns leaf v0 + l and adds its pixels as the butterfly would, (p0 + p2) + (p1 + p3) with
+        // absent partial sums +0 -- so 32 leaves are in flight per warp instead of one; larger leaves are then taken one at a time
+        // by the whole warp.
+        const int groups = (N + 31) / 32;
+        for (long long w = warp; w < (long long)a.T * groups; w += nwarps) {
+            const int b = (int)(w / groups), v0 = (int)(w - (long long)b * groups) * 32;
+            const float* src = a.img + (size_t)b * P * a.C;
+            const int vl = v0 + lane;
+            int4 rcl = make_int4(0, 0, 0, 0);
+            if (vl < N) rcl = a.rect[vl];
+            const int cntl = rcl.z * rcl.w;
+            if (vl < N && cntl <= 4) {
+                const float np = a.npix[vl];
+                float* orow = a.data + ((size_t)b * N + vl) * Cd;
+                const float* px[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int kk = k < cntl ? k : 0;
+                    const int rr = kk / rcl.w;
+                    px[k] = src + ((size_t)(rcl.x + rr) * a.m + rcl.y + (kk - rr * rcl.w)) * a.C;
+                }
+                for (int c = 0; c < a.C; ++c) {
+                    float pk[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pk[k] = (k < cntl) ? 0.f + px[k][c] : 0.f;
+                    orow[c] = ((pk[0] + pk[2]) + (pk[1] + pk[3])) / np;
+                }
+                orow[a.C] = np / a.size_div;
+            }
+            // larger leaves: queued (once, by the warps of frame 0) and summed below, a warp per (frame, leaf)
+            if (b == 0 && vl < N && cntl > 4) a.tmp_in[atomicAdd(&a.counts[3], 1)] = vl;
+        }
+    }
+    for (long long e = gtid; e < E; e += gthreads) {
+        const int s = a.src32[e], d = a.dst32[e];
+        a.ei64[e] = s;
+        a.ei64[(size_t)E + e] = d;
+        atomicAdd(&a.cnt_in[d], 1);
+        atomicAdd(&a.cnt_out[s], 1);
+    }
+    grid.sync();                                            // the queue of larger leaves is complete
+    {
+        const int lane = tid & 31;
+        const long long warp = gtid >> 5, nwarps = gthreads >> 5;
+        const int n_large = a.counts[3];
+        for (long long w = warp; w < (long long)a.T * n_large; w += nwarps) {
+            const int b = (int)(w / n_large), v = a.tmp_in[w - (long long)b * n_large];
+            const float* src = a.img + (size_t)b * P * a.C;
             // the pixels of a leaf in raster order come straight from its rectangle (no pixel-list indirection: every load
             // address is known up front, so the loads of several rounds are in flight together; the additions stay in the
-            // defined order)
+            // defined order).  (Eight rounds in flight, float4 loads, or a warp per group of four channels did not measure
+            // faster: the phase stays at 35 - 65 us for the 64 x 64 leaves of the ice grid, run-to-run spread included.)
             const int4 rc = a.rect[v];
             const int cnt = rc.z * rc.w;
-            const float* src = a.img + (size_t)b * P * a.C;
             const float np = a.npix[v];
             float* orow = a.data + ((size_t)b * N + v) * Cd;
             for (int c0 = 0; c0 < a.C; c0 += 8) {
@@ -532,13 +579,6 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
             }
             if (lane == 0) orow[a.C] = np / a.size_div;
         }
-    }
-    for (long long e = gtid; e < E; e += gthreads) {
-        const int s = a.src32[e], d = a.dst32[e];
-        a.ei64[e] = s;
-        a.ei64[(size_t)E + e] = d;
-        atomicAdd(&a.cnt_in[d], 1);
-        atomicAdd(&a.cnt_out[s], 1);
     }
     grid.sync();
     gb_mark(a, 8);
@@ -618,17 +658,40 @@ __global__ void __launch_bounds__(GB_THREADS, 2) quadtree_graph_kernel(const GbA
     {
         const int lane = tid & 31;
         const long long warp = gtid >> 5, nwarps = gthreads >> 5;
-        for (long long t = warp; t < 2ll * N; t += nwarps) {
-            const int v = (int)(t >> 1);
-            const int* ptr = (t & 1) ? a.out_ptr : a.in_ptr;
-            const int* tmp = (t & 1) ? a.tmp_out : a.tmp_in;
-            int* eid = (t & 1) ? a.eid_out : a.in_eid;
-            const int lo = ptr[v], r = ptr[v + 1] - lo;
-            for (int i = lane; i < r; i += 32) {
-                const int x = tmp[lo + i];
-                int rank = 0;
-                for (int j = 0; j < r; ++j) rank += (tmp[lo + j] < x);
-                eid[lo + rank] = x;
+        // a warp takes 32 consecutive rows of one CSR: rows of <= 8 entries (a small leaf's neighbours) are ranked by their own lane,
+        // longer rows afterwards by the whole warp
+        const int groups = (N + 31) / 32;
+        for (long long t = warp; t < 2ll * groups; t += nwarps) {
+            const int which = (int)(t & 1), v0 = (int)(t >> 1) * 32, vl = v0 + lane;
+            const int* ptr = which ? a.out_ptr : a.in_ptr;
+            const int* tmp = which ? a.tmp_out : a.tmp_in;
+            int* eid = which ? a.eid_out : a.in_eid;
+            const int lol = vl < N ? ptr[vl] : 0, rl = vl < N ? ptr[vl + 1] - lol : 0;
+            if (rl > 0 && rl <= 8) {
+                int x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = i < rl ? tmp[lol + i] : INT_MAX;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < rl) {
+                        int rank = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rank += (x[j] < x[i]);
+                        eid[lol + rank] = x[i];
+                    }
+                }
+            }
+            unsigned rest = __ballot_sync(0xffffffffu, rl > 8);
+            while (rest) {
+                const int n = __ffs(rest) - 1;
+                rest &= rest - 1;
+                const int lo = __shfl_sync(0xffffffffu, lol, n), r = __shfl_sync(0xffffffffu, rl, n);
+                for (int i = lane; i < r; i += 32) {
+                    const int x = tmp[lo + i];
+                    int rank = 0;
+                    for (int j = 0; j < r; ++j) rank += (tmp[lo + j] < x);
+                    eid[lo + rank] = x;
+                }
             }
         }
     }

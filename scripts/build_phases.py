@@ -19,7 +19,9 @@ names = ["level-0 planes, table fill, NaN count", "split pyramid (tiles)", "base
          "pixel scan pass 1 + adjacency inserts", "pix_ptr + first-occurrence flags", "pixel lists + edge emission",
          "pooling + edge_index + CSR counts", "edge attributes + CSR scan pass 1", "CSR row pointers", "CSR fill",
          "CSR row sort", "in-CSR payload", "out-CSR payload"]
-for label, im in (("10 frames", img), ("1 frame", img[:1].contiguous())):
+noise = img[:1].clone()
+noise[..., 0] = torch.rand_like(noise[..., 0])          # what an untrained model forecasts: (almost) every pixel its own leaf
+for label, im in (("10 frames", img), ("1 frame", img[:1].contiguous()), ("1 frame of noise (pixel-level mesh)", noise)):
     for _ in range(3):
         g = q.image_to_graph(im, thresh=0.15, mask=mask, transform_func=bench.dist_from_05, use_edge_attrs=True)
     torch.cuda.synchronize()
