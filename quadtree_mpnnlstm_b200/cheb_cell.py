@@ -182,6 +182,52 @@ def _bwd_py(N, F, C, K, S, cheb, g, dP, packs, accs, ws, ws2, need_dx, need_dh, 
         basis_bwd(w, [dT[k * w:] for k in range(K)], ld, res)
 
 
+def _cheb_forward(X, H, csr, mode, K, S, C, packs):
+    """P [N, 4C] and the state the backward pass needs."""
+    N, F = X.shape
+    cheb = mode == "cheb"
+    assert 1 <= S <= MAX_LAYERS and len(packs) == S + 1
+    biases = [bias_of(p) for p in packs]
+    _, n_ws = layout(N, F, C, K, S, cheb)
+    ws = torch.empty(n_ws, dtype=_f32, device=X.device)
+    P = torch.empty(N, 4 * C, dtype=_f32, device=X.device)
+    g = (csr.in_ptr, csr.in_src, csr.norm(mode), csr.out_ptr, csr.out_dst, csr.out_kin)
+    if USE_C:
+        pad = [None] * (MAX_LAYERS + 1 - len(packs))
+        _lib.call("qmp_cheb_cell_fwd", N, F, C, K, S, int(cheb), g[0], g[1], g[2], X, H, *packs, *pad, *biases, *pad, ws, P)
+    else:
+        _fwd_py(N, F, C, K, S, cheb, g, X, H, packs, biases, ws, P.view(-1))
+    holders = [getattr(p, "_qmp_acc", None) for p in packs]
+    return P, (g, (cheb, K, S, C, N, F), ws, packs, holders, csr)        # (csr: keeps the CSR arrays alive)
+
+
+def _cheb_backward(state, dP, need_dx, need_dh):
+    """(dX, dH, gradients of the packs as autograd expects them)."""
+    g, (cheb, K, S, C, N, F), ws, packs, holders, _ = state
+    dev = dP.device
+    grads = [None] * len(packs)
+    accs = []
+    for i, h in enumerate(holders):
+        if h is not None:
+            _fused.ACC_HITS += 1
+            accs.append(h.acc)
+        else:
+            grads[i] = torch.zeros_like(packs[i])
+            accs.append(grads[i])
+    dX = torch.empty(N, F, dtype=_f32, device=dev) if need_dx else None
+    dH = torch.empty(N, C, dtype=_f32, device=dev) if need_dh else None
+    ws2 = torch.empty(scratch_size(N, F, C, K, S), dtype=_f32, device=dev)
+    if USE_C:
+        pad = [None] * (MAX_LAYERS + 1 - len(packs))
+        _lib.call("qmp_cheb_cell_bwd", N, F, C, K, S, int(cheb), g[3], g[4], g[5], g[2], dP, *packs, *pad, *accs, *pad, ws, ws2,
+                  int(need_dx), int(need_dh), dX, dH)
+    else:
+        _bwd_py(N, F, C, K, S, cheb, g, dP.view(-1), packs, accs, ws, ws2, need_dx, need_dh,
+                dX.view(-1) if need_dx else None, dH.view(-1) if need_dh else None)
+    out = [_fused.hand_over(h, gr) if h is not None else gr for h, gr in zip(holders, grads)]
+    return dX, dH, tuple(out)
+
+
 class ChebCellFn(torch.autograd.Function):
     """``P [N, 4C] = sum over the x and the h stack of conv_{x,h}_g(...)`` for the gates g = i, f, c, o.
 
@@ -190,49 +236,57 @@ class ChebCellFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, X, H, csr, mode, K, S, C, *packs):
-        X, H = X.contiguous(), H.contiguous()
-        N, F = X.shape
-        cheb = mode == "cheb"
-        assert 1 <= S <= MAX_LAYERS and len(packs) == S + 1
-        biases = [bias_of(p) for p in packs]
-        _, n_ws = layout(N, F, C, K, S, cheb)
-        ws = torch.empty(n_ws, dtype=_f32, device=X.device)
-        P = torch.empty(N, 4 * C, dtype=_f32, device=X.device)
-        g = (csr.in_ptr, csr.in_src, csr.norm(mode), csr.out_ptr, csr.out_dst, csr.out_kin)
-        if USE_C:
-            pad = [None] * (MAX_LAYERS + 1 - len(packs))
-            _lib.call("qmp_cheb_cell_fwd", N, F, C, K, S, int(cheb), g[0], g[1], g[2], X, H, *packs, *pad, *biases, *pad, ws, P)
-        else:
-            _fwd_py(N, F, C, K, S, cheb, g, X, H, packs, biases, ws, P.view(-1))
-        ctx.g, ctx.cfg, ctx.ws, ctx.packs = g, (cheb, K, S, C, N, F), ws, packs
-        ctx.holders = [getattr(p, "_qmp_acc", None) for p in packs]
-        ctx.csr = csr                       # keeps the CSR arrays alive
+        P, ctx.state = _cheb_forward(X.contiguous(), H.contiguous(), csr, mode, K, S, C, packs)
         return P
 
     @staticmethod
     def backward(ctx, dP):
-        g, (cheb, K, S, C, N, F), ws, packs = ctx.g, ctx.cfg, ctx.ws, ctx.packs
-        dev = dP.device
-        dP = dP.contiguous()
-        grads = [None] * len(packs)
-        accs = []
-        for i, h in enumerate(ctx.holders):
-            if h is not None:
-                _fused.ACC_HITS += 1
-                accs.append(h.acc)
-            else:
-                grads[i] = torch.zeros_like(packs[i])
-                accs.append(grads[i])
-        need_dx, need_dh = bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1])
-        dX = torch.empty(N, F, dtype=_f32, device=dev) if need_dx else None
-        dH = torch.empty(N, C, dtype=_f32, device=dev) if need_dh else None
-        ws2 = torch.empty(scratch_size(N, F, C, K, S), dtype=_f32, device=dev)
-        if USE_C:
-            pad = [None] * (MAX_LAYERS + 1 - len(packs))
-            _lib.call("qmp_cheb_cell_bwd", N, F, C, K, S, int(cheb), g[3], g[4], g[5], g[2], dP, *packs, *pad, *accs, *pad, ws, ws2,
-                      int(need_dx), int(need_dh), dX, dH)
+        dX, dH, gp = _cheb_backward(ctx.state, dP.contiguous(), bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]))
+        return (dX, dH, None, None, None, None, None) + gp
+
+
+class ChebLstmCellFn(torch.autograd.Function):
+    """The whole cell step -- the eight stacks AND the gate epilogue (peepholes, LayerNorms, head input; csrc/lstm.cu) -- as one
+    autograd node: ``(O, H', C', head_in)`` from ``X, H, C`` (model/model.py:430-463).  ``flags = (norm_h, norm_c, norm_o,
+    want_head, eps)``; ``params`` [13, C] as ``GConvLSTM._gate_params`` packs them (through ``fused.shared_pack``: the gate kernel's
+    parameter gradients then accumulate in place over the timesteps)."""
+
+    @staticmethod
+    def forward(ctx, X, H, Cprev, params, concat, csr, mode, K, S, C, flags, *packs):
+        norm_h, norm_c, norm_o, want_head, eps = flags
+        P, ctx.state = _cheb_forward(X.contiguous(), H.contiguous(), csr, mode, K, S, C, packs)
+        N = P.shape[0]
+        dev = P.device
+        params = params.contiguous()
+        Cp = Cprev.contiguous() if Cprev is not None else None
+        gates = torch.empty(N, 4 * C, dtype=_f32, device=dev)
+        Craw, O, Hn, Cn = (torch.empty(N, C, dtype=_f32, device=dev) for _ in range(4))
+        head = torch.empty(N, C + 1, dtype=_f32, device=dev) if want_head else None
+        cc = concat.contiguous().reshape(-1) if (want_head and concat is not None) else None
+        if want_head and cc is None:
+            head.zero_()
+        _lib.call("qmp_lstm_gates_fwd", N, C, P, 4 * C, Cp, params, int(norm_h), int(norm_c), int(norm_o), float(eps),
+                  gates, Craw, O, Hn, Cn, head, C + 1, cc)
+        ctx.gate = (gates, Craw, Cp, params, getattr(params, "_qmp_acc", None), (int(norm_h), int(norm_c), int(norm_o), float(eps)))
+        return O, Hn, Cn, head
+
+    @staticmethod
+    def backward(ctx, dO, dH, dC, dHead):
+        gates, Craw, Cp, params, holder, (norm_h, norm_c, norm_o, eps) = ctx.gate
+        N, C = Craw.shape
+        dev = gates.device
+        c_ = lambda t: t.contiguous() if t is not None else None
+        dO, dH, dC, dHead = c_(dO), c_(dH), c_(dC), c_(dHead)
+        dP = torch.empty(N, 4 * C, dtype=_f32, device=dev)
+        dCprev = torch.empty(N, C, dtype=_f32, device=dev) if (Cp is not None and ctx.needs_input_grad[2]) else None
+        if holder is not None:
+            _fused.ACC_HITS += 1
+            dparams = holder.acc
         else:
-            _bwd_py(N, F, C, K, S, cheb, g, dP.view(-1), packs, accs, ws, ws2, need_dx, need_dh,
-                    dX.view(-1) if need_dx else None, dH.view(-1) if need_dh else None)
-        out = [_fused.hand_over(h, gr) if h is not None else gr for h, gr in zip(ctx.holders, grads)]
-        return (dX, dH, None, None, None, None, None) + tuple(out)
+            dparams = torch.zeros(13, C, dtype=_f32, device=dev)
+        _lib.call("qmp_lstm_gates_bwd", N, C, gates, Craw, Cp, params, norm_h, norm_c, norm_o, eps, dH, dC, dO, dHead,
+                  C + 1, dP, 4 * C, dCprev, dparams)
+        dconcat = dHead[:, C:].clone() if (dHead is not None and ctx.needs_input_grad[4]) else None
+        dX, dHin, gp = _cheb_backward(ctx.state, dP, bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]))
+        gparams = _fused.hand_over(holder, dparams) if holder is not None else dparams
+        return (dX, dHin, dCprev, gparams, dconcat, None, None, None, None, None, None) + gp

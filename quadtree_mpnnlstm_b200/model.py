@@ -18,7 +18,7 @@ import torch.nn.functional as F
 from .convs import (ChebConv, GATConv, GATv2Conv, GCNConv, MHTransformerConv, TransformerConv, cheb_basis,
                     pack_tconv)
 from . import fused as _fused
-from .cheb_cell import ChebCellFn, pack_linear_group
+from .cheb_cell import ChebCellFn, ChebLstmCellFn, pack_linear_group
 from .graph_csr import get_csr
 from .ops import LstmGatesFn, NodeLinearFn, SpmmFn, TConvFn, next_seed
 
@@ -136,7 +136,7 @@ class GConvLSTM(nn.Module):
             for nm in (norm_h, norm_c, norm_o):
                 rows += [nm.weight, nm.bias] if nm is not None else [one, zero]
             return _fused.RowsPackFn.apply(len(rows), *rows)     # == torch.stack(rows), copy-free parameter gradients
-        if self._fusable():         # consumed once per timestep by FusedGroupFn: gradients accumulate in place (fused._GradAccum)
+        if self._fusable() or self._cheb_cell():   # consumed once per timestep by one autograd node: gradients accumulate in place (fused._GradAccum)
             return self._cached(("gates", id(norm_h), id(norm_c), id(norm_o)), epoch, lambda: _fused.shared_pack(build()))
         return self._cached(("gates", id(norm_h), id(norm_c), id(norm_o)), epoch, build)
 
@@ -157,14 +157,9 @@ class GConvLSTM(nn.Module):
                                    lambda: pack_tconv(self._convs("x", l) + self._convs("h", l)))
                 cur = TConvFn.apply(cur, *pka, csr, False, p, seed(), False, None)
             return cur[:, :4 * C] + cur[:, 4 * C:]
-        if kind in ('GCNConv', 'ChebConv') and CHEB_CELL_FN:
+        if self._cheb_cell():
             # one autograd node for the eight stacks (cheb_cell.py): basis blocks, grouped GEMMs and the in-place weight gradients
-            mode = "gcn" if kind == 'GCNConv' else "cheb"
-            K = 1 if kind == 'GCNConv' else self.conv_x_i.convolutions[0].K
-            pk = lambda key, convs: self._cached((mode, "cell") + key, epoch,
-                                                 lambda: _fused.shared_pack(pack_linear_group(convs(), kind)))
-            packs = [pk(("x", 0), lambda: self._convs("x", 0)), pk(("h", 0), lambda: self._convs("h", 0))]
-            packs += [pk(("all", l), lambda l=l: self._convs("x", l) + self._convs("h", l)) for l in range(1, S)]
+            mode, K, packs = self._cheb_packs(epoch)
             return ChebCellFn.apply(X.contiguous(), H, csr, mode, K, S, C, *packs)
         if kind in ('GCNConv', 'ChebConv'):
             mode = "gcn" if kind == 'GCNConv' else "cheb"
@@ -202,6 +197,21 @@ class GConvLSTM(nn.Module):
         for g in GATES:
             outs.append(getattr(self, f"conv_x_{g}")(X, ei, ea) + getattr(self, f"conv_h_{g}")(H, ei, ea))
         return torch.cat(outs, dim=1)
+
+    # ---- ChebConv / GCNConv cell as one autograd node (cheb_cell.py) -----------------------------
+    def _cheb_cell(self):
+        from .cheb_cell import MAX_LAYERS
+        return CHEB_CELL_FN and self.convolution_type in ('GCNConv', 'ChebConv') and self.n_conv_layers <= MAX_LAYERS
+
+    def _cheb_packs(self, epoch):
+        kind, S = self.convolution_type, self.n_conv_layers
+        mode = "gcn" if kind == 'GCNConv' else "cheb"
+        K = 1 if kind == 'GCNConv' else self.conv_x_i.convolutions[0].K
+        pk = lambda key, convs: self._cached((mode, "cell") + key, epoch,
+                                             lambda: _fused.shared_pack(pack_linear_group(convs(), kind)))
+        packs = [pk(("x", 0), lambda: self._convs("x", 0)), pk(("h", 0), lambda: self._convs("h", 0))]
+        packs += [pk(("all", l), lambda l=l: self._convs("x", l) + self._convs("h", l)) for l in range(1, S)]
+        return mode, K, packs
 
     # ---- single-launch path (TransformerConv, hidden 32) ---------------------------------------
     def _fusable(self):
@@ -251,6 +261,11 @@ class GConvLSTM(nn.Module):
         if self._fusable():
             return self._fused_cell(X, H, C, csr, params, norm_h is not None, norm_c is not None, norm_o is not None,
                                     concat, want_head, eps, epoch)
+        if self._cheb_cell():
+            mode, K, packs = self._cheb_packs(epoch)
+            flags = (norm_h is not None, norm_c is not None, norm_o is not None, bool(want_head), float(eps))
+            return ChebLstmCellFn.apply(X.contiguous(), H, C, params, concat, csr, mode, K, self.n_conv_layers, self.out_channels,
+                                        flags, *packs)
         P = self._pre_activations(X, H, csr, epoch)
         return LstmGatesFn.apply(P, C, params, concat, norm_h is not None, norm_c is not None, norm_o is not None,
                                  want_head, eps)
