@@ -621,9 +621,10 @@ def run_gpu(args):
                 "roofline": roof}
         if world == 1 and not args.no_extras:
             extra = {}
-            for name, fn in (("dynamic_quadtree", lambda: extra_dynamic_quadtree(dev, mask, cube, clim, args.dropout, hbm)),
-                             ("cheb_dynamic", lambda: extra_cheb_dynamic(dev)),
-                             ("inference", lambda: extra_inference(dev, mask, cube, clim))):
+            # (the eager dynamic-mesh steps switch the allocator to expandable segments: they run after the captured rollouts)
+            for name, fn in (("inference", lambda: extra_inference(dev, mask, cube, clim)),
+                             ("dynamic_quadtree", lambda: extra_dynamic_quadtree(dev, mask, cube, clim, args.dropout, hbm)),
+                             ("cheb_dynamic", lambda: extra_cheb_dynamic(dev))):
                 try:
                     extra[name] = fn()
                 except Exception as exc:        # an extra must never take the headline line down with it

@@ -31,6 +31,8 @@ SIGNATURES = {
     "qmp_regrid": "ppiiiippifpppiippp",
     "qmp_cheb_cell_fwd": "iiiiii" + "p" * 16,
     "qmp_cheb_cell_bwd": "iiiiii" + "p" * 15 + "ii" + "ppp",
+    "qmp_cheb_stack_fwd": "i" * 11 + "p" * 13,
+    "qmp_cheb_stack_bwd": "i" * 11 + "p" * 14 + "i" + "pp",
     "qmp_adjacency_quadtree": "piippppppplppppp",
     "qmp_adjacency_pixelwise": "piippppppppp",
     "qmp_edge_attrs": "ppipppiiifipp",
@@ -86,7 +88,7 @@ SIGNATURES = {
 # kernels launched by one call of each entry point (for bench.py's gpu_launches accounting)
 KERNELS_PER_CALL = {
     "qmp_exclusive_scan_i32": 3, "qmp_frame_max_pad": 1, "qmp_quadtree_labels": 3, "qmp_mesh_pixels_from_rects": 5,
-    "qmp_mesh_pixelwise": 5, "qmp_segment_sum": 1, "qmp_quadtree_graph": 1, "qmp_quadtree_graph_export": 1, "qmp_gather_by_label": 1, "qmp_regrid": 1, "qmp_cheb_cell_fwd": 14, "qmp_cheb_cell_bwd": 21, "qmp_adjacency_quadtree": 8,
+    "qmp_mesh_pixelwise": 5, "qmp_segment_sum": 1, "qmp_quadtree_graph": 1, "qmp_quadtree_graph_export": 1, "qmp_gather_by_label": 1, "qmp_regrid": 1, "qmp_cheb_cell_fwd": 14, "qmp_cheb_cell_bwd": 21, "qmp_cheb_stack_fwd": 8, "qmp_cheb_stack_bwd": 12, "qmp_adjacency_quadtree": 8,
     "qmp_adjacency_pixelwise": 5, "qmp_edge_attrs": 1, "qmp_add_positional_encoding": 1,
     "qmp_csr_from_edge_index": 16, "qmp_gather_rows": 1, "qmp_gemm": 1, "qmp_gemm_tn_acc": 1, "qmp_attn_fwd": 1,
     "qmp_attn_bwd_target": 1, "qmp_attn_bwd_source": 1, "qmp_edge_norm": 2, "qmp_spmm": 1, "qmp_lstm_gates_fwd": 1,

@@ -290,3 +290,135 @@ class ChebLstmCellFn(torch.autograd.Function):
         dX, dHin, gp = _cheb_backward(ctx.state, dP, bool(ctx.needs_input_grad[0]), bool(ctx.needs_input_grad[1]))
         gparams = _fused.hand_over(holder, dparams) if holder is not None else dparams
         return (dX, dHin, dCprev, gparams, dconcat, None, None, None, None, None, None) + gp
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# A chain of ChebConv / GCNConv layers on one input (decoder head fc_out2(relu(fc_out1(.))), model/seq2seq.py:182-187)
+def stack_layout(N, K, w0, Ms):
+    """Offsets of T_l [N, K w_l] and out_l [N, M_l] (every layer but the last) in the forward workspace, widths, total."""
+    pos, w, T, out, ws_ = 0, w0, [], [], []
+    for l, M in enumerate(Ms):
+        ws_.append(w)
+        T.append(pos)
+        pos += N * K * w
+        out.append(pos)
+        if l + 1 < len(Ms):
+            pos += N * M
+        w = M
+    return T, out, ws_, pos
+
+
+def _stack_fwd_py(N, K, cheb, w0, Ms, relus, g, X, packs, biases, ws, out):
+    """The launch sequence of qmp_cheb_stack_fwd."""
+    T_off, o_off, widths, _ = stack_layout(N, K, w0, Ms)
+    inp = X
+    for l, M in enumerate(Ms):
+        w = widths[l]
+        ld = K * w
+        T = ws[T_off[l]:T_off[l] + N * ld]
+        if cheb:
+            T.view(N, ld)[:, :w].copy_(inp.view(-1)[:N * w].view(N, w))
+            if K > 1:
+                _spmm(g, cheb, False, N, w, T, ld, 1.0, 0.0, None, w, T[w:], ld)
+            for k in range(2, K):
+                _spmm(g, cheb, False, N, w, T[(k - 1) * w:], ld, 2.0, -1.0, T[(k - 2) * w:], ld, T[k * w:], ld)
+        else:
+            _spmm(g, cheb, False, N, w, inp, w, 1.0, 0.0, None, w, T, ld)
+        o = ws[o_off[l]:o_off[l] + N * M] if l + 1 < len(Ms) else out
+        gemm(T, packs[l], biases[l], o, N, M, ld, ld, ld + 1, M, relu=int(relus[l]))
+        inp = o
+
+
+def _stack_bwd_py(N, K, cheb, w0, Ms, relus, g, dOut, out_last, packs, accs, ws, ws2, need_dx, dX):
+    """The launch sequence of qmp_cheb_stack_bwd."""
+    T_off, o_off, widths, _ = stack_layout(N, K, w0, Ms)
+    L = len(Ms)
+    mx = max(max(Ms), max(widths))
+    gbuf = [ws2[:N * mx], ws2[N * mx:2 * N * mx]]
+    dT0 = ws2[2 * N * mx:]
+    gcur, flip = dOut, 0
+    for l in range(L - 1, -1, -1):
+        w, M = widths[l], Ms[l]
+        ld = K * w
+        T = ws[T_off[l]:T_off[l] + N * ld]
+        if relus[l]:
+            y = ws[o_off[l]:o_off[l] + N * M] if l + 1 < L else out_last
+            _lib.call("qmp_relu_mask_to", y, gcur, gbuf[flip], N * M)
+            gcur = gbuf[flip]
+            flip ^= 1
+        gemm_tn_acc(gcur, T, accs[l], N, M, ld + 1, M, ld, ld + 1, b_ones=1)
+        if l == 0 and not need_dx:
+            break
+        gemm(gcur, packs[l], None, dT0, N, ld, M, M, ld + 1, ld, b_is_kxm=1)
+        res = dX if l == 0 else gbuf[flip]
+        blocks = [dT0[k * w:] for k in range(K)]
+        if not cheb:
+            _spmm(g, cheb, True, N, w, blocks[0], ld, 1.0, 0.0, None, w, res, w)
+        else:
+            for k in range(K - 1, 1, -1):
+                _spmm(g, cheb, True, N, w, blocks[k], ld, 2.0, 1.0, blocks[k - 1], ld, blocks[k - 1], ld)
+                torch.as_strided(blocks[k - 2], (N, w), (ld, 1)).sub_(torch.as_strided(blocks[k], (N, w), (ld, 1)))
+            if K > 1:
+                _spmm(g, cheb, True, N, w, blocks[1], ld, 1.0, 1.0, blocks[0], ld, res, w)
+            else:
+                res[:N * w].view(N, w).copy_(torch.as_strided(blocks[0], (N, w), (ld, 1)))
+        gcur = res
+        flip ^= 1
+
+
+class ChebStackFn(torch.autograd.Function):
+    """``x -> conv_L(...relu?(conv_1(x)))`` for up to three ChebConv / GCNConv layers as one autograd node and one library call
+    each way (``qmp_cheb_stack_fwd`` / ``_bwd``).  ``packs[l]``: ``[1, M_l, K w_l + 1]`` (``pack_linear_group([conv], kind)``)."""
+
+    @staticmethod
+    def forward(ctx, x, csr, mode, K, relus, *packs):
+        x = x.contiguous()
+        N, w0 = x.shape
+        cheb = mode == "cheb"
+        L = len(packs)
+        assert 1 <= L <= MAX_LAYERS and len(relus) == L
+        Ms = [int(p.shape[1]) for p in packs]
+        biases = [bias_of(p) for p in packs]
+        *_, n_ws = stack_layout(N, K, w0, Ms)
+        ws = torch.empty(max(n_ws, 1), dtype=_f32, device=x.device)
+        out = torch.empty(N, Ms[-1], dtype=_f32, device=x.device)
+        g = (csr.in_ptr, csr.in_src, csr.norm(mode), csr.out_ptr, csr.out_dst, csr.out_kin)
+        pad = [None] * (MAX_LAYERS - L)
+        if USE_C:
+            _lib.call("qmp_cheb_stack_fwd", N, K, int(cheb), L, w0, *(Ms + [0] * (MAX_LAYERS - L)),
+                      *([int(r) for r in relus] + [0] * (MAX_LAYERS - L)), g[0], g[1], g[2], x, *packs, *pad, *biases, *pad, ws, out)
+        else:
+            _stack_fwd_py(N, K, cheb, w0, Ms, relus, g, x.view(-1), packs, biases, ws, out.view(-1))
+        ctx.state = (g, (N, K, cheb, w0, Ms, tuple(relus)), ws, out, packs, [getattr(p, "_qmp_acc", None) for p in packs], csr)
+        return out
+
+    @staticmethod
+    def backward(ctx, dOut):
+        g, (N, K, cheb, w0, Ms, relus), ws, out, packs, holders, _ = ctx.state
+        dev = dOut.device
+        dOut = dOut.contiguous()
+        L = len(packs)
+        grads = [None] * L
+        accs = []
+        for i, h in enumerate(holders):
+            if h is not None:
+                _fused.ACC_HITS += 1
+                accs.append(h.acc)
+            else:
+                grads[i] = torch.zeros_like(packs[i])
+                accs.append(grads[i])
+        need_dx = bool(ctx.needs_input_grad[0])
+        dX = torch.empty(N, w0, dtype=_f32, device=dev) if need_dx else None
+        widths = stack_layout(N, K, w0, Ms)[2]
+        mx = max(max(Ms), max(widths))
+        ws2 = torch.empty(2 * N * mx + N * K * max(widths), dtype=_f32, device=dev)
+        pad = [None] * (MAX_LAYERS - L)
+        if USE_C:
+            _lib.call("qmp_cheb_stack_bwd", N, K, int(cheb), L, w0, *(Ms + [0] * (MAX_LAYERS - L)),
+                      *([int(r) for r in relus] + [0] * (MAX_LAYERS - L)), g[3], g[4], g[5], g[2], dOut, out, *packs, *pad, *accs, *pad,
+                      ws, ws2, int(need_dx), dX)
+        else:
+            _stack_bwd_py(N, K, cheb, w0, Ms, relus, g, dOut.view(-1), out.view(-1), packs, accs, ws, ws2, need_dx,
+                          dX.view(-1) if need_dx else None)
+        gp = [_fused.hand_over(h, gr) if h is not None else gr for h, gr in zip(holders, grads)]
+        return (dX, None, None, None, None) + tuple(gp)

@@ -36,6 +36,8 @@ REPLACES = {  # entry point -> reference interface it stands in for
     "qmp_gather_by_label": "model/graph_functions.py:451-468 unflatten (and the backward of flatten)",
     "qmp_cheb_cell_fwd": "model/model.py:430-447 GConvLSTM gate pre-activations with ChebConv / GCNConv stacks (GraphConv :60-97; PyG ChebConv / GCNConv forward) -- the launch sequence of one cell step issued from C++",
     "qmp_cheb_cell_bwd": "autograd of the same (weight / bias gradients accumulated in place, dX, dH)",
+    "qmp_cheb_stack_fwd": "model/seq2seq.py:182-187 decoder head fc_out2(relu(fc_out1(.))) and model/model.py:60-97 GraphConv with ChebConv / GCNConv layers -- the launch sequence of the chain issued from C++",
+    "qmp_cheb_stack_bwd": "autograd of the same",
     "qmp_regrid": "model/seq2seq.py:434-491 do_remesh: unflatten (graph_functions.py:451-468) + flatten (:391-419) of a recurrent state as one pass, and their backward",
     "qmp_adjacency_quadtree": "model/graph_functions.py:261-345 get_adj",
     "qmp_adjacency_pixelwise": "model/graph_functions.py:471-493 get_adj_pixelwise",

@@ -197,3 +197,104 @@ QMP_API int qmp_cheb_cell_bwd(int N, int F, int C, int K, int S, int cheb, const
     QMP_LAUNCH_CHECK("qmp_cheb_cell_bwd");
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// A chain of up to three ChebConv / GCNConv layers on one input, optional relu after each: the decoder head of a ChebConv / GCNConv
+// model (fc_out2(relu(fc_out1(.))), model/seq2seq.py:182-187) and GraphConv stacks (model/model.py:60-97).  Same building blocks
+// and pack format as the cell (G = 1: pack_l [1, M_l, K w_l + 1], w_0 = input width, w_(l+1) = M_l).
+// ws (saved for the backward pass): per layer T_l [N, K w_l], then out_l [N, M_l] for every layer but the last.
+QMP_API int qmp_relu_mask_to(const float* y, const float* g, float* out, long long n, void* stream);
+
+namespace qmp {
+struct CsLayout {
+    long long T[3], out[3], total;
+    int w[3], M[3];
+    CsLayout(int N, int K, int L, int w0, int M0, int M1, int M2) {
+        M[0] = M0; M[1] = M1; M[2] = M2;
+        long long pos = 0;
+        int wl = w0;
+        for (int l = 0; l < L; ++l) {
+            w[l] = wl;
+            T[l] = pos; pos += (long long)N * K * wl;
+            out[l] = pos;
+            if (l + 1 < L) pos += (long long)N * M[l];
+            wl = M[l];
+        }
+        total = pos;
+    }
+};
+}  // namespace qmp
+
+QMP_API int qmp_cheb_stack_fwd(int N, int K, int cheb, int L, int w0, int M0, int M1, int M2, int relu0, int relu1, int relu2,
+                               const int* in_ptr, const int* in_src, const float* val, const float* X, const float* pack0,
+                               const float* pack1, const float* pack2, const float* bias0, const float* bias1, const float* bias2,
+                               float* ws, float* out, void* stream) {
+    QMP_REQUIRE(L >= 1 && L <= 3 && K >= 1 && K <= 8 && (cheb || K == 1), "qmp_cheb_stack_fwd: 1 <= L <= 3, 1 <= K <= 8, GCN has K = 1");
+    if (N <= 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* packs[3] = {pack0, pack1, pack2};
+    const float* biases[3] = {bias0, bias1, bias2};
+    const int relus[3] = {relu0, relu1, relu2};
+    const CsLayout lay(N, K, L, w0, M0, M1, M2);
+    const float* inp = X;
+    for (int l = 0; l < L; ++l) {
+        const int w = lay.w[l], ld = K * w, M = lay.M[l];
+        float* T = ws + lay.T[l];
+        if (cheb) {
+            cc_rows(0, N, w, inp, w, nullptr, 0, T, ld, st);
+            if (K > 1) CC_CHECK(qmp_spmm(N, w, in_ptr, in_src, nullptr, val, T, ld, 1.f, 0.f, nullptr, w, T + w, ld, stream));
+            for (int k = 2; k < K; ++k)
+                CC_CHECK(qmp_spmm(N, w, in_ptr, in_src, nullptr, val, T + (k - 1) * w, ld, 2.f, -1.f, T + (k - 2) * w, ld, T + k * w, ld, stream));
+        } else {
+            CC_CHECK(qmp_spmm(N, w, in_ptr, in_src, nullptr, val, inp, w, 1.f, 0.f, nullptr, w, T, ld, stream));
+        }
+        float* o = (l + 1 < L) ? ws + lay.out[l] : out;
+        CC_CHECK(qmp_gemm(T, packs[l], biases[l], o, N, M, ld, ld, ld + 1, M, 0, 0, 0, 0, 1, 0, 0, relus[l], stream));
+        inp = o;
+    }
+    QMP_LAUNCH_CHECK("qmp_cheb_stack_fwd");
+    return 0;
+}
+
+// accN += weight | bias gradients; dX [N, w0] when asked for.  out_last: the forward result (relu mask of the last layer).
+// ws2: scratch of 2 N max(M) + N K max(w) floats.
+QMP_API int qmp_cheb_stack_bwd(int N, int K, int cheb, int L, int w0, int M0, int M1, int M2, int relu0, int relu1, int relu2,
+                               const int* out_ptr, const int* out_dst, const int* out_kin, const float* val, const float* dOut,
+                               const float* out_last, const float* pack0, const float* pack1, const float* pack2, float* acc0,
+                               float* acc1, float* acc2, const float* ws, float* ws2, int need_dx, float* dX, void* stream) {
+    QMP_REQUIRE(L >= 1 && L <= 3 && K >= 1 && K <= 8 && (cheb || K == 1), "qmp_cheb_stack_bwd: 1 <= L <= 3, 1 <= K <= 8, GCN has K = 1");
+    if (N <= 0) return 0;
+    const float* packs[3] = {pack0, pack1, pack2};
+    float* accs[3] = {acc0, acc1, acc2};
+    const int relus[3] = {relu0, relu1, relu2};
+    const CsLayout lay(N, K, L, w0, M0, M1, M2);
+    const CcGraph g{out_ptr, out_dst, out_kin, val};
+    int maxM = 0, maxw = 0;
+    for (int l = 0; l < L; ++l) { maxM = lay.M[l] > maxM ? lay.M[l] : maxM; maxw = lay.w[l] > maxw ? lay.w[l] : maxw; }
+    maxM = maxM > maxw ? maxM : maxw;
+    float* gbuf[2] = {ws2, ws2 + (long long)N * maxM};
+    float* dT0 = ws2 + 2LL * N * maxM;
+    const float* gcur = dOut;
+    int flip = 0;
+    for (int l = L - 1; l >= 0; --l) {
+        const int w = lay.w[l], ld = K * w, M = lay.M[l];
+        const float* T = ws + lay.T[l];
+        if (relus[l]) {
+            const float* y = (l + 1 < L) ? ws + lay.out[l] : out_last;
+            CC_CHECK(qmp_relu_mask_to(y, gcur, gbuf[flip], (long long)N * M, stream));
+            gcur = gbuf[flip];
+            flip ^= 1;
+        }
+        CC_CHECK(qmp_gemm_tn_acc(gcur, T, accs[l], N, M, ld + 1, M, ld, ld + 1, 0, 0, 0, 1, 1, stream));
+        if (l == 0 && !need_dx) break;
+        CC_CHECK(qmp_gemm(gcur, packs[l], nullptr, dT0, N, ld, M, M, ld + 1, ld, 0, 0, 0, 0, 1, 1, 0, 0, stream));
+        float* dT[8];
+        for (int k = 0; k < K; ++k) dT[k] = dT0 + k * w;
+        float* res = (l == 0) ? dX : gbuf[flip];
+        CC_CHECK(cc_basis_bwd(g, cheb != 0, K, N, w, dT, ld, res, stream));
+        gcur = res;
+        flip ^= 1;
+    }
+    QMP_LAUNCH_CHECK("qmp_cheb_stack_bwd");
+    return 0;
+}

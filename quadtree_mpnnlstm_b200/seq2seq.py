@@ -10,6 +10,7 @@ is seeded from the top layer's state; the decoder always uses one conv per stack
 """
 from __future__ import annotations
 
+import os
 import random
 
 import numpy as np
@@ -23,6 +24,13 @@ from .graph_functions import Graph, Mesh, flatten, image_to_graph, regrid, unfla
 from .model import CONVOLUTION_KWARGS, CONVOLUTIONS, GConvLSTM, new_epoch
 from .ops import HeadFinishFn, NodeLinearFn, SpmmFn, TConvFn, next_seed
 from .convs import cheb_basis, pack_tconv
+from .cheb_cell import ChebStackFn, pack_linear_group
+from . import model as _model
+
+# ChebConv / GCNConv decoder head as one autograd node (cheb_cell.ChebStackFn).  OFF by default -- measured: no host time gained
+# on the configs[0]-like sample (32.5 vs 32.3 ms) and its two ~2 MB workspaces per forecast step fragment the caching allocator's
+# 20 MB segments next to the cell's ~9 MB workspaces (51 cudaMalloc per sample, 32 -> 41 ... 290 ms without expandable segments).
+CHEB_STACK_FN = os.environ.get("QMP_CHEB_STACK_FN", "0") == "1"
 from .utils import add_positional_encoding
 
 
@@ -189,6 +197,12 @@ class Decoder(torch.nn.Module):
             pk2 = self._cached("fc2", epoch, lambda: pack_tconv([self.fc_out2]))
             h1 = TConvFn.apply(head, *pk1, csr, True, p, sd(), True, None)
             return TConvFn.apply(h1, *pk2, csr, True, p, sd(), False, None)
+        if kind in ('GCNConv', 'ChebConv') and _model.CHEB_CELL_FN and CHEB_STACK_FN:
+            # fc_out2(relu(fc_out1(.))) as one autograd node and one library call each way (cheb_cell.ChebStackFn)
+            mode = "gcn" if kind == 'GCNConv' else "cheb"
+            K = 1 if kind == 'GCNConv' else self.fc_out1.K
+            pk = lambda key, conv: self._cached(key, epoch, lambda: _fused.shared_pack(pack_linear_group([conv], kind)))
+            return ChebStackFn.apply(head, csr, mode, K, (True, False), pk("cs1", self.fc_out1), pk("cs2", self.fc_out2))
         if kind in ('GCNConv', 'ChebConv'):
             def lin(conv, z, relu):
                 if kind == 'GCNConv':

@@ -388,6 +388,20 @@ def qmp_cheb_cell_bwd(N, F, C, K, S, cheb, out_ptr, out_dst, out_kin, val, dP, p
                bool(need_dx), bool(need_dh), dX.view(-1) if dX is not None else None, dH.view(-1) if dH is not None else None)
 
 
+def qmp_cheb_stack_fwd(N, K, cheb, L, w0, M0, M1, M2, r0, r1, r2, in_ptr, in_src, val, X, p0, p1, p2, b0, b1, b2, ws, out):
+    from quadtree_mpnnlstm_b200 import cheb_cell as CC
+    CC._stack_fwd_py(N, K, bool(cheb), w0, [M0, M1, M2][:L], [r0, r1, r2][:L], (in_ptr, in_src, val, None, None, None), X.reshape(-1),
+                     [p0, p1, p2][:L], [b0, b1, b2][:L], ws, out.view(-1))
+
+
+def qmp_cheb_stack_bwd(N, K, cheb, L, w0, M0, M1, M2, r0, r1, r2, out_ptr, out_dst, out_kin, val, dOut, out_last, p0, p1, p2, a0, a1,
+                       a2, ws, ws2, need_dx, dX):
+    from quadtree_mpnnlstm_b200 import cheb_cell as CC
+    CC._stack_bwd_py(N, K, bool(cheb), w0, [M0, M1, M2][:L], [r0, r1, r2][:L], (None, None, val, out_ptr, out_dst, out_kin),
+                     dOut.reshape(-1), out_last.reshape(-1), [p0, p1, p2][:L], [a0, a1, a2][:L], ws, ws2, bool(need_dx),
+                     dX.view(-1) if dX is not None else None)
+
+
 # ------------------------------------------------------------------------------------------ LSTM gates
 def _ln(x, gamma, beta, eps):
     mu = x.mean(-1, keepdim=True)

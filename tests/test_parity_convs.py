@@ -689,3 +689,46 @@ def test_cheb_cell_c_sequence_equals_python_sequence_and_modular_path(be, conv, 
         assert rel_err(results["c"][2][k], results["modular"][2][k]) < 1e-4, k
     for a, b in zip(results["c"][0] + results["c"][1], results["modular"][0] + results["modular"][1]):
         assert rel_err(a, b) < 1e-4
+
+
+@pytest.mark.parametrize("conv", ["ChebConv", "GCNConv"])
+def test_cheb_head_chain_c_sequence_equals_python_sequence_and_modular_path(be, conv, monkeypatch):
+    """cheb_cell.ChebStackFn (decoder head fc_out2(relu(fc_out1(.))), model/seq2seq.py:182-187): the chain issued from C++
+    (qmp_cheb_stack_fwd / _bwd) against the same sequence from Python (bit for bit) and against the modular path."""
+    import quadtree_mpnnlstm_b200.cheb_cell as CC
+    import quadtree_mpnnlstm_b200.convs as CV
+    from quadtree_mpnnlstm_b200.graph_csr import get_csr
+    from quadtree_mpnnlstm_b200.ops import NodeLinearFn, SpmmFn
+    ei, ea, n = _graph(6, use_edge_attrs=False)
+    kind, mode, K = conv, ("gcn" if conv == "GCNConv" else "cheb"), (1 if conv == "GCNConv" else 3)
+    torch.manual_seed(9)
+    mk = (lambda i, o: CV.GCNConv(i, o)) if conv == "GCNConv" else (lambda i, o: CV.ChebConv(i, o, K=3))
+    c1, c2 = be.dev(mk(17, 16)), be.dev(mk(16, 1))
+    x0 = torch.randn(n, 17)
+    csr = get_csr(be.dev(ei), None, n)
+    res = {}
+    for path in ("c", "py", "modular"):
+        for p in list(c1.parameters()) + list(c2.parameters()):
+            p.grad = None
+        x = be.dev(x0.clone()).requires_grad_(True)
+        if path == "modular":
+            def lin(cv, z, relu):
+                if conv == "GCNConv":
+                    t, W = SpmmFn.apply(z, None, csr, "gcn", 1.0, 0.0), cv.lin.weight.unsqueeze(0)
+                else:
+                    t = torch.cat(CV.cheb_basis(z, csr, cv.K), dim=1)
+                    W = torch.cat([l.weight for l in cv.lins], dim=1).unsqueeze(0)
+                o = NodeLinearFn.apply(t, W, cv.bias.unsqueeze(0), True)
+                return torch.relu(o) if relu else o
+            y = lin(c2, lin(c1, x, True), False)
+        else:
+            monkeypatch.setattr(CC, "USE_C", path == "c")
+            y = CC.ChebStackFn.apply(x, csr, mode, K, (True, False), CC.pack_linear_group([c1], kind), CC.pack_linear_group([c2], kind))
+        (y * y).sum().backward()
+        res[path] = [y.detach().cpu(), x.grad.cpu()] + [p.grad.cpu() for p in list(c1.parameters()) + list(c2.parameters())]
+    for a, b in zip(res["c"][:2], res["py"][:2]):
+        assert torch.equal(a, b), "C++ and Python launch sequences differ"
+    for a, b in zip(res["c"], res["py"]):
+        assert rel_err(a, b) < 1e-5
+    for a, b in zip(res["c"], res["modular"]):
+        assert rel_err(a, b) < 1e-4
