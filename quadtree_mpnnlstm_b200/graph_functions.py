@@ -184,6 +184,26 @@ class _Pool(torch.autograd.Function):
         return dimg, None
 
 
+class _PooledByBuild(torch.autograd.Function):
+    """``data`` [B, N, c + 1] = (pooled ``img`` | node size) exactly as qmp_quadtree_graph wrote it, made differentiable in
+    ``img``: the forward is the identity on the build's output (bit-identical to ``cat([_Pool(img), size])``), the backward is
+    ``_Pool``'s (gather by label with the division); the size column carries no gradient."""
+
+    @staticmethod
+    def forward(ctx, img, data, mesh):
+        ctx.mesh, ctx.shape = mesh, tuple(img.shape)
+        return data.view_as(data)
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, C = ctx.shape
+        mesh = ctx.mesh
+        gc = g[..., :C].contiguous()
+        dimg = torch.empty(B, H, W, C, dtype=torch.float32, device=g.device)
+        _lib.call("qmp_gather_by_label", gc, B, H * W, C, mesh.n_nodes, mesh.labels, mesh.npix, 1, 0.0, dimg)
+        return dimg, None, None
+
+
 class _Unpool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, data, mesh, fill):
@@ -437,9 +457,8 @@ def _quadtree_graph_one_launch(img, crit, m8, h8, S, cond, thresh, use_edge_attr
     if two:
         edge_attrs, edge_attr_in = edge_attrs.view(E, 2), edge_attr_in.view(E, 2)
     mesh = Mesh(labels, N, npix, pix_ptr, pix_idx, (h, w), "quadtree")
-    if img.requires_grad:            # differentiable pooling (seq2seq.py:440-476 regrids state)
-        cell_sizes = (npix / ((max_grid_size / 2) ** 2)).reshape(1, N, 1).expand(n, N, 1)   # :665-666
-        data = torch.cat([_Pool.apply(img, mesh), cell_sizes], -1)
+    if img.requires_grad:            # differentiable pooling (seq2seq.py:440-476 regrids state): the build already pooled the
+        data = _PooledByBuild.apply(img, data, mesh)      # frames (same summation order as _Pool); only the backward is added
     edge_index._qmp_trusted = True
     graph_csr.register(graph_csr.GraphCSR.from_parts(edge_index, edge_attrs, N, src32, dst32, in_ptr, in_src, in_eid, out_ptr, out_dst,
                                                      out_kin, edge_attr_in))
