@@ -320,6 +320,7 @@ class Seq2Seq(torch.nn.Module):
     def unroll_output(self, unroll_steps, y, concat_layers=None, teacher_forcing_ratio=0.5, mask=None,
                       high_interest_region=None, remesh_every=1):
         """Decoder rollout (seq2seq.py:339-398)."""
+        self._unpooled = {}
         outputs = []
         output_mappings = []
         g = self.graph
@@ -379,6 +380,9 @@ class Seq2Seq(torch.nn.Module):
         g = self.graph
         image_shape = g.image_shape
         data_img = unflatten(data, g.mapping, image_shape)
+        # (the loss of a dynamic-mesh training step unpools this very output on this very mesh: train.TrainStep reuses the image)
+        if getattr(self, "_unpooled", None) is not None:
+            self._unpooled[id(data)] = (data, g.mapping, data_img)
         if teacher_force:
             gs = self._image_to_graph(add_positional_encoding(teacher_input.float()), mask, high_interest_region)
         else:

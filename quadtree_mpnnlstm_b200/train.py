@@ -42,15 +42,18 @@ def _expandable_segments():
     the caching allocator's fixed 20 MB segments fragment under that pattern and every miss is a device-synchronising
     ``cudaMalloc`` (measured: 51 per 20-frame sample, 31 -> 85 ... 290 ms, when one more ~2 MB workspace per step joined the mix).
     Expandable segments (one growing virtual range per stream, physical pages mapped on demand) take the misses away:
-    configs[2] 120 -> 112 ms per sample.  Process-wide allocator setting, switched on once by the first eager ``TrainStep``;
-    ``QMP_EXPANDABLE_SEGMENTS=0`` leaves the allocator alone."""
-    if _expandable_done[0] or os.environ.get("QMP_EXPANDABLE_SEGMENTS", "1") == "0":
+    configs[2] 120 -> 112 ms per sample with ``PYTORCH_CUDA_ALLOC_CONF=expandable_segments:True`` from process start.  Switching
+    an allocator that already holds fixed segments is another matter -- inside ``bench.py`` (after the captured static-mesh step
+    and the rollouts) the switch made the dynamic-mesh sample bimodal, 105 or 140 ... 200 ms -- so the first eager ``TrainStep`` only
+    does it when asked to: ``QMP_EXPANDABLE_SEGMENTS=1``."""
+    if _expandable_done[0] or os.environ.get("QMP_EXPANDABLE_SEGMENTS", "0") != "1":
         return
     _expandable_done[0] = True
     if "expandable_segments" in os.environ.get("PYTORCH_CUDA_ALLOC_CONF", ""):
         return
     try:
-        torch.cuda.memory._set_allocator_settings("expandable_segments:True")
+        setter = getattr(torch._C, "_accelerator_setAllocatorSettings", None) or torch.cuda.memory._set_allocator_settings
+        setter("expandable_segments:True")
     except Exception:                      # an allocator backend without the setting: keep going
         pass
 
@@ -103,7 +106,14 @@ class TrainStep:
             # dynamic quadtree: the mesh differs per forecast step -> unpool every step and compare the unmasked pixels,
             # as the reference trainer does (model/mpnnlstm.py:243-246)
             shape = tuple(x.shape[1:3])
-            y_hat = torch.stack([unflatten(out[t], maps[t], shape, self.mask) for t in range(len(out))])
+            done = getattr(self.model, "_unpooled", {})         # images the decoder already unpooled while remeshing (do_remesh)
+
+            def image(t):
+                hit = done.get(id(out[t]))
+                if hit is not None and hit[0] is out[t] and hit[1] is maps[t] and tuple(hit[2].shape[:2]) == shape:
+                    return hit[2]
+                return unflatten(out[t], maps[t], shape, self.mask)
+            y_hat = torch.stack([image(t) for t in range(len(out))])
             keep = self._keep_mask(x.device)
             loss = torch.nn.functional.mse_loss(y_hat[:, keep], y[:, keep])
         loss.backward()
