@@ -626,6 +626,10 @@ def run_gpu(args):
                 "roofline": roof}
         if world == 1 and not args.no_extras:
             extra = {}
+            dev_samples = hs = None          # the timed loop's inputs: release them (and the allocator's cache) before the extras
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
             # (the eager dynamic-mesh steps switch the allocator to expandable segments: they run after the captured rollouts)
             for name, fn in (("inference", lambda: extra_inference(dev, mask, cube, clim)),
                              ("dynamic_quadtree", lambda: extra_dynamic_quadtree(dev, mask, cube, clim, args.dropout, hbm)),
