@@ -393,7 +393,7 @@ class Seq2Seq(torch.nn.Module):
         g.pyg.edge_index = gs['edge_index']
         g.pyg.edge_attr = gs['edge_attrs']
         g.pyg.x = gs['data'].squeeze(0)
-        g.concat_layers = gs['data'][:, :, [0]]
+        g.concat_layers = gs['data'][:, :, :1]             # (a view: indexing with [0] costs an index tensor, a host-to-device copy and a gather)
         g.mapping = gs['mapping']
         g.n_pixels_per_node = gs['n_pixels_per_node']
         g.image_shape = image_shape
